@@ -1,0 +1,256 @@
+"""Seeded, batched restatement of the reference's per-problem sampling.
+
+The reference draws every OCP's data with the unseeded `random` module inside forked workers
+(SURVEY §9), so no run is repeatable.  Here the same distributions are drawn from an explicit seed
+as *arrays* (one row per problem) so that the CUDA engine, the CPU oracle and -- when it is
+available -- acados all consume identical inputs.
+
+Follows (file:line relative to /root/reference):
+  sample_vboc      VBOC/triplependulum_vboc.py:33-103, VBOC/doublependulum_vboc.py:33-99
+  sample_testdata  triplependulum_testdata.py:15-38, doublependulum_testdata.py:16-37,
+                   pendulum_testdata.py:11-27
+  sample_al        AL/triplependulum_al.py:115-123 (uniform pool; velocities 5 % beyond the box)
+
+All arrays are reference-shaped: VBOC states are [q(n), v(n), dt], AL states [q(n), v(n)].
+"""
+import math
+
+import numpy as np
+
+
+class Model:
+    """Constants of the reference models (constructor blocks of the *_class_*.py files)."""
+
+    def __init__(self, n):
+        self.n = n
+        self.thetamax = np.pi / 4 + np.pi
+        self.thetamin = -np.pi / 4 + np.pi
+        self.dthetamax = 10.0
+        if n == 1:
+            # VBOC/pendulum_class_vboc.py:14-17, :64-67
+            self.m, self.g, self.d, self.b = 0.5, 9.81, 0.3, 0.01
+            self.Fmax = 3.0
+            self.umax = 3.0
+            self.N0 = 50
+        else:
+            # VBOC/doublependulum_class_vboc.py:14-18, :114-117; VBOC/triplependulum_class_vboc.py:15-21, :90-93
+            self.m1 = self.m2 = self.m3 = 0.4
+            self.l1 = self.l2 = self.l3 = 0.8
+            self.g = 9.81
+            self.Cmax = 10.0
+            self.umax = 10.0
+            self.N0 = 100
+
+    def gravity_comp(self, q):
+        """Torques holding the arm still at positions q (reference VBOC/doublependulum_vboc.py:84;
+        generalised to n links: u_i = g l_i (sum_{k>=i} m_k) sin q_i)."""
+        q = np.asarray(q, dtype=float)
+        n = self.n
+        if n == 1:
+            return -self.m * self.g * self.d * np.sin(q)
+        mu = np.array([0.4 * (n - i) for i in range(n)])
+        return self.g * 0.8 * mu * np.sin(q)
+
+
+def _rng(seed):
+    return np.random.Generator(np.random.Philox(key=int(seed)))
+
+
+def expand_guess(x_rows, u_rows, N):
+    """Reference `OCP_solve` semantics (VBOC/triplependulum_class_vboc.py:161-186): stages 0..N-1 take
+    guess rows 0..N-1, stage N takes the LAST row of the state guess (the guesses the drivers pass have
+    N or N+1 rows)."""
+    x_rows = np.asarray(x_rows, dtype=float)
+    u_rows = np.asarray(u_rows, dtype=float)
+    x = np.empty((N + 1, x_rows.shape[1]))
+    x[:N] = x_rows[:N]
+    x[N] = x_rows[-1]
+    return x, np.array(u_rows[:N], dtype=float)
+
+
+def sample_vboc(n, batch, seed, N=None, dt_sym=1e-2, tol=1e-3):
+    """Batched restatement of the sampling block of `data_generation` (n = 2 or 3).
+
+    Returns a dict of arrays (leading dim = batch) with the reference-shaped OCP data and the
+    bookkeeping the state machine needs (joint_sel, vel_sel).  x_guess is already expanded to N+1 rows.
+    """
+    assert n in (2, 3)
+    mdl = Model(n)
+    N = N or mdl.N0
+    eps = 10 * tol
+    q_min, q_max, v_max, tau_max = mdl.thetamin, mdl.thetamax, mdl.dthetamax, mdl.umax
+    v_min = -v_max
+    rng = _rng(seed)
+    R = rng.random((batch, 4 * n + 2))  # fixed column count => batch-size independent streams
+    c = 0
+    joint_sel = np.minimum((R[:, c] * n).astype(int), n - 1); c += 1
+    vel_sel = np.where(R[:, c] < 0.5, -1.0, 1.0); c += 1
+    ran = np.empty((batch, n))
+    ran[:, 0] = vel_sel * R[:, c]; c += 1
+    for j in range(1, n):
+        sgn = np.where(R[:, c] < 0.5, -1.0, 1.0); c += 1
+        ran[:, j] = sgn * R[:, c]; c += 1
+    ran /= np.linalg.norm(ran, axis=1, keepdims=True)
+    # place ran1 on the selected joint, keep the others in order (triplependulum_vboc.py:49-54)
+    p = np.zeros((batch, n + 1))
+    for b_sel in range(n):
+        m = joint_sel == b_sel
+        others = [j for j in range(n) if j != b_sel]
+        p[m, b_sel] = ran[m, 0]
+        for t, j in enumerate(others):
+            p[m, j] = ran[m, 1 + t]
+    q_init = np.empty((batch, n))
+    for j in range(n):
+        q = q_min + R[:, c] * (q_max - q_min); c += 1
+        q = np.where(q > q_max - eps, q - eps, q)
+        q = np.where(q < q_min + eps, q + eps, q)
+        q_init[:, j] = q
+    q_init_sel = np.where(vel_sel < 0, q_min, q_max)
+    q_fin_sel = np.where(vel_sel < 0, q_max, q_min)
+    rows = np.arange(batch)
+
+    nx = 2 * n + 1
+    lbx0 = np.empty((batch, nx)); ubx0 = np.empty((batch, nx))
+    lbx0[:, :n] = q_init; ubx0[:, :n] = q_init
+    lbx0[:, n:2 * n] = v_min; ubx0[:, n:2 * n] = v_max
+    lbx0[:, 2 * n] = dt_sym; ubx0[:, 2 * n] = dt_sym
+    fixed = np.where(vel_sel < 0, q_min + eps, q_max - eps)
+    lbx0[rows, joint_sel] = fixed; ubx0[rows, joint_sel] = fixed
+
+    # guess: N rows, linspace(0,1,N), then stage N repeats the last row
+    tau = np.linspace(0, 1, N)
+    xg = np.zeros((batch, N + 1, nx))
+    xg[:, :N, :n] = q_init[:, None, :]
+    xg[:, :N, 2 * n] = dt_sym
+    qs = (1 - tau)[None, :] * q_init_sel[:, None] + tau[None, :] * q_fin_sel[:, None]
+    vs = 2 * (1 - tau)[None, :] * (q_fin_sel - q_init_sel)[:, None]
+    for b_sel in range(n):
+        m = joint_sel == b_sel
+        xg[m, :N, b_sel] = qs[m]
+        xg[m, :N, n + b_sel] = vs[m]
+    xg[:, N] = xg[:, N - 1]
+    ug = np.zeros((batch, N, n))
+    if n == 2:
+        # gravity-compensation torques along the guess (doublependulum_vboc.py:84)
+        ug[:, :, 0] = mdl.g * mdl.l1 * (mdl.m1 + mdl.m2) * np.sin(xg[:, :N, 0])
+        ug[:, :, 1] = mdl.g * mdl.l2 * mdl.m2 * np.sin(xg[:, :N, 1])
+
+    def rep(v):
+        return np.tile(np.asarray(v, dtype=float), (batch, 1))
+
+    out = dict(
+        n=n, family="vboc", N=np.full(batch, N, dtype=np.int32), x_guess=xg, u_guess=ug, p=p,
+        lbx0=lbx0, ubx0=ubx0,
+        lbx=rep([q_min] * n + [v_min] * n + [dt_sym]), ubx=rep([q_max] * n + [v_max] * n + [dt_sym]),
+        lbxN=rep([q_min] * n + [0.0] * n + [dt_sym]), ubxN=rep([q_max] * n + [0.0] * n + [dt_sym]),
+        lbu=rep([-tau_max] * n), ubu=rep([tau_max] * n),
+        joint_sel=joint_sel, vel_sel=vel_sel, q_init_sel=q_init_sel, q_fin_sel=q_fin_sel,
+    )
+    out["C0"] = stage0_projector(p[:, :n], nx)
+    return out
+
+
+def stage0_projector(d, nx):
+    """C[:, n:2n] = I - d d^T  (VBOC/triplependulum_class_vboc.py:174-178): forces v_0 parallel to d."""
+    d = np.asarray(d, dtype=float)
+    batch, n = d.shape
+    C0 = np.zeros((batch, n, nx))
+    C0[:, :, n:2 * n] = np.eye(n)[None] - d[:, :, None] * d[:, None, :]
+    return C0
+
+
+def sample_testdata(n, batch, seed, N=None, dt_sym=1e-2):
+    """Batched restatement of `testing(v)` sampling: random position, random direction, constant guess."""
+    mdl = Model(n)
+    N = N or mdl.N0
+    q_min, q_max, v_max, tau_max = mdl.thetamin, mdl.thetamax, mdl.dthetamax, mdl.umax
+    v_min = -v_max
+    rng = _rng(seed)
+    R = rng.random((batch, 3 * n))
+    nx = 2 * n + 1
+    if n == 1:
+        # pendulum_testdata.py:14-27: p = [+-1, 0]
+        p = np.zeros((batch, 2))
+        p[:, 0] = np.where(R[:, 0] < 0.5, -1.0, 1.0)
+        q_init = (q_min + R[:, 2] * (q_max - q_min))[:, None]
+    else:
+        ran = np.where(R[:, :n] < 0.5, -1.0, 1.0) * R[:, n:2 * n]
+        ran /= np.linalg.norm(ran, axis=1, keepdims=True)
+        p = np.zeros((batch, n + 1))
+        p[:, :n] = ran
+        q_init = q_min + R[:, 2 * n:3 * n] * (q_max - q_min)
+    lbx0 = np.empty((batch, nx)); ubx0 = np.empty((batch, nx))
+    lbx0[:, :n] = q_init; ubx0[:, :n] = q_init
+    lbx0[:, n:2 * n] = v_min; ubx0[:, n:2 * n] = v_max
+    lbx0[:, 2 * n] = dt_sym; ubx0[:, 2 * n] = dt_sym
+    xg = np.zeros((batch, N + 1, nx))
+    xg[:, :, :n] = q_init[:, None, :]
+    xg[:, :, 2 * n] = dt_sym
+    ug = np.zeros((batch, N, n))
+    if n == 2:
+        ug[:, :, 0] = (mdl.g * mdl.l1 * (mdl.m1 + mdl.m2) * np.sin(q_init[:, 0]))[:, None]
+        ug[:, :, 1] = (mdl.g * mdl.l2 * mdl.m2 * np.sin(q_init[:, 1]))[:, None]
+
+    def rep(v):
+        return np.tile(np.asarray(v, dtype=float), (batch, 1))
+
+    out = dict(
+        n=n, family="vboc", N=np.full(batch, N, dtype=np.int32), x_guess=xg, u_guess=ug, p=p,
+        lbx0=lbx0, ubx0=ubx0,
+        lbx=rep([q_min] * n + [v_min] * n + [dt_sym]), ubx=rep([q_max] * n + [v_max] * n + [dt_sym]),
+        lbxN=rep([q_min] * n + [0.0] * n + [dt_sym]), ubxN=rep([q_max] * n + [0.0] * n + [dt_sym]),
+        lbu=rep([-tau_max] * n), ubu=rep([tau_max] * n),
+    )
+    out["C0"] = stage0_projector(p[:, :n], nx) if n > 1 else None
+    return out
+
+
+def sample_al(n, batch, seed, N=100, Tf=1.0):
+    """AL feasibility problems (`compute_problem`, AL/triplependulum_class_al.py:148-169): x0 uniform in the
+    position box x velocities 5 % beyond the velocity box (AL/triplependulum_al.py:115-123); guess
+    x_k = [q0, 0], u = 0."""
+    mdl = Model(n)
+    q_min, q_max, v_max, tau_max = mdl.thetamin, mdl.thetamax, mdl.dthetamax, mdl.umax
+    rng = _rng(seed)
+    R = rng.random((batch, 2 * n))
+    x0 = np.empty((batch, 2 * n))
+    x0[:, :n] = q_min + R[:, :n] * (q_max - q_min)
+    vlim = v_max * 1.05
+    x0[:, n:] = -vlim + R[:, n:] * 2 * vlim
+    return al_problems(n, x0, N=N, Tf=Tf)
+
+
+def al_problems(n, x0, N=100, Tf=1.0, x_guess=None):
+    """Reference-shaped AL OCP data for given initial states x0 (batch, 2n)."""
+    mdl = Model(n)
+    x0 = np.asarray(x0, dtype=float)
+    batch = x0.shape[0]
+    q_min, q_max, v_max, tau_max = mdl.thetamin, mdl.thetamax, mdl.dthetamax, mdl.umax
+    nx = 2 * n
+    if x_guess is None:
+        xg = np.zeros((batch, N + 1, nx))
+        xg[:, :, :n] = x0[:, None, :n]
+    else:
+        xg = np.array(x_guess, dtype=float)
+
+    def rep(v):
+        return np.tile(np.asarray(v, dtype=float), (batch, 1))
+
+    return dict(
+        n=n, family="al", N=np.full(batch, N, dtype=np.int32), Tf=Tf, x_guess=xg,
+        u_guess=np.zeros((batch, N, n)), p=None, lbx0=x0.copy(), ubx0=x0.copy(),
+        lbx=rep([q_min] * n + [-v_max] * n), ubx=rep([q_max] * n + [v_max] * n),
+        lbxN=rep([q_min] * n + [0.0] * n), ubxN=rep([q_max] * n + [0.0] * n),
+        lbu=rep([-tau_max] * n), ubu=rep([tau_max] * n), C0=None, x0=x0,
+    )
+
+
+def take(bp, i):
+    """Single-problem view (dict) of batched problem data."""
+    N = int(bp["N"][i])
+    out = dict(n=bp["n"], family=bp["family"], Tf=bp.get("Tf", 1.0))
+    out["x_guess"] = np.ascontiguousarray(bp["x_guess"][i, :N + 1])
+    out["u_guess"] = np.ascontiguousarray(bp["u_guess"][i, :N])
+    for k in ("p", "lbx0", "ubx0", "lbx", "ubx", "lbxN", "ubxN", "lbu", "ubu", "C0"):
+        out[k] = None if bp.get(k) is None else np.ascontiguousarray(bp[k][i])
+    return out

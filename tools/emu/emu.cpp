@@ -1,0 +1,64 @@
+// emu.cpp -- host emulation of the warp solver (development / test harness, NOT the product).
+// Compiles vboc_b200/csrc/ocp_warp.h with VBOC_EMU so that the 32 lanes of every lane region run
+// as a loop; lets the lane program be debugged against the oracle on a machine without a GPU.
+// Nothing under vboc_b200/ loads this library.
+#define VBOC_EMU
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../vboc_b200/csrc/ocp_warp.h"
+
+using namespace vboc;
+
+template <int NQ, int FAM>
+static void run(int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug,
+                const double *p, const double *lbx0, const double *ubx0, const double *lbx,
+                const double *ubx, const double *lbxN, const double *ubxN, const double *lbu,
+                const double *ubu, const double *dir, const double *h, const vboc_opts *o, double *x,
+                double *u, vboc_stats *st) {
+    const int nxr = 2 * NQ + (FAM == VBOC_FAMILY_VBOC), nu = NQ;
+#pragma omp parallel
+    {
+        std::vector<double> buf(Work<NQ>::doubles(Nmax));
+        Smem<NQ> *sm = new Smem<NQ>();
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < batch; ++b) {
+            Work<NQ> w;
+            w.carve(buf.data(), Nmax);
+            Prob pb;
+            pb.N = N[b], pb.nxr = nxr, pb.h = h[b];
+            pb.wt = p ? p[(size_t)b * (NQ + 1) + NQ] : 0.0;
+            pb.xg = xg + (size_t)b * (Nmax + 1) * nxr, pb.ug = ug + (size_t)b * Nmax * nu;
+            pb.p = p ? p + (size_t)b * (NQ + 1) : nullptr;
+            pb.lbx0 = lbx0 + (size_t)b * nxr, pb.ubx0 = ubx0 + (size_t)b * nxr;
+            pb.lbx = lbx + (size_t)b * nxr, pb.ubx = ubx + (size_t)b * nxr;
+            pb.lbxN = lbxN + (size_t)b * nxr, pb.ubxN = ubxN + (size_t)b * nxr;
+            pb.lbu = lbu + (size_t)b * nu, pb.ubu = ubu + (size_t)b * nu;
+            pb.dir = dir ? dir + (size_t)b * NQ : nullptr;
+            pb.x = x + (size_t)b * (Nmax + 1) * nxr, pb.u = u + (size_t)b * Nmax * nu;
+            pb.st = st + b;
+            WarpSolver<NQ, FAM> sol(*sm, w, *o);
+            sol.solve(pb, mode);
+        }
+        delete sm;
+    }
+}
+
+extern "C" int emu_solve_batch(int n, int family, int mode, int batch, int Nmax, const int *N,
+                               const double *xg, const double *ug, const double *p,
+                               const double *lbx0, const double *ubx0, const double *lbx,
+                               const double *ubx, const double *lbxN, const double *ubxN,
+                               const double *lbu, const double *ubu, const double *dir,
+                               const double *h, const vboc_opts *o, double *x, double *u,
+                               vboc_stats *st) {
+#define GO(NQ, FAM)                                                                              \
+    if (n == NQ && family == FAM) {                                                              \
+        run<NQ, FAM>(mode, batch, Nmax, N, xg, ug, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu, ubu, \
+                     dir, h, o, x, u, st);                                                       \
+        return 0;                                                                                \
+    }
+    GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
+#undef GO
+    return -1;
+}

@@ -1,0 +1,63 @@
+"""ctypes wrapper of tools/emu/libemu.so (host emulation of the warp solver; dev/test harness only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Opts(C.Structure):
+    _fields_ = [
+        ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double), ("tol_comp", C.c_double),
+        ("max_iter", C.c_int), ("levenberg_marquardt", C.c_double),
+        ("alpha_min", C.c_double), ("alpha_reduction", C.c_double), ("globalization", C.c_int),
+        ("qp_tol_stat", C.c_double), ("qp_tol_eq", C.c_double), ("qp_tol_ineq", C.c_double), ("qp_tol_comp", C.c_double),
+        ("qp_iter_max", C.c_int),
+        ("qp_mu0", C.c_double), ("qp_alpha_min", C.c_double), ("qp_reg_prim", C.c_double),
+        ("qp_lam_min", C.c_double), ("qp_t_min", C.c_double), ("qp_tau_min", C.c_double),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("status", C.c_int), ("sqp_iter", C.c_int), ("qp_iter", C.c_int), ("ls_evals", C.c_int),
+        ("qp_status", C.c_int), ("pad_", C.c_int), ("cost", C.c_double),
+        ("res_stat", C.c_double), ("res_eq", C.c_double), ("res_ineq", C.c_double), ("res_comp", C.c_double),
+    ]
+
+
+def build():
+    so = os.path.join(_HERE, "libemu.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                           "-o", so, os.path.join(_HERE, "emu.cpp")])
+    return so
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def solve_batch(n, family, mode, bp, opts):
+    lib = C.CDLL(build() if not os.path.exists(os.path.join(_HERE, "libemu.so")) else os.path.join(_HERE, "libemu.so"))
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    xg, ug = c(bp["x_guess"]), c(bp["u_guess"])
+    B, Np1, nxr = xg.shape
+    Nmax = Np1 - 1
+    Nv = np.ascontiguousarray(bp["N"], dtype=np.int32)
+    keep = [c(bp.get(k)) for k in ("p", "lbx0", "ubx0", "lbx", "ubx", "lbxN", "ubxN", "lbu", "ubu")]
+    if family == 0:
+        h = np.ascontiguousarray(bp["lbx0"][:, 2 * n])
+        d = None if bp.get("C0") is None else c(bp["p"][:, :n] / np.linalg.norm(bp["p"][:, :n], axis=1, keepdims=True))
+    else:
+        h = np.full(B, bp.get("Tf", 1.0) / Nv, dtype=np.float64)
+        d = None
+    x, u = np.zeros_like(xg), np.zeros_like(ug)
+    st = (Stats * B)()
+    lib.emu_solve_batch(n, family, mode, B, Nmax, Nv.ctypes.data_as(C.POINTER(C.c_int)), _p(xg), _p(ug),
+                        *[_p(a) for a in keep], _p(d), _p(h), C.byref(opts), _p(x), _p(u), st)
+    f = lambda name: np.array([getattr(s_, name) for s_ in st])
+    return dict(status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),
+                ls_evals=f("ls_evals"), qp_status=f("qp_status"),
+                res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))

@@ -1,0 +1,88 @@
+"""ctypes binding of libvboc_b200.so (include/vboc_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `python -m vboc_b200.build`.  There is
+no CPU fallback: if the shared object is missing, or no CUDA device is visible when a solver is
+created, the calls raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvboc_b200.so")
+
+FAMILY_VBOC, FAMILY_AL = 0, 1
+MODE_SQP, MODE_RTI = 0, 1
+ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA = -1, -2, -3
+
+EXPORTS = (
+    "vboc_default_opts", "vboc_create", "vboc_destroy", "vboc_set_opts", "vboc_set_stream",
+    "vboc_solve_batch", "vboc_upload", "vboc_solve_resident", "vboc_download", "vboc_last_kernel_ms",
+    "vboc_sim_step", "vboc_last_error", "vboc_version",
+)
+
+
+class Opts(C.Structure):
+    """vboc_opts"""
+    _fields_ = [
+        ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double), ("tol_comp", C.c_double),
+        ("max_iter", C.c_int), ("levenberg_marquardt", C.c_double),
+        ("alpha_min", C.c_double), ("alpha_reduction", C.c_double), ("globalization", C.c_int),
+        ("qp_tol_stat", C.c_double), ("qp_tol_eq", C.c_double), ("qp_tol_ineq", C.c_double),
+        ("qp_tol_comp", C.c_double), ("qp_iter_max", C.c_int),
+        ("qp_mu0", C.c_double), ("qp_alpha_min", C.c_double), ("qp_reg_prim", C.c_double),
+        ("qp_lam_min", C.c_double), ("qp_t_min", C.c_double), ("qp_tau_min", C.c_double),
+    ]
+
+
+class Stats(C.Structure):
+    """vboc_stats"""
+    _fields_ = [
+        ("status", C.c_int), ("sqp_iter", C.c_int), ("qp_iter", C.c_int), ("ls_evals", C.c_int),
+        ("qp_status", C.c_int), ("pad_", C.c_int), ("cost", C.c_double),
+        ("res_stat", C.c_double), ("res_eq", C.c_double), ("res_ineq", C.c_double), ("res_comp", C.c_double),
+    ]
+
+
+class VbocError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvboc_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+                "g.build()').  vboc_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+        L.vboc_default_opts.argtypes = [C.c_int, C.POINTER(Opts)]
+        L.vboc_default_opts.restype = None
+        L.vboc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.vboc_destroy.argtypes = [vp]
+        L.vboc_destroy.restype = None
+        L.vboc_set_opts.argtypes = [vp, C.POINTER(Opts)]
+        L.vboc_set_stream.argtypes = [vp, vp]
+        prob = [dp] * 13  # x_guess, u_guess, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu, ubu, C0 + Tf below
+        L.vboc_upload.argtypes = [vp, C.c_int, ip] + [dp] * 12 + [C.c_double]
+        L.vboc_solve_batch.argtypes = [vp, C.c_int, C.c_int, ip] + [dp] * 12 + [C.c_double, dp, dp, C.POINTER(Stats)]
+        L.vboc_solve_resident.argtypes = [vp, C.c_int]
+        L.vboc_download.argtypes = [vp, dp, dp, C.POINTER(Stats)]
+        L.vboc_last_kernel_ms.argtypes = [vp]
+        L.vboc_last_kernel_ms.restype = C.c_double
+        L.vboc_sim_step.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, dp]
+        L.vboc_last_error.restype = C.c_char_p
+        L.vboc_version.restype = C.c_char_p
+        del prob
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise VbocError(rc, lib().vboc_last_error().decode())

@@ -1,0 +1,434 @@
+// vboc_cuda.cu -- kernels and the C-ABI of libvboc_b200.so (see include/vboc_b200.h).
+//
+// solve_kernel: persistent CTAs of WARPS_PER_CTA independent warps; every warp pulls the next
+// problem index from a global counter (iteration counts vary 100x between problems, so static
+// assignment would leave most of the machine idle at the tail) and runs the whole SQP solve of
+// that problem (ocp_warp.h) on its private workspace slot in HBM / L2 and its private block of
+// shared memory.  No inter-warp synchronisation anywhere.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vboc_b200.h"
+#include "ocp_warp.h"
+
+using namespace vboc;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_OK(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(VBOC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+constexpr int WARPS_PER_CTA = 4;
+
+// device-resident problem batch, reference-shaped
+struct Batch {
+    int batch, Nmax, nxr;
+    const int *N;
+    const double *xg, *ug, *p, *lbx0, *ubx0, *lbx, *ubx, *lbxN, *ubxN, *lbu, *ubu, *dir, *h;
+    double *x, *u;
+    vboc_stats *st;
+    double *work;  // slots * work_doubles
+    size_t work_doubles;
+    unsigned int *counter;
+    int mode;
+    vboc_opts opts;
+};
+
+template <int NQ, int FAM>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) solve_kernel(const Batch B) {
+    __shared__ Smem<NQ> smem[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * WARPS_PER_CTA + warp;
+    Work<NQ> w;
+    w.carve(B.work + (size_t)slot * B.work_doubles, B.Nmax);
+    WarpSolver<NQ, FAM> sol(smem[warp], w, B.opts);
+    const int nu = NQ;
+    for (;;) {
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(B.counter, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned)B.batch) break;
+        Prob pb;
+        pb.N = B.N[b], pb.nxr = B.nxr, pb.h = B.h[b];
+        pb.p = B.p ? B.p + (size_t)b * (NQ + 1) : nullptr;
+        pb.wt = B.p ? pb.p[NQ] : 0.0;
+        pb.xg = B.xg + (size_t)b * (B.Nmax + 1) * B.nxr, pb.ug = B.ug + (size_t)b * B.Nmax * nu;
+        pb.lbx0 = B.lbx0 + (size_t)b * B.nxr, pb.ubx0 = B.ubx0 + (size_t)b * B.nxr;
+        pb.lbx = B.lbx + (size_t)b * B.nxr, pb.ubx = B.ubx + (size_t)b * B.nxr;
+        pb.lbxN = B.lbxN + (size_t)b * B.nxr, pb.ubxN = B.ubxN + (size_t)b * B.nxr;
+        pb.lbu = B.lbu + (size_t)b * nu, pb.ubu = B.ubu + (size_t)b * nu;
+        pb.dir = B.dir ? B.dir + (size_t)b * NQ : nullptr;
+        pb.x = B.x + (size_t)b * (B.Nmax + 1) * B.nxr, pb.u = B.u + (size_t)b * B.Nmax * nu;
+        pb.st = B.st + b;
+        sol.solve(pb, B.mode);
+        __syncwarp();
+    }
+}
+
+// one RK4 step of the unscaled model per thread (the reference's AcadosSimSolver)
+template <int NQ>
+__global__ void sim_kernel(int batch, const double *x, const double *u, double T, double *xn) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double xi[2 * NQ], ui[NQ], xo[2 * NQ];
+#pragma unroll
+    for (int i = 0; i < 2 * NQ; ++i) xi[i] = x[(size_t)b * 2 * NQ + i];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) ui[i] = u[(size_t)b * NQ + i];
+    rk4_step<NQ, double>(xi, ui, T, xo);
+#pragma unroll
+    for (int i = 0; i < 2 * NQ; ++i) xn[(size_t)b * 2 * NQ + i] = xo[i];
+}
+
+}  // namespace
+
+struct vboc_solver {
+    int n, family, cap, Nmax, device, nxr, nu;
+    int slots, grid;
+    cudaStream_t stream;
+    vboc_opts opts;
+    // device buffers
+    int *dN;
+    double *dxg, *dug, *dp, *dlbx0, *dubx0, *dlbx, *dubx, *dlbxN, *dubxN, *dlbu, *dubu, *ddir, *dh;
+    double *dx, *du, *dwork;
+    vboc_stats *dst;
+    unsigned int *dcounter;
+    size_t work_doubles;
+    cudaEvent_t ev0, ev1;
+    int batch;  // resident batch, 0 if none
+    int has_dir, has_p;
+    double last_ms;
+    // pinned staging for the host <-> device copies
+    char *stage;
+    size_t stage_bytes;
+};
+
+template <int NQ, int FAM>
+static cudaError_t launch(vboc_solver *s, const Batch &B) {
+    solve_kernel<NQ, FAM><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+const char *vboc_last_error(void) { return g_err.c_str(); }
+const char *vboc_version(void) { return "vboc_b200 0.1 (sm_100a)"; }
+
+void vboc_default_opts(int family, vboc_opts *o) {
+    memset(o, 0, sizeof(*o));
+    // acados / HPIPM (BALANCE) defaults
+    o->tol_eq = o->tol_ineq = o->tol_comp = 1e-6;
+    o->alpha_min = 0.05, o->alpha_reduction = 0.7;
+    o->qp_tol_stat = 1e-6, o->qp_tol_eq = o->qp_tol_ineq = o->qp_tol_comp = 1e-8;
+    o->qp_mu0 = 1e1, o->qp_alpha_min = 1e-12, o->qp_reg_prim = 1e-15;
+    o->qp_lam_min = 1e-16, o->qp_t_min = 1e-16, o->qp_tau_min = 1e-16;
+    if (family == VBOC_FAMILY_VBOC) {
+        // VBOC/triplependulum_class_vboc.py:129-141
+        o->tol_stat = 1e-3, o->qp_tol_stat = 1e-3;
+        o->qp_iter_max = 100, o->max_iter = 1000;
+        o->globalization = 1, o->alpha_reduction = 0.3, o->alpha_min = 1e-2;
+        o->levenberg_marquardt = 1e-5;
+    } else {
+        // AL classes: SQP_RTI with acados defaults (AL/pendulum_class_al.py:124)
+        o->tol_stat = 1e-6;
+        o->qp_iter_max = 50, o->max_iter = 100;
+        o->globalization = 0, o->levenberg_marquardt = 0.0;
+    }
+}
+
+static size_t work_doubles_for(int n, int Nmax) {
+    return n == 1 ? Work<1>::doubles(Nmax) : (n == 2 ? Work<2>::doubles(Nmax) : Work<3>::doubles(Nmax));
+}
+
+int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device, vboc_solver **out) {
+    if (!out || n_dof < 1 || n_dof > 3 || (family != VBOC_FAMILY_VBOC && family != VBOC_FAMILY_AL) ||
+        batch_capacity < 1 || N_max < 1 || N_max > 1024)
+        return fail(VBOC_ERR_ARG, "vboc_create: bad argument");
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(VBOC_ERR_CUDA, "vboc_create: no such CUDA device");
+    CUDA_OK(cudaSetDevice(device));
+    vboc_solver *s = new vboc_solver();
+    memset(s, 0, sizeof(*s));
+    s->n = n_dof, s->family = family, s->cap = batch_capacity, s->Nmax = N_max, s->device = device;
+    s->nxr = 2 * n_dof + (family == VBOC_FAMILY_VBOC), s->nu = n_dof;
+    s->last_ms = -1.0;
+    vboc_default_opts(family, &s->opts);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    int ctas_per_sm = 4;
+    int max_grid = prop.multiProcessorCount * ctas_per_sm;
+    int need = (batch_capacity + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    s->grid = need < max_grid ? need : max_grid;
+    s->slots = s->grid * WARPS_PER_CTA;
+    s->work_doubles = work_doubles_for(n_dof, N_max);
+    size_t B = (size_t)batch_capacity, nxr = s->nxr, nu = s->nu;
+#define DEV_ALLOC(ptr, count) CUDA_OK(cudaMalloc((void **)&s->ptr, (size_t)(count) * sizeof(*s->ptr)))
+    DEV_ALLOC(dN, B);
+    DEV_ALLOC(dxg, B * (N_max + 1) * nxr);
+    DEV_ALLOC(dug, B * N_max * nu);
+    DEV_ALLOC(dp, B * (n_dof + 1));
+    DEV_ALLOC(dlbx0, B * nxr);
+    DEV_ALLOC(dubx0, B * nxr);
+    DEV_ALLOC(dlbx, B * nxr);
+    DEV_ALLOC(dubx, B * nxr);
+    DEV_ALLOC(dlbxN, B * nxr);
+    DEV_ALLOC(dubxN, B * nxr);
+    DEV_ALLOC(dlbu, B * nu);
+    DEV_ALLOC(dubu, B * nu);
+    DEV_ALLOC(ddir, B * n_dof);
+    DEV_ALLOC(dh, B);
+    DEV_ALLOC(dx, B * (N_max + 1) * nxr);
+    DEV_ALLOC(du, B * N_max * nu);
+    DEV_ALLOC(dst, B);
+    DEV_ALLOC(dcounter, 1);
+    DEV_ALLOC(dwork, (size_t)s->slots * s->work_doubles);
+#undef DEV_ALLOC
+    CUDA_OK(cudaEventCreate(&s->ev0));
+    CUDA_OK(cudaEventCreate(&s->ev1));
+    s->stage_bytes = B * (N_max + 1) * nxr * sizeof(double);
+    CUDA_OK(cudaMallocHost((void **)&s->stage, s->stage_bytes));
+    *out = s;
+    return 0;
+}
+
+void vboc_destroy(vboc_solver *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    void *ptrs[] = {s->dN,    s->dxg,   s->dug,  s->dp,   s->dlbx0, s->dubx0, s->dlbx,
+                    s->dubx,  s->dlbxN, s->dubxN, s->dlbu, s->dubu,  s->ddir,  s->dh,
+                    s->dx,    s->du,    s->dst,  s->dcounter, s->dwork};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (s->stage) cudaFreeHost(s->stage);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+int vboc_set_opts(vboc_solver *s, const vboc_opts *o) {
+    if (!s || !o) return fail(VBOC_ERR_ARG, "vboc_set_opts: null argument");
+    s->opts = *o;
+    return 0;
+}
+
+int vboc_set_stream(vboc_solver *s, void *cuda_stream) {
+    if (!s) return fail(VBOC_ERR_ARG, "vboc_set_stream: null handle");
+    s->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+// host -> device through the pinned staging buffer (host arrays may be pageable)
+static int h2d(vboc_solver *s, void *dst, const void *src, size_t bytes) {
+    const char *p = (const char *)src;
+    char *d = (char *)dst;
+    while (bytes) {
+        size_t c = bytes < s->stage_bytes ? bytes : s->stage_bytes;
+        memcpy(s->stage, p, c);
+        CUDA_OK(cudaMemcpyAsync(d, s->stage, c, cudaMemcpyHostToDevice, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        p += c, d += c, bytes -= c;
+    }
+    return 0;
+}
+static int d2h(vboc_solver *s, void *dst, const void *src, size_t bytes) {
+    char *p = (char *)dst;
+    const char *d = (const char *)src;
+    while (bytes) {
+        size_t c = bytes < s->stage_bytes ? bytes : s->stage_bytes;
+        CUDA_OK(cudaMemcpyAsync(s->stage, d, c, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        memcpy(p, s->stage, c);
+        p += c, d += c, bytes -= c;
+    }
+    return 0;
+}
+
+int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
+                const double *u_guess, const double *p, const double *lbx0, const double *ubx0,
+                const double *lbx, const double *ubx, const double *lbxN, const double *ubxN,
+                const double *lbu, const double *ubu, const double *C0, double Tf) {
+    if (!s) return fail(VBOC_ERR_ARG, "vboc_upload: null handle");
+    if (batch < 1 || batch > s->cap) return fail(VBOC_ERR_ARG, "vboc_upload: batch exceeds capacity");
+    if (!N || !x_guess || !u_guess || !lbx0 || !ubx0 || !lbx || !ubx || !lbxN || !ubxN || !lbu || !ubu)
+        return fail(VBOC_ERR_ARG, "vboc_upload: null array");
+    const int n = s->n, nxr = s->nxr, Nmax = s->Nmax;
+    if (s->family == VBOC_FAMILY_VBOC && !p) return fail(VBOC_ERR_ARG, "vboc_upload: p required");
+    CUDA_OK(cudaSetDevice(s->device));
+    // ---- validation and host-side preparation (what the shim's OCP_solve would otherwise do
+    // stage by stage through ocp_solver.set / constraints_set)
+    std::vector<double> h(batch), dir;
+    if (C0) dir.resize((size_t)batch * n);
+    for (int b = 0; b < batch; ++b) {
+        if (N[b] < 1 || N[b] > Nmax) return fail(VBOC_ERR_ARG, "vboc_upload: horizon out of range");
+        const double *l0 = lbx0 + (size_t)b * nxr, *u0 = ubx0 + (size_t)b * nxr;
+        const double *l1 = lbx + (size_t)b * nxr, *u1 = ubx + (size_t)b * nxr;
+        const double *lN = lbxN + (size_t)b * nxr, *uN = ubxN + (size_t)b * nxr;
+        if (s->family == VBOC_FAMILY_VBOC) {
+            // the dt state must be pinned (VBOC/triplependulum_vboc.py:98-103)
+            double dt = l0[2 * n];
+            bool pinned = u0[2 * n] == dt && l1[2 * n] == dt && u1[2 * n] == dt && lN[2 * n] == dt &&
+                          uN[2 * n] == dt;
+            const double *xg = x_guess + (size_t)b * (Nmax + 1) * nxr;
+            for (int k = 0; k <= N[b] && pinned; ++k) pinned = xg[(size_t)k * nxr + 2 * n] == dt;
+            if (!pinned || !(dt > 0.0))
+                return fail(VBOC_ERR_UNSUPPORTED,
+                            "vboc_upload: the dt state must be pinned to one positive value at every "
+                            "stage and in the guess (free-dt problems are not supported)");
+            h[b] = dt;
+        } else {
+            h[b] = Tf / N[b];
+        }
+        int nf = 0, nfv = 0;
+        for (int i = 0; i < 2 * n; ++i)
+            if (lN[i] == uN[i]) {
+                ++nf;
+                nfv += i >= n;
+            }
+        if (!(nf == 0 || (nf == n && nfv == n)))
+            return fail(VBOC_ERR_UNSUPPORTED,
+                        "vboc_upload: terminal equalities must be on none or exactly all velocities");
+        if (C0) {
+            // only C0 = [0 | I - d d' | 0] (VBOC/triplependulum_class_vboc.py:174-178)
+            const double *C = C0 + (size_t)b * n * nxr;
+            double Md[3][3], d[3];
+            int jm = 0;
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) Md[i][j] = (i == j) - C[i * nxr + n + j];
+            for (int i = 1; i < n; ++i)
+                if (Md[i][i] > Md[jm][jm]) jm = i;
+            if (!(Md[jm][jm] > 0.0))
+                return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: C0 is not a projector I - d d'");
+            double dj = sqrt(Md[jm][jm]), nrm = 0.0;
+            for (int i = 0; i < n; ++i) d[i] = Md[i][jm] / dj, nrm += d[i] * d[i];
+            nrm = sqrt(nrm);
+            for (int i = 0; i < n; ++i) d[i] /= nrm;
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < nxr; ++j) {
+                    double want = (j >= n && j < 2 * n) ? (i == j - n) - d[i] * d[j - n] : 0.0;
+                    if (fabs(C[i * nxr + j] - want) > 1e-9)
+                        return fail(VBOC_ERR_UNSUPPORTED,
+                                    "vboc_upload: C0 is not of the form [0 | I - d d' | 0]");
+                }
+            for (int i = 0; i < n; ++i)
+                if (l0[n + i] == u0[n + i])
+                    return fail(VBOC_ERR_UNSUPPORTED,
+                                "vboc_upload: fixed initial velocity together with a direction constraint");
+            for (int i = 0; i < n; ++i) dir[(size_t)b * n + i] = d[i];
+        }
+    }
+    size_t B = batch;
+    int rc = 0;
+#define UP(dst, src, count) \
+    if ((rc = h2d(s, s->dst, src, (size_t)(count) * sizeof(*s->dst)))) return rc
+    UP(dN, N, B);
+    UP(dxg, x_guess, B * (Nmax + 1) * nxr);
+    UP(dug, u_guess, B * Nmax * s->nu);
+    if (p) UP(dp, p, B * (n + 1));
+    UP(dlbx0, lbx0, B * nxr);
+    UP(dubx0, ubx0, B * nxr);
+    UP(dlbx, lbx, B * nxr);
+    UP(dubx, ubx, B * nxr);
+    UP(dlbxN, lbxN, B * nxr);
+    UP(dubxN, ubxN, B * nxr);
+    UP(dlbu, lbu, B * s->nu);
+    UP(dubu, ubu, B * s->nu);
+    UP(dh, h.data(), B);
+    if (C0) UP(ddir, dir.data(), B * n);
+#undef UP
+    s->batch = batch, s->has_dir = C0 != nullptr, s->has_p = p != nullptr;
+    return 0;
+}
+
+int vboc_solve_resident(vboc_solver *s, int mode) {
+    if (!s) return fail(VBOC_ERR_ARG, "vboc_solve_resident: null handle");
+    if (!s->batch) return fail(VBOC_ERR_ARG, "vboc_solve_resident: nothing uploaded");
+    if (mode != VBOC_MODE_SQP && mode != VBOC_MODE_RTI) return fail(VBOC_ERR_ARG, "bad mode");
+    CUDA_OK(cudaSetDevice(s->device));
+    Batch B;
+    B.batch = s->batch, B.Nmax = s->Nmax, B.nxr = s->nxr;
+    B.N = s->dN, B.xg = s->dxg, B.ug = s->dug, B.p = s->has_p ? s->dp : nullptr;
+    B.lbx0 = s->dlbx0, B.ubx0 = s->dubx0, B.lbx = s->dlbx, B.ubx = s->dubx;
+    B.lbxN = s->dlbxN, B.ubxN = s->dubxN, B.lbu = s->dlbu, B.ubu = s->dubu;
+    B.dir = s->has_dir ? s->ddir : nullptr, B.h = s->dh;
+    B.x = s->dx, B.u = s->du, B.st = s->dst;
+    B.work = s->dwork, B.work_doubles = s->work_doubles, B.counter = s->dcounter;
+    B.mode = mode, B.opts = s->opts;
+    CUDA_OK(cudaMemsetAsync(s->dcounter, 0, sizeof(unsigned int), s->stream));
+    CUDA_OK(cudaEventRecord(s->ev0, s->stream));
+    cudaError_t e = cudaErrorInvalidValue;
+#define GO(NQ, FAM) \
+    if (s->n == NQ && s->family == FAM) e = launch<NQ, FAM>(s, B);
+    GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
+#undef GO
+    if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("solve_kernel launch: ") + cudaGetErrorString(e));
+    CUDA_OK(cudaEventRecord(s->ev1, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    return 0;
+}
+
+double vboc_last_kernel_ms(vboc_solver *s) { return s ? s->last_ms : -1.0; }
+
+int vboc_download(vboc_solver *s, double *x, double *u, vboc_stats *stats) {
+    if (!s || !s->batch) return fail(VBOC_ERR_ARG, "vboc_download: nothing resident");
+    CUDA_OK(cudaSetDevice(s->device));
+    size_t B = s->batch;
+    int rc;
+    if (x && (rc = d2h(s, x, s->dx, B * (s->Nmax + 1) * s->nxr * sizeof(double)))) return rc;
+    if (u && (rc = d2h(s, u, s->du, B * s->Nmax * s->nu * sizeof(double)))) return rc;
+    if (stats && (rc = d2h(s, stats, s->dst, B * sizeof(vboc_stats)))) return rc;
+    return 0;
+}
+
+int vboc_solve_batch(vboc_solver *s, int mode, int batch, const int *N, const double *x_guess,
+                     const double *u_guess, const double *p, const double *lbx0, const double *ubx0,
+                     const double *lbx, const double *ubx, const double *lbxN, const double *ubxN,
+                     const double *lbu, const double *ubu, const double *C0, double Tf, double *x,
+                     double *u, vboc_stats *stats) {
+    int rc = vboc_upload(s, batch, N, x_guess, u_guess, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu, ubu,
+                         C0, Tf);
+    if (rc) return rc;
+    if ((rc = vboc_solve_resident(s, mode))) return rc;
+    return vboc_download(s, x, u, stats);
+}
+
+int vboc_sim_step(int n_dof, int device, int batch, const double *x, const double *u, double T,
+                  double *x_next) {
+    if (n_dof < 1 || n_dof > 3 || batch < 1 || !x || !u || !x_next)
+        return fail(VBOC_ERR_ARG, "vboc_sim_step: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    double *dx = nullptr, *du = nullptr, *dxn = nullptr;
+    size_t nx = 2 * n_dof, B = batch;
+    CUDA_OK(cudaMalloc((void **)&dx, B * nx * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&du, B * n_dof * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&dxn, B * nx * sizeof(double)));
+    CUDA_OK(cudaMemcpy(dx, x, B * nx * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(du, u, B * n_dof * sizeof(double), cudaMemcpyHostToDevice));
+    int th = 128, bl = (batch + th - 1) / th;
+    if (n_dof == 1) sim_kernel<1><<<bl, th>>>(batch, dx, du, T, dxn);
+    if (n_dof == 2) sim_kernel<2><<<bl, th>>>(batch, dx, du, T, dxn);
+    if (n_dof == 3) sim_kernel<3><<<bl, th>>>(batch, dx, du, T, dxn);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(x_next, dxn, B * nx * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx), cudaFree(du), cudaFree(dxn);
+    return 0;
+}
+
+}  // extern "C"

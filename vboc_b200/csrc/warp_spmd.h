@@ -1,0 +1,105 @@
+// warp_spmd.h -- the warp-cooperative programming style of the OCP kernels.
+//
+// One warp owns one OCP.  The solver code (ocp_warp.h) is written as a sequence of LANE REGIONS:
+//
+//     FOR_LANES   ... code executed by each of the 32 lanes, `lane` in scope ...   END_LANES
+//
+// Rules of the style:
+//   * inside one region a lane never reads shared/global data that another lane writes in the
+//     same region; END_LANES is a __syncwarp(), which also orders the warp's memory accesses;
+//   * code outside the regions is WARP-UNIFORM: every lane computes the same values from
+//     shared memory, uniform global loads or reduction results, and writes nothing;
+//   * a per-lane value that must survive a region boundary is declared with LV(type, name) and
+//     accessed as L(name); WARP_MIN/MAX/SUM(name) reduce it over the warp (shuffle butterflies);
+//   * uniform code whose loads are overwritten by the next region ends with UNIFORM_SYNC().
+//
+// With nvcc this is ordinary SIMT code.  With a host compiler (VBOC_EMU, tools/emu) the same
+// source runs the 32 lanes of a region as a loop -- the lane program is then debuggable on a
+// machine without a GPU.  The emulation is a development/test harness only; nothing in the
+// product loads it.
+#pragma once
+
+#if defined(__CUDACC__) && !defined(VBOC_EMU)
+
+#define VB_HD __host__ __device__ __forceinline__
+#define VB_DEV __device__ __forceinline__
+#define FOR_LANES {                                   \
+    const int lane = (int)(threadIdx.x & 31u);        \
+    (void)lane;
+#define END_LANES }                                   \
+    __syncwarp();
+#define LV(type, name) type name
+#define L(name) name
+#define UNIFORM_SYNC() __syncwarp()
+
+__device__ __forceinline__ double vb_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double vb_warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double vb_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int vb_warp_or(int v) { return __reduce_or_sync(0xffffffffu, (unsigned)v) != 0; }
+#define WARP_MAX(name) vb_warp_max(name)
+#define WARP_MIN(name) vb_warp_min(name)
+#define WARP_SUM(name) vb_warp_sum(name)
+#define WARP_ANY(name) vb_warp_or(name)
+
+#else  // host emulation
+
+#include <cmath>
+#define VB_HD inline
+#define VB_DEV inline
+#define FOR_LANES for (int lane = 0; lane < 32; ++lane) {
+#define END_LANES }
+#define LV(type, name) type name[32]
+#define L(name) name[lane]
+#define UNIFORM_SYNC() ((void)0)
+
+// the same butterfly order as the shuffle versions, so sums round identically
+inline double vb_emu_max(const double *a) {
+    double t[32], u[32];
+    for (int i = 0; i < 32; ++i) t[i] = a[i];
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int i = 0; i < 32; ++i) u[i] = std::fmax(t[i], t[i ^ o]);
+        for (int i = 0; i < 32; ++i) t[i] = u[i];
+    }
+    return t[0];
+}
+inline double vb_emu_min(const double *a) {
+    double t[32], u[32];
+    for (int i = 0; i < 32; ++i) t[i] = a[i];
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int i = 0; i < 32; ++i) u[i] = std::fmin(t[i], t[i ^ o]);
+        for (int i = 0; i < 32; ++i) t[i] = u[i];
+    }
+    return t[0];
+}
+inline double vb_emu_sum(const double *a) {
+    double t[32], u[32];
+    for (int i = 0; i < 32; ++i) t[i] = a[i];
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int i = 0; i < 32; ++i) u[i] = t[i] + t[i ^ o];
+        for (int i = 0; i < 32; ++i) t[i] = u[i];
+    }
+    return t[0];
+}
+inline int vb_emu_any(const int *a) {
+    int r = 0;
+    for (int i = 0; i < 32; ++i) r |= a[i] != 0;
+    return r;
+}
+#define WARP_MAX(name) vb_emu_max(name)
+#define WARP_MIN(name) vb_emu_min(name)
+#define WARP_SUM(name) vb_emu_sum(name)
+#define WARP_ANY(name) vb_emu_any(name)
+
+#endif

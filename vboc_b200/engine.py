@@ -1,0 +1,129 @@
+"""Batched OCP engine: thin Python face of the C-ABI (one handle = one GPU, one system, one family).
+
+`BatchSolver.solve(bp)` is the batched equivalent of calling the reference's `OCP_solve(...)` /
+`compute_problem(...)` once per problem under `multiprocessing.Pool` (VBOC/triplependulum_vboc.py:399-402,
+AL/triplependulum_al.py:132-134): `bp` holds the per-problem arrays those methods would pass stage by
+stage to acados (`vboc_b200.problems` builds them).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FAMILY_AL, FAMILY_VBOC, MODE_RTI, MODE_SQP, Opts, Stats, check
+
+_FAM = {"vboc": FAMILY_VBOC, "al": FAMILY_AL}
+_STAT_FIELDS = ("status", "sqp_iter", "qp_iter", "ls_evals", "qp_status", "cost",
+                "res_stat", "res_eq", "res_ineq", "res_comp")
+_STATS_DTYPE = np.dtype([("status", "i4"), ("sqp_iter", "i4"), ("qp_iter", "i4"), ("ls_evals", "i4"),
+                         ("qp_status", "i4"), ("pad_", "i4"), ("cost", "f8"), ("res_stat", "f8"),
+                         ("res_eq", "f8"), ("res_ineq", "f8"), ("res_comp", "f8")])
+assert _STATS_DTYPE.itemsize == C.sizeof(Stats)
+
+
+def default_opts(family):
+    o = Opts()
+    _lib.lib().vboc_default_opts(_FAM.get(family, family), C.byref(o))
+    return o
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _c(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class BatchSolver:
+    def __init__(self, n, family, batch_capacity, N_max, device=0, opts=None):
+        self.n, self.family = int(n), _FAM.get(family, family)
+        self.cap, self.N_max, self.device = int(batch_capacity), int(N_max), int(device)
+        self.nx = 2 * self.n + (self.family == FAMILY_VBOC)
+        self.nu = self.n
+        self._h = C.c_void_p()
+        check(_lib.lib().vboc_create(self.n, self.family, self.cap, self.N_max, self.device, C.byref(self._h)))
+        self.opts = opts or default_opts(self.family)
+        self.set_opts(self.opts)
+        self._batch = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().vboc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def set_opts(self, opts):
+        self.opts = opts
+        check(_lib.lib().vboc_set_opts(self._h, C.byref(opts)))
+
+    def set_stream(self, cuda_stream_ptr):
+        check(_lib.lib().vboc_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
+
+    # -- data marshalling -------------------------------------------------------------------
+    def _pack(self, bp):
+        Nv = np.ascontiguousarray(bp["N"], dtype=np.int32)
+        B = Nv.shape[0]
+        xg, ug = _c(bp["x_guess"]), _c(bp["u_guess"])
+        if xg.shape[1] != self.N_max + 1:  # re-stride to the solver's N_max
+            x2 = np.zeros((B, self.N_max + 1, self.nx))
+            u2 = np.zeros((B, self.N_max, self.nu))
+            m = min(xg.shape[1], self.N_max + 1)
+            x2[:, :m] = xg[:, :m]
+            u2[:, :m - 1] = ug[:, :m - 1]
+            xg, ug = x2, u2
+        assert xg.shape == (B, self.N_max + 1, self.nx) and ug.shape == (B, self.N_max, self.nu)
+        arrs = [xg, ug] + [_c(bp.get(k)) for k in
+                           ("p", "lbx0", "ubx0", "lbx", "ubx", "lbxN", "ubxN", "lbu", "ubu", "C0")]
+        return B, Nv, arrs, float(bp.get("Tf", 1.0))
+
+    def upload(self, bp):
+        B, Nv, arrs, Tf = self._pack(bp)
+        check(_lib.lib().vboc_upload(self._h, B, Nv.ctypes.data_as(C.POINTER(C.c_int)),
+                                     *[_dp(a) for a in arrs], Tf))
+        self._batch = B
+
+    def solve_resident(self, mode=MODE_SQP):
+        check(_lib.lib().vboc_solve_resident(self._h, int(mode)))
+        return _lib.lib().vboc_last_kernel_ms(self._h)
+
+    def download(self):
+        B = self._batch
+        x = np.empty((B, self.N_max + 1, self.nx))
+        u = np.empty((B, self.N_max, self.nu))
+        st = np.empty(B, dtype=_STATS_DTYPE)
+        check(_lib.lib().vboc_download(self._h, _dp(x), _dp(u), st.ctypes.data_as(C.POINTER(Stats))))
+        return self._result(x, u, st)
+
+    def solve(self, bp, mode=MODE_SQP):
+        """upload + solve + download in one C call (host buffers in, host buffers out)."""
+        B, Nv, arrs, Tf = self._pack(bp)
+        x = np.empty((B, self.N_max + 1, self.nx))
+        u = np.empty((B, self.N_max, self.nu))
+        st = np.empty(B, dtype=_STATS_DTYPE)
+        check(_lib.lib().vboc_solve_batch(self._h, int(mode), B, Nv.ctypes.data_as(C.POINTER(C.c_int)),
+                                          *[_dp(a) for a in arrs], Tf, _dp(x), _dp(u),
+                                          st.ctypes.data_as(C.POINTER(Stats))))
+        self._batch = B
+        return self._result(x, u, st)
+
+    @staticmethod
+    def _result(x, u, st):
+        out = dict(x=x, u=u)
+        for f in _STAT_FIELDS:
+            out[f] = st[f].copy()
+        out["res"] = np.stack([st["res_stat"], st["res_eq"], st["res_ineq"], st["res_comp"]], axis=1)
+        return out
+
+    @property
+    def last_kernel_ms(self):
+        return _lib.lib().vboc_last_kernel_ms(self._h)
+
+
+def sim_step(n, x, u, T, device=0):
+    """Batched RK4 step of the unscaled model (the reference's `sim.acados_integrator`)."""
+    x, u = _c(np.atleast_2d(x)), _c(np.atleast_2d(u))
+    xn = np.empty_like(x)
+    check(_lib.lib().vboc_sim_step(int(n), int(device), x.shape[0], _dp(x), _dp(u), float(T), _dp(xn)))
+    return xn

@@ -123,34 +123,24 @@ template <int NQ, class T>
 VB_HD void rk4_step(const T *x, const T *u, double h, T *xn) {
     constexpr int NX = 2 * NQ;
     T k[NX], xt[NX], acc[NX];
-    // k1
-    accel<NQ, T>(x, x + NQ, u, k + NQ);
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) k[i] = x[NQ + i];
+    for (int i = 0; i < NX; ++i) xt[i] = x[i], acc[i] = constant<T>(0.0);
+    // the four stages share one copy of the model code (instruction-cache footprint)
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        accel<NQ, T>(xt, xt + NQ, u, k + NQ);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) acc[i] = k[i], xt[i] = x[i] + (0.5 * h) * k[i];
-    // k2
-    accel<NQ, T>(xt, xt + NQ, u, k + NQ);
+        for (int i = 0; i < NQ; ++i) k[i] = xt[NQ + i];
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;  // k1 + 2 k2 + 2 k3 + k4
+        const double adv = st == 2 ? h : 0.5 * h;             // x + h/2 k1, x + h/2 k2, x + h k3
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) k[i] = xt[NQ + i];
+        for (int i = 0; i < NX; ++i) {
+            acc[i] = acc[i] + wgt * k[i];
+            xt[i] = x[i] + adv * k[i];
+        }
+    }
 #pragma unroll
-    for (int i = 0; i < NX; ++i) acc[i] = acc[i] + 2.0 * k[i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xt[i] = x[i] + (0.5 * h) * k[i];
-    // k3
-    accel<NQ, T>(xt, xt + NQ, u, k + NQ);
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) k[i] = xt[NQ + i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) acc[i] = acc[i] + 2.0 * k[i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xt[i] = x[i] + h * k[i];
-    // k4
-    accel<NQ, T>(xt, xt + NQ, u, k + NQ);
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) k[i] = xt[NQ + i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xn[i] = x[i] + (h / 6.0) * (acc[i] + k[i]);
+    for (int i = 0; i < NX; ++i) xn[i] = x[i] + (h / 6.0) * acc[i];
 }
 
 }  // namespace vboc

@@ -48,23 +48,48 @@ struct Dim {
     static constexpr int MFS = NZ * NZ + NZ + NU;           // last-stage record
 };
 
+// Per-stage record: everything the serial Riccati sweeps read at stage k, contiguous so that one
+// TMA bulk copy brings it into the shared-memory ring.
+template <int NQ>
+struct Rec {
+    using D = Dim<NQ>;
+    static constexpr int BAT = 0;                      // [B A]' (nz x nx): column j of [B A] contiguous
+    static constexpr int RB = BAT + D::NZ * D::NX;     // dynamics residual of the QP iterate
+    static constexpr int HH = RB + D::NX;              // effective Hessian diagonal  hd + lam/t (both sides)
+    static constexpr int RR = HH + D::NZ;              // predictor gradient
+    static constexpr int Q1 = RR + D::NZ;              // corrector gradient = Q1 - sigma*mu*Q2
+    static constexpr int Q2 = Q1 + D::NZ;
+    static constexpr int MB = Q2 + D::NZ;              // [B A]' P+ beta (kept for the re-solves)
+    static constexpr int LUU = MB + D::NZ;             // nu x nu Cholesky factor, inverse diagonal
+    static constexpr int LXU = LUU + D::NU * D::NU;    // nx x nu
+    static constexpr int YV = LXU + D::NX * D::NU;     // Luu^-1 m_u
+    static constexpr int END = YV + D::NU;
+    static constexpr int SIZE = (END + 1) & ~1;        // doubles; bytes are a multiple of 16
+    static constexpr int BYTES = SIZE * 8;
+};
+
+constexpr int RING_DEPTH = 4;
+
 // Global-memory workspace of one warp slot, stage-major.
 template <int NQ>
 struct Work {
     using D = Dim<NQ>;
-    double *Z, *PI, *LAM;            // NLP iterate: z_k = [u_k; x_k], dynamics and bound multipliers
-    double *BAT, *BD;                // [B A]' per stage (nz x nx: column j of [B A] contiguous), gap
+    using R = Rec<NQ>;
+    static constexpr int PPS = D::NX * D::NX + D::NX;  // value function record: P (nx x nx), p (nx)
+    double *SR;                      // stage records (16-byte aligned)
+    double *Z, *PI, *LAM, *BD;       // NLP iterate z_k = [u_k; x_k], multipliers, shooting gaps
     double *DZ, *PIQ, *LAMQ, *TQ;    // QP iterate
-    double *DV, *DPI, *DLAM, *DT;    // IPM step
-    double *RG, *RB, *RD, *RM, *RMB; // IPM residuals (RMB = lam*t, RM = corrector rhs)
-    double *FAC, *PV, *YV, *MF;      // Riccati factors and vectors
+    double *DV, *DLAM, *DT;          // IPM step
+    double *RG, *RD, *RM, *RMB;      // IPM residuals (RMB = lam*t, RM = dt_aff*dlam_aff)
+    double *PP, *MF;                 // value functions; last-stage record
     double *WDYN, *WB, *ZT;          // merit weights, trial point
     static VB_HD size_t doubles(int Nmax) {
         size_t S = (size_t)Nmax + 1;
-        return S * (size_t)(D::NZ + D::NX + D::NC + D::NZ * D::NX + D::NX + D::NZ + D::NX + D::NC +
-                            D::NC + D::NZ + D::NX + D::NC + D::NC + D::NZ + D::NX + D::NC + D::NC +
-                            D::NC + D::FS + D::NX + D::NU + D::NX + D::NC + D::NZ) +
-               D::MFS;
+        size_t n = S * (size_t)(R::SIZE + D::NZ + D::NX + D::NC + D::NX + D::NZ + D::NX + D::NC + D::NC +
+                                D::NZ + D::NC + D::NC + D::NZ + D::NC + D::NC + D::NC + PPS + D::NX +
+                                D::NC + D::NZ) +
+                   D::MFS;
+        return (n + 1) & ~(size_t)1;
     }
     VB_HD void carve(double *b, int Nmax) {
         size_t S = (size_t)Nmax + 1;
@@ -73,12 +98,12 @@ struct Work {
             b += S * per;
             return p;
         };
-        Z = take(D::NZ), PI = take(D::NX), LAM = take(D::NC);
-        BAT = take(D::NZ * D::NX), BD = take(D::NX);
+        SR = take(R::SIZE);
+        Z = take(D::NZ), PI = take(D::NX), LAM = take(D::NC), BD = take(D::NX);
         DZ = take(D::NZ), PIQ = take(D::NX), LAMQ = take(D::NC), TQ = take(D::NC);
-        DV = take(D::NZ), DPI = take(D::NX), DLAM = take(D::NC), DT = take(D::NC);
-        RG = take(D::NZ), RB = take(D::NX), RD = take(D::NC), RM = take(D::NC), RMB = take(D::NC);
-        FAC = take(D::FS), PV = take(D::NX), YV = take(D::NU);
+        DV = take(D::NZ), DLAM = take(D::NC), DT = take(D::NC);
+        RG = take(D::NZ), RD = take(D::NC), RM = take(D::NC), RMB = take(D::NC);
+        PP = take(PPS);
         WDYN = take(D::NX), WB = take(D::NC), ZT = take(D::NZ);
         MF = b;
     }
@@ -86,8 +111,10 @@ struct Work {
 
 // Shared-memory block of one warp.
 template <int NQ>
-struct Smem {
+struct alignas(16) Smem {
     using D = Dim<NQ>;
+    double ring[RING_DEPTH][Rec<NQ>::SIZE];  // TMA destination: stage records
+    unsigned long long bar[RING_DEPTH];      // one mbarrier per ring slot
     // problem constants
     double lb[3][D::NZ], ub[3][D::NZ];  // stage classes 0, 1..N-1, N in z ordering
     double Z0[D::NX][D::NX];            // orthonormal basis of the stage-0 free subspace, zero padded
@@ -95,9 +122,10 @@ struct Smem {
     double h, wtdt;
     int N, fixed0, fixedN, termfix, nact;
     // Riccati staging
-    double BAT[D::NZ][D::NX], P[D::NX][D::NX], PBAT[D::NZ][D::NX], M[D::NZ][D::NZ];
-    double hh[D::NZ], rr[D::NZ], t2[D::NX], m[D::NZ], pvec[D::NX], beta[D::NX], dz[D::NZ], dxn[D::NX];
-    double e0[D::NX], eN[D::NX], hhN[D::NX], rN[D::NX], Lz[D::NX][D::NX];
+    double P[D::NX][D::NX], PBAT[D::NZ][D::NX], M[D::NZ][D::NZ];
+    double tb[D::NX], m[D::NZ], pvec[D::NX], dx[2][D::NX];
+    double e0[D::NX], eN[D::NX], hhN[D::NX], rN[D::NX], nuv[D::NX], Lz[D::NX][D::NX], dzi[D::NX], Pe[D::NX];
+    double K[D::NU][D::NX], tz[D::NZ], va[D::NX], vb[D::NX], vc[D::NX], vt[D::NX];
     // merit weights / multipliers of the eliminated equalities
     double w0[D::NX], wN[D::NX], nu0q[D::NX], nuNq[D::NX];
 };
@@ -109,11 +137,15 @@ struct WarpSolver {
     static constexpr int OFF_LXU = NU * NU, OFF_P = NU * NU + NX * NU;
     static constexpr int TRI = NZ * (NZ + 1) / 2;
 
+    using R = Rec<NQ>;
     Smem<NQ> &s;
     Work<NQ> w;
     const vboc_opts &o;
+    VbRing ring;
 
-    VB_DEV WarpSolver(Smem<NQ> &s_, const Work<NQ> &w_, const vboc_opts &o_) : s(s_), w(w_), o(o_) {}
+    VB_DEV WarpSolver(Smem<NQ> &s_, const Work<NQ> &w_, const vboc_opts &o_) : s(s_), w(w_), o(o_) {
+        RING_INIT(ring, s.bar, RING_DEPTH);
+    }
 
     // ---------------------------------------------------------------- problem structure helpers
     VB_DEV int sclass(int k) const { return k == 0 ? 0 : (k == s.N ? 2 : 1); }
@@ -137,43 +169,43 @@ struct WarpSolver {
         if (FAM == VBOC_FAMILY_AL && i >= NU + NQ) hd += 2.0 * (k < s.N ? s.h : 1.0);
         return hd;
     }
-    // e = (I - Z0 Z0')(x - c0): violation of the stage-0 equalities (uniform)
-    VB_DEV void eq0_violation(const double *x, double *e) const {
-        double y[NX];
-#pragma unroll
-        for (int c = 0; c < NX; ++c) {
+    // e = (I - Z0 Z0')(x - c0): violation of the stage-0 equalities; x, e in shared memory
+    VB_DEV void eq0_violation(const double *x, double *e) {
+        FOR_LANES
+        if (lane < NX) {
             double a = 0.0;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) a += s.Z0[i][c] * (x[i] - s.c0[i]);
-            y[c] = a;
+            for (int i = 0; i < NX; ++i) a += s.Z0[i][lane] * (x[i] - s.c0[i]);
+            s.vt[lane] = a;
         }
+        END_LANES
+        FOR_LANES
+        if (lane < NX) {
+            double a = x[lane] - s.c0[lane];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) {
-            double a = x[i] - s.c0[i];
-#pragma unroll
-            for (int c = 0; c < NX; ++c) a -= s.Z0[i][c] * y[c];
-            e[i] = a;
+            for (int c = 0; c < NX; ++c) a -= s.Z0[lane][c] * s.vt[c];
+            e[lane] = a;
         }
+        END_LANES
     }
-    // v <- Z0 Z0' v (uniform)
-    VB_DEV void proj0(double *v) const {
-        double y[NX], out[NX];
-#pragma unroll
-        for (int c = 0; c < NX; ++c) {
+    // v <- Z0 Z0' v; v in shared memory
+    VB_DEV void proj0(double *v) {
+        FOR_LANES
+        if (lane < NX) {
             double a = 0.0;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) a += s.Z0[i][c] * v[i];
-            y[c] = a;
+            for (int i = 0; i < NX; ++i) a += s.Z0[i][lane] * v[i];
+            s.vt[lane] = a;
         }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
+        END_LANES
+        FOR_LANES
+        if (lane < NX) {
             double a = 0.0;
 #pragma unroll
-            for (int c = 0; c < NX; ++c) a += s.Z0[i][c] * y[c];
-            out[i] = a;
+            for (int c = 0; c < NX; ++c) a += s.Z0[lane][c] * s.vt[c];
+            v[lane] = a;
         }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) v[i] = out[i];
+        END_LANES
     }
 
     // ---------------------------------------------------------------- problem load / store
@@ -240,6 +272,9 @@ struct WarpSolver {
         END_LANES
     }
 
+    // ---------------------------------------------------------------- stage-record access
+    VB_DEV double *rec(int k) const { return w.SR + (size_t)k * R::SIZE; }
+
     // ---------------------------------------------------------------- linearisation
     // ERK4 with forward tangents: NZ+1 lanes per shooting interval, lane `dir` < NZ carries the
     // tangent d/dz_dir (one column of [B A]), lane NZ the value (gap).  32/(NZ+1) intervals per pass.
@@ -258,7 +293,7 @@ struct WarpSolver {
                 for (int i = 0; i < NX; ++i) x[i] = {z[NU + i], dir == NU + i ? 1.0 : 0.0};
                 rk4_step<NQ, Dual1>(x, u, s.h, xn);
                 if (dir < NZ) {
-                    double *col = w.BAT + ((size_t)k * NZ + dir) * NX;
+                    double *col = rec(k) + R::BAT + dir * NX;
 #pragma unroll
                     for (int i = 0; i < NX; ++i) col[i] = xn[i].d;
                 } else {
@@ -290,7 +325,7 @@ struct WarpSolver {
                 double z = w.Z[idx];
                 r = cost_g(k, i, z);
                 if (k < N) {
-                    const double *col = w.BAT + (size_t)idx * NX, *pi = w.PI + k * NX;
+                    const double *col = rec(k) + R::BAT + i * NX, *pi = w.PI + k * NX;
 #pragma unroll
                     for (int m = 0; m < NX; ++m) r += col[m] * pi[m];
                 }
@@ -320,19 +355,20 @@ struct WarpSolver {
         }
         L(a_s) = vs, L(a_e) = ve, L(a_i) = vi, L(a_c) = vc, L(bad) = nb;
         END_LANES
-        double r0[NX], x0[NX], e[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) r0[i] = w.RG[NU + i], x0[i] = w.Z[NU + i];
-        proj0(r0);
-        eq0_violation(x0, e);
+        FOR_LANES
+        if (lane < NX) s.va[lane] = w.RG[NU + lane], s.vb[lane] = w.Z[NU + lane];
+        END_LANES
+        proj0(s.va);
+        eq0_violation(s.vb, s.vc);
         rs = WARP_MAX(a_s), re = WARP_MAX(a_e), ri = WARP_MAX(a_i), rc = WARP_MAX(a_c);
         bool nan = WARP_ANY(bad);
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-            nan |= (r0[i] != r0[i]);
-            rs = fmax(rs, fabs(r0[i]));
-            ri = fmax(ri, fabs(e[i]));
+            nan |= (s.va[i] != s.va[i]);
+            rs = fmax(rs, fabs(s.va[i]));
+            ri = fmax(ri, fabs(s.vc[i]));
         }
+        UNIFORM_SYNC();
         return !nan;
     }
 
@@ -370,24 +406,19 @@ struct WarpSolver {
         }
         for (int idx = lane; idx < N * NX; idx += 32) w.PIQ[idx] = 0.0;
         END_LANES
-        double x0[NX], e[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) x0[i] = w.Z[NU + i] + w.DZ[NU + i];
-        eq0_violation(x0, e);
-        UNIFORM_SYNC();  // the loads above precede the stores below
         FOR_LANES
-        if (lane < NX) {
-            double ev = 0.0;
-#pragma unroll
-            for (int i = 0; i < NX; ++i)
-                if (i == lane) ev = e[i];
-            w.DZ[NU + lane] -= ev;
-        }
+        if (lane < NX) s.vb[lane] = w.Z[NU + lane] + w.DZ[NU + lane];
+        END_LANES
+        eq0_violation(s.vb, s.vc);
+        FOR_LANES
+        if (lane < NX) w.DZ[NU + lane] -= s.vc[lane];
         END_LANES
     }
 
     // ---------------------------------------------------------------- QP: residuals
-    // RG (stationarity), RB (dynamics), RD (bounds), RMB (lam*t); returns mu, norms by reference.
+    // RG (stationarity), RB (dynamics, into the stage records), RD (bounds), RMB (lam*t), and the
+    // Newton-system data of the predictor: HH = hd + lam/t, RR = RG + (lam*t - lam*rd)/t (signed).
+    // Returns mu, norms by reference.
     VB_DEV double qp_residuals(double &ng, double &nb_, double &nd, double &nm, bool &nan) {
         const int N = s.N;
         LV(double, a_g);
@@ -402,9 +433,11 @@ struct WarpSolver {
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             double v = w.DZ[idx];
-            double r = cost_h(k, i) * v + cost_g(k, i, w.Z[idx]);
+            double hh = cost_h(k, i) + o.qp_reg_prim, bar = 0.0;
+            double r = (hh - o.qp_reg_prim) * v + cost_g(k, i, w.Z[idx]);
+            double *rk = rec(k);
             if (k < N) {
-                const double *col = w.BAT + (size_t)idx * NX, *pi = w.PIQ + k * NX;
+                const double *col = rk + R::BAT + i * NX, *pi = w.PIQ + k * NX;
 #pragma unroll
                 for (int m = 0; m < NX; ++m) r += col[m] * pi[m];
             }
@@ -422,11 +455,16 @@ struct WarpSolver {
                 vd = fmax(vd, fmax(fabs(dl), fabs(du)));
                 vm = fmax(vm, fmax(fabs(ml), fabs(mu_)));
                 mu += ml + mu_;
+                double itl = 1.0 / tl, itu = 1.0 / tu;
+                hh += ll * itl + lu * itu;
+                bar = (ml - ll * dl) * itl - (mu_ - lu * du) * itu;
             } else {
                 w.RD[c] = 0.0, w.RD[c + NZ] = 0.0, w.RMB[c] = 0.0, w.RMB[c + NZ] = 0.0;
                 if (k == N) r = 0.0;
             }
             w.RG[idx] = r;
+            rk[R::HH + i] = hh;
+            rk[R::RR + i] = r + bar;
             if (!(k == 0 && i >= NU)) {
                 nb |= (r != r);
                 vg = fmax(vg, fabs(r));
@@ -435,134 +473,131 @@ struct WarpSolver {
         for (int idx = lane; idx < N * NX; idx += 32) {
             int k = idx / NX, i = idx - k * NX;
             double a = w.BD[idx] - w.DZ[(k + 1) * NZ + NU + i];
-            const double *dz = w.DZ + k * NZ, *bat = w.BAT + (size_t)k * NZ * NX + i;
+            const double *dz = w.DZ + k * NZ, *bat = rec(k) + R::BAT + i;
 #pragma unroll
             for (int j = 0; j < NZ; ++j) a += bat[j * NX] * dz[j];
-            w.RB[idx] = a;
+            rec(k)[R::RB + i] = a;
             nb |= (a != a);
             vb = fmax(vb, fabs(a));
         }
         L(a_g) = vg, L(a_b) = vb, L(a_d) = vd, L(a_m) = vm, L(a_mu) = mu, L(bad) = nb;
         END_LANES
-        double r0[NX], x0[NX], e[NX], eN[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-            r0[i] = w.RG[NU + i];
-            x0[i] = w.Z[NU + i] + w.DZ[NU + i];
-            eN[i] = ((s.fixedN >> i) & 1) ? w.Z[N * NZ + NU + i] + w.DZ[N * NZ + NU + i] - s.cN[i] : 0.0;
+        FOR_LANES
+        if (lane < NX) {
+            s.va[lane] = w.RG[NU + lane];
+            s.vb[lane] = w.Z[NU + lane] + w.DZ[NU + lane];
+            s.eN[lane] = ((s.fixedN >> lane) & 1)
+                             ? w.Z[N * NZ + NU + lane] + w.DZ[N * NZ + NU + lane] - s.cN[lane]
+                             : 0.0;
         }
-        proj0(r0);
-        eq0_violation(x0, e);
+        END_LANES
+        proj0(s.va);
+        eq0_violation(s.vb, s.e0);
         ng = WARP_MAX(a_g), nb_ = WARP_MAX(a_b), nd = WARP_MAX(a_d), nm = WARP_MAX(a_m);
         double mu = WARP_SUM(a_mu);
         nan = WARP_ANY(bad);
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-            nan |= (r0[i] != r0[i]);
-            ng = fmax(ng, fabs(r0[i]));
-            nb_ = fmax(nb_, fmax(fabs(e[i]), fabs(eN[i])));
+            nan |= (s.va[i] != s.va[i]);
+            ng = fmax(ng, fabs(s.va[i]));
+            nb_ = fmax(nb_, fmax(fabs(s.e0[i]), fabs(s.eN[i])));
         }
-        UNIFORM_SYNC();
         FOR_LANES
         if (lane < NX) {
-            double rv = 0, ev = 0, env = 0;
-#pragma unroll
-            for (int i = 0; i < NX; ++i)
-                if (i == lane) rv = r0[i], ev = e[i], env = eN[i];
+            double rv = s.va[lane], rraw = w.RG[NU + lane];
             w.RG[NU + lane] = rv;
-            s.e0[lane] = ev, s.eN[lane] = env;
+            rec(0)[R::RR + NU + lane] += rv - rraw;  // the stage-0 state gradient is the projected one
         }
         END_LANES
+        PROXY_FENCE();  // the sweeps read the records through TMA
         return s.nact ? mu / (2.0 * s.nact) : 0.0;
     }
 
-    // effective Hessian diagonal / gradient of component (k, i) for the Newton system
-    VB_DEV void eff(int k, int i, const double *RMs, double &hh, double &rr) const {
-        hh = cost_h(k, i) + o.qp_reg_prim;
-        rr = w.RG[k * NZ + i];
-        if (active(k, i)) {
-            int c = k * NC + i;
-            double ll = w.LAMQ[c], lu = w.LAMQ[c + NZ], tl = w.TQ[c], tu = w.TQ[c + NZ];
-            hh += ll / tl + lu / tu;
-            rr += (RMs[c] - ll * w.RD[c]) / tl - (RMs[c + NZ] - lu * w.RD[c + NZ]) / tu;
-        }
+    // gradient of the Newton system in the three solve modes: 0 predictor, 1 corrector
+    // (centering + second-order term), 2 centering only
+    VB_DEV double rhs_of(const double *r, int i, int mode, double sm) const {
+        if (mode == 0) return r[R::RR + i];
+        return (mode == 1 ? r[R::Q1 + i] : r[R::RR + i]) - sm * r[R::Q2 + i];
     }
 
     // ---------------------------------------------------------------- Riccati: backward sweep
-    // factor = true: factorise and solve; false: re-use the stored factors with a new rhs.
-    // Ends with the stage-0 step in s.dz[NU..].  Returns false on a singular terminal block / NaN.
-    VB_DEV bool backward(bool factor, const double *RMs) {
+    // mode 0: factorise + solve the predictor; mode 1/2: re-use the factors with the corrector /
+    // centering-only gradient.  Stage records arrive through the TMA ring (RING_DEPTH stages ahead).
+    // Ends with the stage-0 step in s.dx[0].  Returns false on a singular terminal block.
+    VB_DEV bool backward(int mode, double sm) {
         const int N = s.N;
-        FOR_LANES
-        if (lane < NX) {
-            double hh, rr;
-            eff(N, NU + lane, RMs, hh, rr);
-            bool fx = (s.fixedN >> lane) & 1;
-            s.hhN[lane] = fx ? 0.0 : hh;
-            s.rN[lane] = fx ? 0.0 : rr;
-            s.pvec[lane] = fx ? 0.0 : rr;
-#pragma unroll
-            for (int j = 0; j < NX; ++j) s.P[lane][j] = (j == lane && !fx) ? hh : 0.0;
-        }
-        END_LANES
-        bool ok = true;
-        for (int k = N - 1; k >= 0; --k) {
-            const bool last = (k == N - 1) && s.termfix;
-            double *fac = w.FAC + (size_t)k * FS;
-            // A: stage data to shared memory
+        const bool factor = mode == 0;
+        {
+            const double *rN = rec(N);
             FOR_LANES
-            for (int idx = lane; idx < NZ * NX; idx += 32)
-                (&s.BAT[0][0])[idx] = w.BAT[(size_t)k * NZ * NX + idx];
-            if (lane < NX) s.beta[lane] = w.RB[k * NX + lane];
-            if (lane < NZ) {
-                double hh, rr;
-                eff(k, lane, RMs, hh, rr);
-                s.hh[lane] = hh, s.rr[lane] = rr;
-            }
-            if (!factor) {
-                if (k < N - 1) {
-                    const double *Pn = w.FAC + (size_t)(k + 1) * FS + OFF_P;
-                    for (int idx = lane; idx < NX * NX; idx += 32) (&s.P[0][0])[idx] = Pn[idx];
+            if (lane < NX) {
+                bool fx = (s.fixedN >> lane) & 1;
+                double hh = rN[R::HH + NU + lane], rr = rhs_of(rN, NU + lane, mode, sm);
+                s.hhN[lane] = fx ? 0.0 : hh;
+                s.rN[lane] = fx ? 0.0 : rr;
+                s.pvec[lane] = fx ? 0.0 : rr;
+                if (factor) {
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) s.P[lane][j] = (j == lane && !fx) ? hh : 0.0;
                 }
-                if (last)
-                    for (int idx = lane; idx < NZ * NZ; idx += 32) (&s.M[0][0])[idx] = w.MF[idx];
             }
             END_LANES
-            // B: P+ [B A]  and  t2 = P+ beta + p+
-            FOR_LANES
+        }
+        for (int j = 0; j < RING_DEPTH && j < N; ++j)
+            RING_FETCH(ring, j, s.ring[j], rec(N - 1 - j), R::BYTES);
+        bool ok = true;
+        for (int it = 0; it < N; ++it) {
+            const int k = N - 1 - it, slot = it % RING_DEPTH;
+            const bool last = (it == 0) && s.termfix;
+            RING_WAIT(ring, slot);
+            const double *r = s.ring[slot];
+            double *gk = rec(k), *pp = w.PP + (size_t)k * Work<NQ>::PPS;
             if (factor) {
+                // B: P+ [B A]  and  tb = P+ beta
+                FOR_LANES
                 for (int idx = lane; idx < NZ * NX; idx += 32) {
                     int j = idx / NX, i = idx - j * NX;
                     double a = 0.0;
 #pragma unroll
-                    for (int m = 0; m < NX; ++m) a += s.P[i][m] * s.BAT[j][m];
+                    for (int m = 0; m < NX; ++m) a += s.P[i][m] * r[R::BAT + j * NX + m];
                     s.PBAT[j][i] = a;
                 }
-            }
-            if (lane < NX) {
-                double a = s.pvec[lane];
+                if (lane < NX) {
+                    double a = 0.0;
 #pragma unroll
-                for (int m = 0; m < NX; ++m) a += s.P[lane][m] * s.beta[m];
-                s.t2[lane] = a;
+                    for (int m = 0; m < NX; ++m) a += s.P[lane][m] * r[R::RB + m];
+                    s.tb[lane] = a;
+                }
+                END_LANES
             }
-            END_LANES
-            // C: M = H + [B A]' P+ [B A]  and  m = r + [B A]' t2
+            // C: M = H + [B A]' P+ [B A]  and  m = r + [B A]'(P+ beta) + [B A]' p+
             FOR_LANES
             if (factor) {
                 for (int idx = lane; idx < TRI; idx += 32) {
                     int a_ = 0;
                     while ((a_ + 1) * (a_ + 2) / 2 <= idx) ++a_;
                     int b_ = idx - a_ * (a_ + 1) / 2;
-                    double a = (a_ == b_) ? s.hh[a_] : 0.0;
+                    double a = (a_ == b_) ? r[R::HH + a_] : 0.0;
 #pragma unroll
-                    for (int m = 0; m < NX; ++m) a += s.BAT[a_][m] * s.PBAT[b_][m];
+                    for (int m = 0; m < NX; ++m) a += r[R::BAT + a_ * NX + m] * s.PBAT[b_][m];
                     s.M[a_][b_] = a, s.M[b_][a_] = a;
                 }
+            } else if (last) {
+                for (int idx = lane; idx < NZ * NZ; idx += 32) (&s.M[0][0])[idx] = w.MF[idx];
             }
             if (lane < NZ) {
-                double a = s.rr[lane];
+                double mb;
+                if (factor) {
+                    mb = 0.0;
 #pragma unroll
-                for (int i = 0; i < NX; ++i) a += s.BAT[lane][i] * s.t2[i];
+                    for (int i = 0; i < NX; ++i) mb += r[R::BAT + lane * NX + i] * s.tb[i];
+                    gk[R::MB + lane] = mb;
+                } else {
+                    mb = r[R::MB + lane];
+                }
+                double a = rhs_of(r, lane, mode, sm) + mb;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) a += r[R::BAT + lane * NX + i] * s.pvec[i];
                 s.m[lane] = a;
             }
             END_LANES
@@ -588,9 +623,9 @@ struct WarpSolver {
                 } else {
 #pragma unroll
                     for (int i = 0; i < NU; ++i) {
-                        di[i] = fac[i * NU + i];
+                        di[i] = r[R::LUU + i * NU + i];
 #pragma unroll
-                        for (int c = 0; c < i; ++c) Lu[i][c] = fac[i * NU + c];
+                        for (int c = 0; c < i; ++c) Lu[i][c] = r[R::LUU + i * NU + c];
                     }
                 }
 #pragma unroll
@@ -616,10 +651,10 @@ struct WarpSolver {
 #pragma unroll
                         for (int c = 0; c < NU; ++c) a -= li[c] * lj[c];
                         s.P[i][j] = a;
-                        fac[OFF_P + idx] = a;
+                        pp[idx] = a;
                         if (j == 0) {
 #pragma unroll
-                            for (int c = 0; c < NU; ++c) fac[OFF_LXU + i * NU + c] = li[c];
+                            for (int c = 0; c < NU; ++c) gk[R::LXU + i * NU + c] = li[c];
                         }
                     }
                     if (lane == 0) {
@@ -627,7 +662,7 @@ struct WarpSolver {
                         for (int i = 0; i < NU; ++i)
 #pragma unroll
                             for (int c = 0; c < NU; ++c)
-                                fac[i * NU + c] = (c == i) ? di[i] : (c < i ? Lu[i][c] : 0.0);
+                                gk[R::LUU + i * NU + c] = (c == i) ? di[i] : (c < i ? Lu[i][c] : 0.0);
                     }
                 }
                 if (lane < NX) {
@@ -642,113 +677,101 @@ struct WarpSolver {
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < NU; ++c) li[c] = fac[OFF_LXU + lane * NU + c];
+                        for (int c = 0; c < NU; ++c) li[c] = r[R::LXU + lane * NU + c];
                     }
                     double p = s.m[NU + lane];
 #pragma unroll
                     for (int c = 0; c < NU; ++c) p -= li[c] * y[c];
                     s.pvec[lane] = p;
-                    w.PV[k * NX + lane] = p;
+                    pp[NX * NX + lane] = p;
                 }
                 if (lane < NU) {
                     double yv = 0.0;
 #pragma unroll
                     for (int c = 0; c < NU; ++c)
                         if (c == lane) yv = y[c];
-                    w.YV[k * NU + lane] = yv;
+                    gk[R::YV + lane] = yv;
                 }
                 END_LANES
             } else {
                 // terminal equalities: G du + Gx dx + beta_v = -eN on the velocity rows determines
                 // du = K dx + k0; the value function is the restriction of M to that manifold.
-                double Gi[NU][NU], K[NU][NX], k0[NU], tmp[NZ];
+                double Gi[NU][NU], k0[NU];
                 if (factor) {
                     double G[NU][NU];
 #pragma unroll
                     for (int a = 0; a < NU; ++a)
 #pragma unroll
-                        for (int b = 0; b < NU; ++b) G[a][b] = s.BAT[b][NQ + a];
+                        for (int b = 0; b < NU; ++b) G[a][b] = r[R::BAT + b * NX + NQ + a];
                     ok = inverse_small(G, Gi) && ok;
+                } else {
 #pragma unroll
                     for (int a = 0; a < NU; ++a)
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) {
-                            double v = 0.0;
-#pragma unroll
-                            for (int b = 0; b < NU; ++b) v -= Gi[a][b] * s.BAT[NU + j][NQ + b];
-                            K[a][j] = v;
-                        }
-                } else {
-#pragma unroll
-                    for (int a = 0; a < NU; ++a) {
-#pragma unroll
-                        for (int b = 0; b < NU; ++b) Gi[a][b] = fac[a * NU + b];
-#pragma unroll
-                        for (int j = 0; j < NX; ++j) K[a][j] = fac[OFF_LXU + j * NU + a];
-                    }
+                        for (int b = 0; b < NU; ++b) Gi[a][b] = r[R::LUU + a * NU + b];
                 }
 #pragma unroll
                 for (int a = 0; a < NU; ++a) {
                     double v = 0.0;
 #pragma unroll
-                    for (int b = 0; b < NU; ++b) v -= Gi[a][b] * (s.eN[NQ + b] + s.beta[NQ + b]);
+                    for (int b = 0; b < NU; ++b) v -= Gi[a][b] * (s.eN[NQ + b] + r[R::RB + NQ + b]);
                     k0[a] = v;
                 }
+                FOR_LANES
+                for (int idx = lane; idx < NU * NX; idx += 32) {
+                    int a = idx / NX, j = idx - a * NX;
+                    double v = 0.0;
+                    if (factor) {
 #pragma unroll
-                for (int i = 0; i < NZ; ++i) {
-                    double v = s.m[i];
+                        for (int a2 = 0; a2 < NU; ++a2)
 #pragma unroll
-                    for (int a = 0; a < NU; ++a) v += s.M[i][a] * k0[a];
-                    tmp[i] = v;
+                            for (int b = 0; b < NU; ++b)
+                                if (a2 == a) v -= Gi[a2][b] * r[R::BAT + (NU + j) * NX + NQ + b];
+                    } else {
+                        v = r[R::LXU + j * NU + a];
+                    }
+                    s.K[a][j] = v;
                 }
+                if (lane < NZ) {
+                    double v = s.m[lane];
+#pragma unroll
+                    for (int a = 0; a < NU; ++a) v += s.M[lane][a] * k0[a];
+                    s.tz[lane] = v;
+                }
+                END_LANES
                 FOR_LANES
                 if (factor) {
                     for (int idx = lane; idx < NX * NX; idx += 32) {
                         int i = idx / NX, j = idx - i * NX;
-                        double ki[NU], kj[NU];
-#pragma unroll
-                        for (int a = 0; a < NU; ++a) {
-                            double x1 = 0, x2 = 0;
-#pragma unroll
-                            for (int jj = 0; jj < NX; ++jj) {
-                                if (jj == i) x1 = K[a][jj];
-                                if (jj == j) x2 = K[a][jj];
-                            }
-                            ki[a] = x1, kj[a] = x2;
-                        }
                         double a = s.M[NU + i][NU + j];
 #pragma unroll
                         for (int c = 0; c < NU; ++c) {
-                            a += ki[c] * s.M[c][NU + j] + s.M[NU + i][c] * kj[c];
+                            double ki = s.K[c][i];
+                            a += ki * s.M[c][NU + j] + s.M[NU + i][c] * s.K[c][j];
 #pragma unroll
-                            for (int c2 = 0; c2 < NU; ++c2) a += ki[c] * s.M[c][c2] * kj[c2];
+                            for (int c2 = 0; c2 < NU; ++c2) a += ki * s.M[c][c2] * s.K[c2][j];
                         }
-                        fac[OFF_P + idx] = a;
-                        if (j == 0) {
-#pragma unroll
-                            for (int c = 0; c < NU; ++c) fac[OFF_LXU + i * NU + c] = ki[c];
-                        }
+                        pp[idx] = a;
                         s.P[i][j] = a;
+                    }
+                    for (int idx = lane; idx < NX * NU; idx += 32) {
+                        int i = idx / NU, c = idx - i * NU;
+                        gk[R::LXU + idx] = s.K[c][i];
                     }
                     for (int idx = lane; idx < NZ * NZ; idx += 32) w.MF[idx] = (&s.M[0][0])[idx];
                     if (lane == 0) {
 #pragma unroll
                         for (int a = 0; a < NU; ++a)
 #pragma unroll
-                            for (int b = 0; b < NU; ++b) fac[a * NU + b] = Gi[a][b];
+                            for (int b = 0; b < NU; ++b) gk[R::LUU + a * NU + b] = Gi[a][b];
                     }
                 }
                 if (lane < NX) {
-                    double p = 0.0;
+                    double p = s.tz[NU + lane];
 #pragma unroll
-                    for (int jj = 0; jj < NX; ++jj)
-                        if (jj == lane) {
-                            p = tmp[NU + jj];
-#pragma unroll
-                            for (int a = 0; a < NU; ++a) p += K[a][jj] * tmp[a];
-                        }
+                    for (int a = 0; a < NU; ++a) p += s.K[a][lane] * s.tz[a];
                     s.pvec[lane] = p;
-                    w.PV[k * NX + lane] = p;
+                    pp[NX * NX + lane] = p;
                 }
                 if (lane < NZ) w.MF[NZ * NZ + lane] = s.m[lane];
                 if (lane < NU) {
@@ -760,104 +783,81 @@ struct WarpSolver {
                 }
                 END_LANES
             }
+            if (it + RING_DEPTH < N) RING_FETCH(ring, slot, s.ring[slot], rec(k - RING_DEPTH), R::BYTES);
         }
         // stage 0:  dx0 = -e0 + Z0 dy,  (Z0'P0 Z0) dy = -Z0'(p0 - P0 e0)
+        if (factor) {
+            // T = P0 Z0 (into s.M as scratch), Pe = P0 e0
+            FOR_LANES
+            for (int idx = lane; idx < NX * NX; idx += 32) {
+                int i = idx / NX, c = idx - i * NX;
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a += s.P[i][j] * s.Z0[j][c];
+                s.M[i][c] = a;
+            }
+            if (lane < NX) {
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a += s.P[lane][j] * s.e0[j];
+                s.Pe[lane] = a;
+            }
+            END_LANES
+            FOR_LANES
+            for (int idx = lane; idx < NX * NX; idx += 32) {
+                int a_ = idx / NX, b_ = idx - a_ * NX;
+                double a = 0.0;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) a += s.Z0[i][a_] * s.M[i][b_];
+                s.Lz[a_][b_] = a;
+            }
+            END_LANES
+            // right-looking Cholesky of the (zero padded) reduced Hessian, one column per step
+#pragma unroll 1
+            for (int j = 0; j < NX; ++j) {
+                double d = s.Lz[j][j];
+                double di = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
+                UNIFORM_SYNC();
+                FOR_LANES
+                if (lane > j && lane < NX) s.Lz[lane][j] *= di;
+                if (lane == j) s.dzi[j] = di;
+                END_LANES
+                FOR_LANES
+                for (int idx = lane; idx < NX * NX; idx += 32) {
+                    int i = idx / NX, c = idx - i * NX;
+                    if (c > j && i >= c) s.Lz[i][c] -= s.Lz[i][j] * s.Lz[c][j];
+                }
+                END_LANES
+            }
+        }
         {
-            const double *P0 = w.FAC + OFF_P;
-            double Lz[NX][NX], dzi[NX], Pe[NX], rhs[NX], y[NX], dy[NX];
-            if (factor) {
-                double T[NX][NX];  // P0 Z0
-#pragma unroll
-                for (int i = 0; i < NX; ++i)
-#pragma unroll
-                    for (int c = 0; c < NX; ++c) {
-                        double a = 0.0;
-#pragma unroll
-                        for (int j = 0; j < NX; ++j) a += P0[i * NX + j] * s.Z0[j][c];
-                        T[i][c] = a;
-                    }
-#pragma unroll
-                for (int a_ = 0; a_ < NX; ++a_)
-#pragma unroll
-                    for (int b_ = 0; b_ <= a_; ++b_) {
-                        double a = 0.0;
-#pragma unroll
-                        for (int i = 0; i < NX; ++i) a += s.Z0[i][a_] * T[i][b_];
-                        Lz[a_][b_] = a;
-                    }
-#pragma unroll
-                for (int j = 0; j < NX; ++j) {
-                    double d = Lz[j][j];
-#pragma unroll
-                    for (int c = 0; c < j; ++c) d -= Lz[j][c] * Lz[j][c];
-                    dzi[j] = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
-#pragma unroll
-                    for (int i = j + 1; i < NX; ++i) {
-                        double a = Lz[i][j];
-#pragma unroll
-                        for (int c = 0; c < j; ++c) a -= Lz[i][c] * Lz[j][c];
-                        Lz[i][j] = a * dzi[j];
-                    }
-                    Lz[j][j] = dzi[j];
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NX; ++i) {
-#pragma unroll
-                    for (int c = 0; c <= i; ++c) Lz[i][c] = s.Lz[i][c];
-                    dzi[i] = Lz[i][i];
-                }
-            }
+            double y[NX], dy[NX];
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 double a = 0.0;
 #pragma unroll
-                for (int j = 0; j < NX; ++j) a += P0[i * NX + j] * s.e0[j];
-                Pe[i] = a;
-            }
+                for (int m = 0; m < NX; ++m) a -= s.Z0[m][i] * (s.pvec[m] - s.Pe[m]);
 #pragma unroll
-            for (int c = 0; c < NX; ++c) {
-                double a = 0.0;
-#pragma unroll
-                for (int i = 0; i < NX; ++i) a -= s.Z0[i][c] * (s.pvec[i] - Pe[i]);
-                rhs[c] = a;
-            }
-#pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                double a = rhs[i];
-#pragma unroll
-                for (int j = 0; j < i; ++j) a -= Lz[i][j] * y[j];
-                y[i] = a * dzi[i];
+                for (int j = 0; j < i; ++j) a -= s.Lz[i][j] * y[j];
+                y[i] = a * s.dzi[i];
             }
 #pragma unroll
             for (int i = NX - 1; i >= 0; --i) {
                 double a = y[i];
 #pragma unroll
-                for (int j = i + 1; j < NX; ++j) a -= Lz[j][i] * dy[j];
-                dy[i] = a * dzi[i];
+                for (int j = i + 1; j < NX; ++j) a -= s.Lz[j][i] * dy[j];
+                dy[i] = a * s.dzi[i];
             }
             FOR_LANES
             if (lane < NX) {
-                double a = 0.0;
+                double a = -s.e0[lane];
 #pragma unroll
-                for (int i = 0; i < NX; ++i)
-                    if (i == lane) {
-                        a = -s.e0[i];
-#pragma unroll
-                        for (int c = 0; c < NX; ++c) a += s.Z0[i][c] * dy[c];
-                    }
-                s.dz[NU + lane] = a;
-                if (factor) {
-#pragma unroll
-                    for (int i = 0; i < NX; ++i)
-                        if (i == lane) {
-#pragma unroll
-                            for (int c = 0; c <= i; ++c) s.Lz[i][c] = Lz[i][c];
-                        }
-                }
+                for (int c = 0; c < NX; ++c) a += s.Z0[lane][c] * dy[c];
+                s.dx[0][lane] = a;
             }
             END_LANES
         }
+        PROXY_FENCE();  // the forward sweep re-reads the records through TMA
         return ok;
     }
 
@@ -891,151 +891,145 @@ struct WarpSolver {
         }
     }
 
-    // step of one bound constraint and its contribution to the maximum step length
-    VB_DEV void con_step(int k, int c, double dvv, const double *RMs, double &amin) {
-        int sgn = c >= NZ, i = c - sgn * NZ;
-        if (!active(k, i)) return;
-        int cc = k * NC + c;
-        double lam = w.LAMQ[cc], t = w.TQ[cc];
-        double dtt = (sgn ? -dvv : dvv) - w.RD[cc];
-        double dl = -(RMs[cc] + lam * dtt) / t;
-        w.DT[cc] = dtt, w.DLAM[cc] = dl;
-        if (dtt < 0.0) amin = fmin(amin, -t / dtt);
-        if (dl < 0.0) amin = fmin(amin, -lam / dl);
-    }
-
     // ---------------------------------------------------------------- Riccati: forward sweep
-    // DV, DPI, DT, DLAM from the factors; returns the maximum step to the boundary.
-    VB_DEV double forward(const double *RMs) {
+    // DV from the factors: du_k = -Luu^-T (y_k + Lxu' dx_k), dx_{k+1} = [B A] dz_k + beta_k.  One
+    // lane region per stage: every lane forms du redundantly in registers, lanes < nx form dx+.
+    VB_DEV void forward() {
         const int N = s.N;
-        LV(double, amin);
-        FOR_LANES
-        L(amin) = 1.0;
-        END_LANES
+        for (int j = 0; j < RING_DEPTH && j < N; ++j) RING_FETCH(ring, j, s.ring[j], rec(j), R::BYTES);
         for (int k = 0; k < N; ++k) {
+            const int slot = k % RING_DEPTH, cur = k & 1;
             const bool last = (k == N - 1) && s.termfix;
-            const double *fac = w.FAC + (size_t)k * FS;
-            FOR_LANES
-            for (int idx = lane; idx < NZ * NX; idx += 32)
-                (&s.BAT[0][0])[idx] = w.BAT[(size_t)k * NZ * NX + idx];
-            if (lane < NX) s.beta[lane] = w.RB[k * NX + lane];
-            if (k + 1 < N) {
-                const double *Pn = w.FAC + (size_t)(k + 1) * FS + OFF_P;
-                for (int idx = lane; idx < NX * NX; idx += 32) (&s.P[0][0])[idx] = Pn[idx];
-                if (lane < NX) s.pvec[lane] = w.PV[(k + 1) * NX + lane];
-            } else if (lane < NX) {
-#pragma unroll
-                for (int j = 0; j < NX; ++j) s.P[lane][j] = (j == lane) ? s.hhN[lane] : 0.0;
-                s.pvec[lane] = s.rN[lane];
-            }
-            END_LANES
+            RING_WAIT(ring, slot);
+            const double *r = s.ring[slot];
             double du[NU];
             if (!last) {
                 double t[NU];
 #pragma unroll
                 for (int c = 0; c < NU; ++c) {
-                    double a = w.YV[k * NU + c];
+                    double a = r[R::YV + c];
 #pragma unroll
-                    for (int j = 0; j < NX; ++j) a += fac[OFF_LXU + j * NU + c] * s.dz[NU + j];
+                    for (int j = 0; j < NX; ++j) a += r[R::LXU + j * NU + c] * s.dx[cur][j];
                     t[c] = a;
                 }
 #pragma unroll
                 for (int c = NU - 1; c >= 0; --c) {
                     double a = -t[c];
 #pragma unroll
-                    for (int c2 = c + 1; c2 < NU; ++c2) a -= fac[c2 * NU + c] * du[c2];
-                    du[c] = a * fac[c * NU + c];
+                    for (int c2 = c + 1; c2 < NU; ++c2) a -= r[R::LUU + c2 * NU + c] * du[c2];
+                    du[c] = a * r[R::LUU + c * NU + c];
                 }
             } else {
 #pragma unroll
                 for (int a_ = 0; a_ < NU; ++a_) {
                     double a = w.MF[NZ * NZ + NZ + a_];
 #pragma unroll
-                    for (int j = 0; j < NX; ++j) a += fac[OFF_LXU + j * NU + a_] * s.dz[NU + j];
+                    for (int j = 0; j < NX; ++j) a += r[R::LXU + j * NU + a_] * s.dx[cur][j];
                     du[a_] = a;
                 }
             }
             FOR_LANES
-            if (lane < NU) {
+            if (lane < NX) {
+                double a = r[R::RB + lane];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) a += r[R::BAT + (NU + j) * NX + lane] * s.dx[cur][j];
+#pragma unroll
+                for (int c = 0; c < NU; ++c) a += r[R::BAT + c * NX + lane] * du[c];
+                s.dx[cur ^ 1][lane] = a;
+                w.DV[k * NZ + NU + lane] = s.dx[cur][lane];
+            } else if (lane < NZ) {
                 double v = 0.0;
 #pragma unroll
                 for (int c = 0; c < NU; ++c)
-                    if (c == lane) v = du[c];
-                s.dz[lane] = v;
-                w.DV[k * NZ + lane] = v;
-            } else if (lane < NZ) {
-                w.DV[k * NZ + lane] = s.dz[lane];
+                    if (c == lane - NX) v = du[c];
+                w.DV[k * NZ + lane - NX] = v;
             }
             END_LANES
-            FOR_LANES
-            if (lane < NX) {
-                double a = s.beta[lane];
-#pragma unroll
-                for (int j = 0; j < NZ; ++j) a += s.BAT[j][lane] * s.dz[j];
-                s.dxn[lane] = a;
-            } else if (lane < NX + NC) {
-                int c = lane - NX;
-                con_step(k, c, s.dz[c >= NZ ? c - NZ : c], RMs, L(amin));
-            }
-            END_LANES
-            double nuv[NU];
             if (last) {
                 // multiplier of the eliminated velocity rows from the u-stationarity of the last stage
-                double tu[NU];
+                double tu[NU], nuv[NU];
 #pragma unroll
                 for (int a_ = 0; a_ < NU; ++a_) {
                     double a = w.MF[NZ * NZ + a_];
 #pragma unroll
-                    for (int j = 0; j < NZ; ++j) a += w.MF[a_ * NZ + j] * s.dz[j];
+                    for (int j = 0; j < NU; ++j) a += w.MF[a_ * NZ + j] * du[j];
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) a += w.MF[a_ * NZ + NU + j] * s.dx[cur][j];
                     tu[a_] = a;
                 }
 #pragma unroll
                 for (int b = 0; b < NU; ++b) {
                     double a = 0.0;
 #pragma unroll
-                    for (int a_ = 0; a_ < NU; ++a_) a -= fac[a_ * NU + b] * tu[a_];
+                    for (int a_ = 0; a_ < NU; ++a_) a -= r[R::LUU + a_ * NU + b] * tu[a_];
                     nuv[b] = a;
                 }
-            }
-            UNIFORM_SYNC();
-            FOR_LANES
-            if (lane < NX) {
-                double a = s.pvec[lane];
+                FOR_LANES
+                if (lane < NU) {
+                    double v = 0.0;
 #pragma unroll
-                for (int m = 0; m < NX; ++m) a += s.P[lane][m] * s.dxn[m];
-                if (last && lane >= NQ) {
-#pragma unroll
-                    for (int b = 0; b < NU; ++b)
-                        if (b == lane - NQ) a = nuv[b];
+                    for (int c = 0; c < NU; ++c)
+                        if (c == lane) v = nuv[c];
+                    s.nuv[NQ + lane] = v;
                 }
-                w.DPI[k * NX + lane] = a;
-                s.dz[NU + lane] = s.dxn[lane];
+                END_LANES
             }
-            END_LANES
+            if (k + RING_DEPTH < N) RING_FETCH(ring, slot, s.ring[slot], rec(k + RING_DEPTH), R::BYTES);
         }
         FOR_LANES
-        if (lane < NZ) w.DV[N * NZ + lane] = lane < NU ? 0.0 : s.dz[lane];
-        for (int c = lane; c < NC; c += 32) {
-            int i = c >= NZ ? c - NZ : c;
-            con_step(N, c, i < NU ? 0.0 : s.dz[i], RMs, L(amin));
-        }
+        if (lane < NZ) w.DV[N * NZ + lane] = lane < NU ? 0.0 : s.dx[N & 1][lane - NU];
         END_LANES
-        return WARP_MIN(amin);
     }
 
-    VB_DEV double mu_at(double alpha) {
+    // ---------------------------------------------------------------- constraint pass
+    // Steps of the slacks and multipliers from DV, the maximum step to the boundary, and the three
+    // sums that give mu(alpha) = (S0 + alpha S1 + alpha^2 S2) / nc.  mode 0 (predictor) also stores
+    // the second-order products and the corrector gradient pieces Q1, Q2; modes 1/2 store DT, DLAM.
+    VB_DEV double con_pass(int mode, double sm, double &S0, double &S1, double &S2) {
         const int N = s.N;
-        LV(double, acc);
+        LV(double, amin);
+        LV(double, a0);
+        LV(double, a1);
+        LV(double, a2);
         FOR_LANES
-        double a = 0.0;
-        for (int idx = lane; idx < (N + 1) * NC; idx += 32) {
-            int k = idx / NC, c = idx - k * NC, i = c >= NZ ? c - NZ : c;
-            if (active(k, i)) a += (w.LAMQ[idx] + alpha * w.DLAM[idx]) * (w.TQ[idx] + alpha * w.DT[idx]);
+        double al = 1.0, s0 = 0, s1 = 0, s2 = 0;
+        for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
+            int k = idx / NZ, i = idx - k * NZ;
+            double *rk = rec(k);
+            double q1 = 0.0, q2 = 0.0;
+            if (active(k, i)) {
+                double dvv = w.DV[idx];
+#pragma unroll
+                for (int sd = 0; sd < 2; ++sd) {
+                    int c = k * NC + sd * NZ + i;
+                    double lam = w.LAMQ[c], t = w.TQ[c], rm = w.RMB[c];
+                    if (mode == 1) rm += w.RM[c] - sm;
+                    if (mode == 2) rm -= sm;
+                    double dtt = (sd ? -dvv : dvv) - w.RD[c];
+                    double it = 1.0 / t;
+                    double dl = -(rm + lam * dtt) * it;
+                    // ratio test; the division only when this constraint tightens the step
+                    if (dtt < 0.0 && t + al * dtt < 0.0) al = fmin(al, -t / dtt);
+                    if (dl < 0.0 && lam + al * dl < 0.0) al = fmin(al, -lam / dl);
+                    s0 += lam * t, s1 += lam * dtt + t * dl, s2 += dtt * dl;
+                    if (mode == 0) {
+                        double pr = dtt * dl;
+                        w.RM[c] = pr;
+                        q1 += sd ? -pr * it : pr * it;
+                        q2 += sd ? -it : it;
+                    } else {
+                        w.DT[c] = dtt, w.DLAM[c] = dl;
+                    }
+                }
+            }
+            if (mode == 0) rk[R::Q1 + i] = rk[R::RR + i] + q1, rk[R::Q2 + i] = q2;
         }
-        L(acc) = a;
+        L(amin) = al, L(a0) = s0, L(a1) = s1, L(a2) = s2;
         END_LANES
-        double tot = WARP_SUM(acc);
-        return s.nact ? tot / (2.0 * s.nact) : 0.0;
+        S0 = WARP_SUM(a0), S1 = WARP_SUM(a1), S2 = WARP_SUM(a2);
+        double alpha = WARP_MIN(amin);
+        if (mode == 0) PROXY_FENCE();
+        return alpha;
     }
 
     // ---------------------------------------------------------------- IPM
@@ -1043,48 +1037,60 @@ struct WarpSolver {
     VB_DEV int ipm_solve(int &iters) {
         const int N = s.N;
         qp_init();
-        double rg, rb, rd, rm, alpha = 1.0;
+        double rg = 0, rb = 0, rd = 0, rm = 0, alpha = 1.0, mu = 0.0;
         bool nan = false, ok = true;
-        double mu = qp_residuals(rg, rb, rd, rm, nan);
+        const double nc = 2.0 * s.nact;
         int kk = 0;
-        for (; kk < o.qp_iter_max && alpha > o.qp_alpha_min && !nan &&
-               (rg > o.qp_tol_stat || rb > o.qp_tol_eq || rd > o.qp_tol_ineq || rm > o.qp_tol_comp);
-             ++kk) {
-            // predictor: res_m = lam * t
-            ok = backward(true, w.RMB);
-            if (!ok) break;
-            double a_aff = forward(w.RMB);
-            double m_aff = mu_at(a_aff);
-            double sigma = m_aff / mu;
-            sigma = sigma * sigma * sigma;
-            double sm = sigma * mu;
-            if (sm < o.qp_tau_min) sm = o.qp_tau_min;
-            // centering + corrector: res_m = lam*t + dt_aff*dlam_aff - sigma*mu
-            FOR_LANES
-            for (int idx = lane; idx < (N + 1) * NC; idx += 32) {
-                int k = idx / NC, c = idx - k * NC, i = c >= NZ ? c - NZ : c;
-                w.RM[idx] = active(k, i) ? w.RMB[idx] + w.DT[idx] * w.DLAM[idx] - sm : 0.0;
-            }
-            END_LANES
-            backward(false, w.RM);
-            alpha = forward(w.RM);
-            // conditional predictor-corrector
-            double m_cor = mu_at(alpha);
-            if (m_cor > 2.0 * m_aff) {
-                FOR_LANES
-                for (int idx = lane; idx < (N + 1) * NC; idx += 32) {
-                    int k = idx / NC, c = idx - k * NC, i = c >= NZ ? c - NZ : c;
-                    w.RM[idx] = active(k, i) ? w.RMB[idx] - sm : 0.0;
+        for (;; ++kk) {
+            mu = qp_residuals(rg, rb, rd, rm, nan);
+            if (!(kk < o.qp_iter_max && alpha > o.qp_alpha_min && !nan &&
+                  (rg > o.qp_tol_stat || rb > o.qp_tol_eq || rd > o.qp_tol_ineq || rm > o.qp_tol_comp)))
+                break;
+            // phase 0 predictor (res_m = lam*t), phase 1 centering + corrector
+            // (res_m = lam*t + dt_aff*dlam_aff - sigma*mu), phase 2 centering only, taken when the
+            // corrected step is much worse than the affine one (conditional predictor-corrector)
+            double sm = 0.0, m_aff = 0.0;
+#pragma unroll 1
+            for (int ph = 0; ph < 3; ++ph) {
+                double S0, S1, S2;
+                ok = backward(ph, sm) && ok;
+                if (!ok) break;
+                forward();
+                alpha = con_pass(ph, sm, S0, S1, S2);
+                double m_a = (S0 + alpha * S1 + alpha * alpha * S2) / nc;
+                if (ph == 0) {
+                    m_aff = m_a;
+                    double sigma = m_aff / mu;
+                    sigma = sigma * sigma * sigma;
+                    sm = sigma * mu;
+                    if (sm < o.qp_tau_min) sm = o.qp_tau_min;
+                } else if (ph == 1) {
+                    if (!(m_a > 2.0 * m_aff)) break;
                 }
-                END_LANES
-                backward(false, w.RM);
-                alpha = forward(w.RM);
             }
+            if (!ok) break;
             double as = alpha;
             if (as < 1.0) as = as * ((1.0 - as) * 0.99 + as * 0.9999);
+            // update; the multiplier step of the dynamics is recovered here from the value functions:
+            // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
             FOR_LANES
             for (int idx = lane; idx < (N + 1) * NZ; idx += 32) w.DZ[idx] += as * w.DV[idx];
-            for (int idx = lane; idx < N * NX; idx += 32) w.PIQ[idx] += as * w.DPI[idx];
+            for (int idx = lane; idx < N * NX; idx += 32) {
+                int k = idx / NX, mI = idx - k * NX;
+                const double *dxn = w.DV + (size_t)(k + 1) * NZ + NU;
+                double a;
+                if (k + 1 < N) {
+                    const double *pp = w.PP + (size_t)(k + 1) * Work<NQ>::PPS;
+                    a = pp[NX * NX + mI];
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) a += pp[mI * NX + j] * dxn[j];
+                } else if ((s.fixedN >> mI) & 1) {
+                    a = s.nuv[mI];
+                } else {
+                    a = s.hhN[mI] * dxn[mI] + s.rN[mI];
+                }
+                w.PIQ[idx] += as * a;
+            }
             for (int idx = lane; idx < (N + 1) * NC; idx += 32) {
                 int k = idx / NC, c = idx - k * NC, i = c >= NZ ? c - NZ : c;
                 if (active(k, i)) {
@@ -1093,34 +1099,28 @@ struct WarpSolver {
                 }
             }
             END_LANES
-            mu = qp_residuals(rg, rb, rd, rm, nan);
         }
         iters = kk;
         // multipliers of the eliminated equalities from stationarity
-        {
-            double r[NX], rp[NX], nuN[NX];
+        FOR_LANES
+        if (lane < NX) {
+            const int i = lane;
+            double a = cost_h(0, NU + i) * w.DZ[NU + i] + cost_g(0, NU + i, w.Z[NU + i]);
+            const double *col = rec(0) + R::BAT + (NU + i) * NX;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                double a = cost_h(0, NU + i) * w.DZ[NU + i] + cost_g(0, NU + i, w.Z[NU + i]);
-                const double *col = w.BAT + (size_t)(NU + i) * NX;
-#pragma unroll
-                for (int m = 0; m < NX; ++m) a += col[m] * w.PIQ[m];
-                if (active(0, NU + i)) a += w.LAMQ[NZ + NU + i] - w.LAMQ[NU + i];
-                r[i] = rp[i] = a;
-                nuN[i] = ((s.fixedN >> i) & 1)
-                             ? w.PIQ[(N - 1) * NX + i] - cost_g(N, NU + i, w.Z[N * NZ + NU + i]) -
-                                   cost_h(N, NU + i) * w.DZ[N * NZ + NU + i]
-                             : 0.0;
-            }
-            proj0(rp);
-            FOR_LANES
-            if (lane < NX) {
-#pragma unroll
-                for (int i = 0; i < NX; ++i)
-                    if (i == lane) s.nu0q[lane] = r[i] - rp[i], s.nuNq[lane] = nuN[i];
-            }
-            END_LANES
+            for (int m = 0; m < NX; ++m) a += col[m] * w.PIQ[m];
+            if (active(0, NU + i)) a += w.LAMQ[NZ + NU + i] - w.LAMQ[NU + i];
+            s.va[i] = s.vb[i] = a;
+            s.nuNq[i] = ((s.fixedN >> i) & 1)
+                            ? w.PIQ[(N - 1) * NX + i] - cost_g(N, NU + i, w.Z[N * NZ + NU + i]) -
+                                  cost_h(N, NU + i) * w.DZ[N * NZ + NU + i]
+                            : 0.0;
         }
+        END_LANES
+        proj0(s.va);
+        FOR_LANES
+        if (lane < NX) s.nu0q[lane] = s.vb[lane] - s.va[lane];
+        END_LANES
         if (!ok || nan || mu != mu) return 3;
         if (rg > o.qp_tol_stat || rb > o.qp_tol_eq || rd > o.qp_tol_ineq || rm > o.qp_tol_comp)
             return kk >= o.qp_iter_max ? 1 : 2;
@@ -1173,15 +1173,16 @@ struct WarpSolver {
         L(acc) = a;
         END_LANES
         double m = WARP_SUM(acc) + total_cost(Zs);
-        double x0[NX], e[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) x0[i] = Zs[NU + i];
-        eq0_violation(x0, e);
+        FOR_LANES
+        if (lane < NX) s.vb[lane] = Zs[NU + lane];
+        END_LANES
+        eq0_violation(s.vb, s.vc);
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-            m += s.w0[i] * fabs(e[i]);
+            m += s.w0[i] * fabs(s.vc[i]);
             if ((s.fixedN >> i) & 1) m += s.wN[i] * fabs(Zs[N * NZ + NU + i] - s.cN[i]);
         }
+        UNIFORM_SYNC();
         return m;
     }
 
@@ -1202,17 +1203,22 @@ struct WarpSolver {
             s.wN[lane] = sqp_iter == 0 ? b : fmax(b, 0.5 * (s.wN[lane] + b));
         }
         END_LANES
-        double m0 = merit(w.Z);
-        double alpha = 1.0;
-        for (;;) {
+        // trial -1 evaluates the merit function at the current iterate (alpha = 0)
+        double m0 = 0.0, alpha = 0.0;
+#pragma unroll 1
+        for (int trial = -1;; ++trial) {
             FOR_LANES
             for (int idx = lane; idx < (N + 1) * NZ; idx += 32) w.ZT[idx] = w.Z[idx] + alpha * w.DZ[idx];
             END_LANES
             double m1 = merit(w.ZT);
-            ++evals;
-            if (m1 < m0) break;
-            if (alpha * o.alpha_reduction < o.alpha_min) break;  // the smallest step is taken anyway
-            alpha *= o.alpha_reduction;
+            if (trial < 0) {
+                m0 = m1, alpha = 1.0;
+            } else {
+                ++evals;
+                if (m1 < m0) break;
+                if (alpha * o.alpha_reduction < o.alpha_min) break;  // the smallest step is taken anyway
+                alpha *= o.alpha_reduction;
+            }
         }
         return alpha;
     }

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -48,8 +49,8 @@ struct Batch {
     vboc_opts opts;
 };
 
-template <int NQ, int FAM>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) solve_kernel(const Batch B) {
+template <int NQ, int FAM, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) solve_kernel(const Batch B) {
     __shared__ Smem<NQ> smem[WARPS_PER_CTA];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WARPS_PER_CTA + warp;
@@ -98,7 +99,7 @@ __global__ void sim_kernel(int batch, const double *x, const double *u, double T
 
 struct vboc_solver {
     int n, family, cap, Nmax, device, nxr, nu;
-    int slots, grid;
+    int slots, grid, ctas_per_sm;
     cudaStream_t stream;
     vboc_opts opts;
     // device buffers
@@ -119,7 +120,10 @@ struct vboc_solver {
 
 template <int NQ, int FAM>
 static cudaError_t launch(vboc_solver *s, const Batch &B) {
-    solve_kernel<NQ, FAM><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+    if (s->ctas_per_sm >= 6)
+        solve_kernel<NQ, FAM, 6><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+    else
+        solve_kernel<NQ, FAM, 4><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
     return cudaGetLastError();
 }
 
@@ -170,7 +174,10 @@ int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device
     vboc_default_opts(family, &s->opts);
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    // resident CTAs per SM: 4 (128 registers / thread) or 6 (85); VBOC_CTAS_PER_SM overrides for tuning
     int ctas_per_sm = 4;
+    if (const char *e = getenv("VBOC_CTAS_PER_SM")) ctas_per_sm = atoi(e) >= 6 ? 6 : 4;
+    s->ctas_per_sm = ctas_per_sm;
     int max_grid = prop.multiProcessorCount * ctas_per_sm;
     int need = (batch_capacity + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     s->grid = need < max_grid ? need : max_grid;

@@ -32,17 +32,18 @@
 #define L(name) name
 #define UNIFORM_SYNC() __syncwarp()
 
-__device__ __forceinline__ double vb_warp_max(double v) {
+// out of line on purpose: ~20 call sites share one copy (instruction-cache footprint)
+__device__ __noinline__ double vb_warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ double vb_warp_min(double v) {
+__device__ __noinline__ double vb_warp_min(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ double vb_warp_sum(double v) {
+__device__ __noinline__ double vb_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -52,6 +53,61 @@ __device__ __forceinline__ int vb_warp_or(int v) { return __reduce_or_sync(0xfff
 #define WARP_MIN(name) vb_warp_min(name)
 #define WARP_SUM(name) vb_warp_sum(name)
 #define WARP_ANY(name) vb_warp_or(name)
+
+// ---- stage-record ring: TMA bulk copies global -> shared, completion on an mbarrier per slot ----
+// One lane issues `cp.async.bulk` for a whole contiguous stage record; all lanes wait on the slot's
+// mbarrier phase.  `ph` is the warp-uniform bitmask of the slots' current phase parities.
+struct VbRing {
+    unsigned long long *bar;  // shared: one mbarrier per slot
+    unsigned ph;
+};
+__device__ __forceinline__ unsigned vb_smem_addr(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void vb_ring_init(VbRing &r, unsigned long long *bars, int depth) {
+    r.bar = bars, r.ph = 0u;
+    if ((threadIdx.x & 31u) == 0) {
+        for (int i = 0; i < depth; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(vb_smem_addr(bars + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void vb_ring_fetch(VbRing &r, int slot, void *dst, const void *src, unsigned bytes) {
+    if ((threadIdx.x & 31u) == 0) {
+        unsigned b = vb_smem_addr(r.bar + slot);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                vb_smem_addr(dst)),
+            "l"(src), "r"(bytes), "r"(b)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void vb_ring_wait(VbRing &r, int slot) {
+    unsigned b = vb_smem_addr(r.bar + slot), parity = (r.ph >> slot) & 1u;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "VB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra VB_DONE_%=;\n"
+        "bra VB_WAIT_%=;\n"
+        "VB_DONE_%=:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+    r.ph ^= 1u << slot;
+}
+// generic-proxy global writes -> later async-proxy (TMA) reads of the same memory
+#define PROXY_FENCE()                                      \
+    do {                                                   \
+        asm volatile("fence.proxy.async;" ::: "memory");   \
+        __syncwarp();                                      \
+    } while (0)
+#define RING_INIT(r, bars, depth) vb_ring_init(r, bars, depth)
+#define RING_FETCH(r, slot, dst, src, bytes) vb_ring_fetch(r, slot, dst, src, bytes)
+#define RING_WAIT(r, slot) vb_ring_wait(r, slot)
 
 #else  // host emulation
 
@@ -101,5 +157,15 @@ inline int vb_emu_any(const int *a) {
 #define WARP_MIN(name) vb_emu_min(name)
 #define WARP_SUM(name) vb_emu_sum(name)
 #define WARP_ANY(name) vb_emu_any(name)
+
+#include <cstring>
+struct VbRing {
+    unsigned long long *bar;
+    unsigned ph;
+};
+#define PROXY_FENCE() ((void)0)
+#define RING_INIT(r, bars, depth) ((void)(r).ph)
+#define RING_FETCH(r, slot, dst, src, bytes) std::memcpy(dst, src, bytes)
+#define RING_WAIT(r, slot) ((void)0)
 
 #endif

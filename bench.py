@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py -- converged OCP solves / s on the reference's headline workload (BASELINE.json):
+3-DOF VBOC (`VBOC/triplependulum_vboc.py:33-103, 110`): one SQP solve per sampled problem, N = 100.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA engine through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on all host cores
+
+A step = one pass of the hot path over one batch of `--batch` synthetic problems per GPU (weak
+scaling: every rank samples its own problems, no inter-GPU traffic during the solves; one all-gather
+of the boundary states afterwards, as the drivers do before the NN fit).
+
+`value`  : converged solves / s with the problem data resident in HBM (device time, CUDA events on the
+           solver's stream, max over ranks).
+`e2e`    : the same through `vboc_solve_batch` with HOST buffers: H2D of guesses/bounds and D2H of
+           trajectories/stats inside the timed region.
+`roofline`: FP64.  achieved = algorithmic flops of the launch (per stage 7348 / 3395 /
+           856 flops per linearisation / IPM iteration / merit evaluation, times the per-problem
+           counters the kernel exports) / kernel time; peak = DFMA peak measured live on the device.
+`cpu_baseline`: the oracle port (kind "port": acados is not installable here) on the host cores, on a
+           bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_DOF, N_STAGES = 3, 100
+F_LIN, F_IPM, F_SIM = 7348.0, 3395.0, 856.0  # SURVEY.md 8(d), VBOC n = 3, per stage
+METRIC = "converged OCP solves/sec, 3-DOF VBOC"
+UNIT = "OCP/s"
+
+
+def algorithmic_flops(out):
+    return float(N_STAGES * (F_LIN * out["sqp_iter"].sum() + F_IPM * out["qp_iter"].sum()
+                             + F_SIM * out["ls_evals"].sum()))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in o.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(nprob, seed, threads):
+    """Time the oracle port on `nprob` problems of the workload with `threads` host threads."""
+    from oracle import oracle as orc
+    from vboc_b200 import problems as pr
+    bp = pr.sample_vboc(N_DOF, nprob, seed=seed)
+    t0 = time.perf_counter()
+    r = orc.solve_batch(N_DOF, orc.FAMILY_VBOC, orc.MODE_SQP, bp, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return int((r["status"] == 0).sum()), dt
+
+
+def run_reference(args):
+    """CPU arm: the reference's arithmetic lives in acados/HPIPM, which cannot be installed here
+    (DESIGN.md), so this times the oracle port with all host threads; a step = a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nprob = args.cpu_sample
+    for i in range(args.warmup):
+        cpu_sample(min(nprob, 2 * cores), 900 + i, cores)
+    conv, tot = 0, 0.0
+    for i in range(args.steps):
+        c, dt = cpu_sample(nprob, 1000 + i, cores)
+        conv += c
+        tot += dt
+    v = conv / tot
+    sample = f"{nprob} problems per step x {args.steps} steps, seeded like the GPU arm"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "triplependulum_vboc single SQP solve per problem, N=100, nx=7, nu=3",
+                   "batch_per_step": nprob, "parallelism": f"openmp{cores}"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32768, help="problems per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=256, help="problems of the CPU baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from vboc_b200 import engine, problems as pr
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # One solver handle + CUDA stream per step: the K steps of the timed region are launched back to
+    # back on K streams, so the tail of one step (the few problems that need hundreds of SQP
+    # iterations keep single warps busy for seconds) overlaps the other steps instead of idling the GPU.
+    nh = max(args.steps, 1)
+    streams = [torch.cuda.Stream(device=local) for _ in range(nh)]
+    sols = []
+    for st in streams:
+        sv = engine.BatchSolver(N_DOF, "vboc", B, N_STAGES, device=local)
+        sv.set_stream(st.cuda_stream)
+        sols.append(sv)
+    peak_tf = engine.fp64_peak_tflops(local)
+
+    def batch_for(step):  # every rank / step samples its own problems
+        return pr.sample_vboc(N_DOF, B, seed=10_000 * (rank + 1) + step)
+
+    def run_resident(batches):
+        """upload (untimed) -> timed: all kernels launched on their streams -> elapsed from the first
+        launch to the last completion, CUDA events on the launching streams."""
+        for sv, bp in zip(sols, batches):
+            sv.upload(bp)
+        barrier()
+        start = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in batches]
+        start.record(streams[0])
+        for sv, st, ev in zip(sols, streams, ends):
+            sv.solve_resident_async(0)
+            ev.record(st)
+        for sv in sols[:len(batches)]:
+            sv.sync()
+        barrier()
+        ms = max(start.elapsed_time(ev) for ev in ends)
+        outs = [sv.download() for sv in sols[:len(batches)]]
+        return ms, outs
+
+    # ---- device-resident throughput: `value`
+    for i in range(0, args.warmup, nh):
+        run_resident([batch_for(-1 - j) for j in range(i, min(i + nh, args.warmup))])
+    batches = [batch_for(i) for i in range(args.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    total_ms, outs = run_resident(batches)
+    clocks = sampler.stop()
+    conv = sum(int((o["status"] == 0).sum()) for o in outs)
+    flops = sum(algorithmic_flops(o) for o in outs)
+    t_dev = total_ms * 1e-3
+
+    # ---- end-to-end through the C-ABI with host buffers: `e2e` (one host thread per step; the C call
+    # releases the GIL, so uploads, kernels and downloads of different steps overlap)
+    h2d = sum(a.nbytes for k, a in batches[0].items() if isinstance(a, np.ndarray)
+              and k in ("N", "x_guess", "u_guess", "p", "lbx0", "ubx0", "lbx", "ubx", "lbxN", "ubxN", "lbu", "ubu", "C0"))
+    d2h = B * ((N_STAGES + 1) * 7 + N_STAGES * 3) * 8 + B * 64
+    results = [None] * args.steps
+
+    def worker(i):
+        results[i] = sols[i].solve(batches[i])
+
+    barrier()
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(args.steps)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    conv_e = sum(int((o["status"] == 0).sum()) for o in results)
+    if world > 1:  # the one exchange step: boundary states of all ranks, before the NN fit
+        rows = torch.from_numpy(np.ascontiguousarray(
+            np.concatenate([o["x"][:, 0, :6] for o in results]))).cuda()
+        gathered = [torch.empty_like(rows) for _ in range(world)]
+        dist.all_gather(gathered, rows)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    # ---- whole-job aggregates: max time over ranks, sum of converged solves
+    t_dev_local = t_dev
+    agg = torch.tensor([t_dev, t_e2e, float(conv), float(conv_e), flops], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = agg[:2].clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tot = agg[2:].clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e = tmax.tolist()
+        conv, conv_e, flops_all = tot.tolist()
+    else:
+        flops_all = flops
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        c_conv, c_dt = cpu_sample(args.cpu_sample, 4242, cores) if world == 1 else (0, 1.0)
+        achieved_tf = flops / t_dev_local / 1e12  # rank 0's launches
+        line = {
+            "metric": METRIC, "value": conv / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "triplependulum_vboc single SQP solve per problem, N=100, nx=7, nu=3",
+                       "batch_per_gpu_per_step": B, "parallelism": f"dp{world} (index-sharded problems)",
+                       "l2": "inputs + per-warp workspaces (>700 MB) exceed the 126 MB L2; no flush needed",
+                       "steps_overlap": "the K timed steps run on K CUDA streams (K solver handles); elapsed = first launch to last completion",
+                       "converged_fraction": conv / (B * world * args.steps)},
+            "e2e": {"value": conv_e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": "DFMA micro-benchmark run live by bench.py (MEASURED_PEAKS.json has no FP64 entry)",
+                         "flops_per_launch": flops / args.steps},
+            "clocks": clocks,
+        }
+        if world == 1:
+            line["cpu_baseline"] = {"value": c_conv / c_dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample} problems of the same sampler, oracle port, OpenMP over problems"}
+        print(json.dumps(line))
+    for sv in sols:
+        sv.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

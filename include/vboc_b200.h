@@ -23,7 +23,6 @@
  *                                the same three steps split so that inputs may stay resident in HBM
  *   vboc_sim_step                SYMtriplependulumINIT.acados_integrator set/solve/get
  *                                VBOC/triplependulum_class_vboc.py:194-239, VBOC/triplependulum_vboc.py:348-352
- *   vboc_mlp_forward             NeuralNetDIR / NeuralNetCLS forward my_nn.py:4-34 (inference only)
  */
 #ifndef VBOC_B200_H
 #define VBOC_B200_H
@@ -115,6 +114,10 @@ int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
                 const double *lbx, const double *ubx, const double *lbxN, const double *ubxN,
                 const double *lbu, const double *ubu, const double *C0, double Tf);
 int vboc_solve_resident(vboc_solver *s, int mode);
+/* Launch without waiting / wait for everything queued on the solver's stream.  Two solvers on two
+ * streams let the tail of one batch (a few long-running problems) overlap the next batch. */
+int vboc_solve_resident_async(vboc_solver *s, int mode);
+int vboc_sync(vboc_solver *s);
 int vboc_download(vboc_solver *s, double *x, double *u, vboc_stats *stats);
 /* Device time of the last vboc_solve_resident kernel in milliseconds (CUDA events on the solver's
  * stream); negative if none. */
@@ -124,6 +127,10 @@ double vboc_last_kernel_ms(vboc_solver *s);
  * x [batch][2n], u [batch][n], x_next [batch][2n]. */
 int vboc_sim_step(int n_dof, int device, int batch, const double *x, const double *u, double T,
                   double *x_next);
+
+/* Measured FP64 FMA peak of the device in TFLOP/s (dependent-free DFMA chains on every SM): the
+ * roofline denominator bench.py reports against (MEASURED_PEAKS.json has no FP64 entry). */
+int vboc_fp64_peak(int device, double *tflops);
 
 const char *vboc_last_error(void);
 const char *vboc_version(void);

@@ -16,8 +16,9 @@ ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA = -1, -2, -3
 
 EXPORTS = (
     "vboc_default_opts", "vboc_create", "vboc_destroy", "vboc_set_opts", "vboc_set_stream",
-    "vboc_solve_batch", "vboc_upload", "vboc_solve_resident", "vboc_download", "vboc_last_kernel_ms",
-    "vboc_sim_step", "vboc_last_error", "vboc_version",
+    "vboc_solve_batch", "vboc_upload", "vboc_solve_resident", "vboc_solve_resident_async", "vboc_sync",
+    "vboc_download", "vboc_last_kernel_ms",
+    "vboc_sim_step", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
 )
 
 
@@ -72,10 +73,13 @@ def lib():
         L.vboc_upload.argtypes = [vp, C.c_int, ip] + [dp] * 12 + [C.c_double]
         L.vboc_solve_batch.argtypes = [vp, C.c_int, C.c_int, ip] + [dp] * 12 + [C.c_double, dp, dp, C.POINTER(Stats)]
         L.vboc_solve_resident.argtypes = [vp, C.c_int]
+        L.vboc_solve_resident_async.argtypes = [vp, C.c_int]
+        L.vboc_sync.argtypes = [vp]
         L.vboc_download.argtypes = [vp, dp, dp, C.POINTER(Stats)]
         L.vboc_last_kernel_ms.argtypes = [vp]
         L.vboc_last_kernel_ms.restype = C.c_double
         L.vboc_sim_step.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, dp]
+        L.vboc_fp64_peak.argtypes = [C.c_int, dp]
         L.vboc_last_error.restype = C.c_char_p
         L.vboc_version.restype = C.c_char_p
         del prob

@@ -70,6 +70,19 @@ struct Rec {
 
 constexpr int RING_DEPTH = 4;
 
+// dot product with strides and two accumulators (halves the dependent FP64 chain of the sweeps)
+template <int LEN>
+VB_HD double dot2(const double *a, int sa, const double *b, int sb, double init = 0.0) {
+    double a0 = init, a1 = 0.0;
+#pragma unroll
+    for (int m = 0; m + 1 < LEN; m += 2) {
+        a0 += a[m * sa] * b[m * sb];
+        a1 += a[(m + 1) * sa] * b[(m + 1) * sb];
+    }
+    if (LEN & 1) a0 += a[(LEN - 1) * sa] * b[(LEN - 1) * sb];
+    return a0 + a1;
+}
+
 // Global-memory workspace of one warp slot, stage-major.
 template <int NQ>
 struct Work {
@@ -83,29 +96,27 @@ struct Work {
     double *RG, *RD, *RM, *RMB;      // IPM residuals (RMB = lam*t, RM = dt_aff*dlam_aff)
     double *PP, *MF;                 // value functions; last-stage record
     double *WDYN, *WB, *ZT;          // merit weights, trial point
-    static VB_HD size_t doubles(int Nmax) {
-        size_t S = (size_t)Nmax + 1;
-        size_t n = S * (size_t)(R::SIZE + D::NZ + D::NX + D::NC + D::NX + D::NZ + D::NX + D::NC + D::NC +
-                                D::NZ + D::NC + D::NC + D::NZ + D::NC + D::NC + D::NC + PPS + D::NX +
-                                D::NC + D::NZ) +
-                   D::MFS;
-        return (n + 1) & ~(size_t)1;
-    }
-    VB_HD void carve(double *b, int Nmax) {
-        size_t S = (size_t)Nmax + 1;
-        auto take = [&](size_t per) {
-            double *p = b;
-            b += S * per;
-            return p;
-        };
-        SR = take(R::SIZE);
-        Z = take(D::NZ), PI = take(D::NX), LAM = take(D::NC), BD = take(D::NX);
-        DZ = take(D::NZ), PIQ = take(D::NX), LAMQ = take(D::NC), TQ = take(D::NC);
-        DV = take(D::NZ), DLAM = take(D::NC), DT = take(D::NC);
-        RG = take(D::NZ), RD = take(D::NC), RM = take(D::NC), RMB = take(D::NC);
-        PP = take(PPS);
-        WDYN = take(D::NX), WB = take(D::NC), ZT = take(D::NZ);
-        MF = b;
+    // The workspace is carved with the compile-time stride SMAX so that every array is the slot base
+    // plus a constant (no pointer table in registers, immediate offsets in the load/store
+    // instructions); N_max <= SMAX - 1 is checked by vboc_create.
+    static constexpr size_t SMAX = 129;
+    static constexpr size_t O_SR = 0;
+    static constexpr size_t O_Z = O_SR + SMAX * R::SIZE, O_PI = O_Z + SMAX * D::NZ, O_LAM = O_PI + SMAX * D::NX;
+    static constexpr size_t O_BD = O_LAM + SMAX * D::NC, O_DZ = O_BD + SMAX * D::NX, O_PIQ = O_DZ + SMAX * D::NZ;
+    static constexpr size_t O_LAMQ = O_PIQ + SMAX * D::NX, O_TQ = O_LAMQ + SMAX * D::NC, O_DV = O_TQ + SMAX * D::NC;
+    static constexpr size_t O_DLAM = O_DV + SMAX * D::NZ, O_DT = O_DLAM + SMAX * D::NC, O_RG = O_DT + SMAX * D::NC;
+    static constexpr size_t O_RD = O_RG + SMAX * D::NZ, O_RM = O_RD + SMAX * D::NC, O_RMB = O_RM + SMAX * D::NC;
+    static constexpr size_t O_PP = O_RMB + SMAX * D::NC, O_WDYN = O_PP + SMAX * PPS, O_WB = O_WDYN + SMAX * D::NX;
+    static constexpr size_t O_ZT = O_WB + SMAX * D::NC, O_MF = O_ZT + SMAX * D::NZ;
+    static constexpr size_t TOTAL = (O_MF + D::MFS + 1) & ~(size_t)1;
+    static VB_HD size_t doubles(int) { return TOTAL; }
+    VB_HD void carve(double *b, int) {
+        SR = b + O_SR;
+        Z = b + O_Z, PI = b + O_PI, LAM = b + O_LAM, BD = b + O_BD;
+        DZ = b + O_DZ, PIQ = b + O_PIQ, LAMQ = b + O_LAMQ, TQ = b + O_TQ;
+        DV = b + O_DV, DLAM = b + O_DLAM, DT = b + O_DT;
+        RG = b + O_RG, RD = b + O_RD, RM = b + O_RM, RMB = b + O_RMB;
+        PP = b + O_PP, WDYN = b + O_WDYN, WB = b + O_WB, ZT = b + O_ZT, MF = b + O_MF;
     }
 };
 
@@ -432,6 +443,15 @@ struct WarpSolver {
         int nb = 0;
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
+            {
+                const int nidx = idx + 32, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
+                if (nidx < (N + 1) * NZ) {
+                    VB_PREFETCH(w.DZ + nidx), VB_PREFETCH(w.Z + nidx);
+                    VB_PREFETCH(rec(nk) + R::BAT + (nidx - nk * NZ) * NX), VB_PREFETCH(w.PIQ + nk * NX);
+                    VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
+                    VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.TQ + nc + NZ);
+                }
+            }
             double v = w.DZ[idx];
             double hh = cost_h(k, i) + o.qp_reg_prim, bar = 0.0;
             double r = (hh - o.qp_reg_prim) * v + cost_g(k, i, w.Z[idx]);
@@ -557,16 +577,10 @@ struct WarpSolver {
                 FOR_LANES
                 for (int idx = lane; idx < NZ * NX; idx += 32) {
                     int j = idx / NX, i = idx - j * NX;
-                    double a = 0.0;
-#pragma unroll
-                    for (int m = 0; m < NX; ++m) a += s.P[i][m] * r[R::BAT + j * NX + m];
-                    s.PBAT[j][i] = a;
+                    s.PBAT[j][i] = dot2<NX>(&s.P[i][0], 1, r + R::BAT + j * NX, 1);
                 }
                 if (lane < NX) {
-                    double a = 0.0;
-#pragma unroll
-                    for (int m = 0; m < NX; ++m) a += s.P[lane][m] * r[R::RB + m];
-                    s.tb[lane] = a;
+                    s.tb[lane] = dot2<NX>(&s.P[lane][0], 1, r + R::RB, 1);
                 }
                 END_LANES
             }
@@ -574,12 +588,10 @@ struct WarpSolver {
             FOR_LANES
             if (factor) {
                 for (int idx = lane; idx < TRI; idx += 32) {
-                    int a_ = 0;
-                    while ((a_ + 1) * (a_ + 2) / 2 <= idx) ++a_;
-                    int b_ = idx - a_ * (a_ + 1) / 2;
-                    double a = (a_ == b_) ? r[R::HH + a_] : 0.0;
-#pragma unroll
-                    for (int m = 0; m < NX; ++m) a += r[R::BAT + a_ * NX + m] * s.PBAT[b_][m];
+                    // row of the idx-th entry of the row-major lower triangle: floor((sqrt(8 idx + 1) - 1) / 2),
+                    // exact in FP32 for idx < 2^20
+                    int a_ = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f), b_ = idx - a_ * (a_ + 1) / 2;
+                    double a = dot2<NX>(r + R::BAT + a_ * NX, 1, &s.PBAT[b_][0], 1, (a_ == b_) ? r[R::HH + a_] : 0.0);
                     s.M[a_][b_] = a, s.M[b_][a_] = a;
                 }
             } else if (last) {
@@ -588,17 +600,12 @@ struct WarpSolver {
             if (lane < NZ) {
                 double mb;
                 if (factor) {
-                    mb = 0.0;
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) mb += r[R::BAT + lane * NX + i] * s.tb[i];
+                    mb = dot2<NX>(r + R::BAT + lane * NX, 1, s.tb, 1);
                     gk[R::MB + lane] = mb;
                 } else {
                     mb = r[R::MB + lane];
                 }
-                double a = rhs_of(r, lane, mode, sm) + mb;
-#pragma unroll
-                for (int i = 0; i < NX; ++i) a += r[R::BAT + lane * NX + i] * s.pvec[i];
-                s.m[lane] = a;
+                s.m[lane] = dot2<NX>(r + R::BAT + lane * NX, 1, s.pvec, 1, rhs_of(r, lane, mode, sm) + mb);
             }
             END_LANES
             // D: eliminate the controls
@@ -611,7 +618,7 @@ struct WarpSolver {
                         double d = s.M[j][j];
 #pragma unroll
                         for (int c = 0; c < j; ++c) d -= Lu[j][c] * Lu[j][c];
-                        di[j] = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
+                        di[j] = d > 0.0 ? VB_RSQRT(d) : 0.0;
 #pragma unroll
                         for (int i = j + 1; i < NU; ++i) {
                             double a = s.M[i][j];
@@ -816,7 +823,7 @@ struct WarpSolver {
 #pragma unroll 1
             for (int j = 0; j < NX; ++j) {
                 double d = s.Lz[j][j];
-                double di = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
+                double di = d > 0.0 ? VB_RSQRT(d) : 0.0;
                 UNIFORM_SYNC();
                 FOR_LANES
                 if (lane > j && lane < NX) s.Lz[lane][j] *= di;
@@ -907,10 +914,7 @@ struct WarpSolver {
                 double t[NU];
 #pragma unroll
                 for (int c = 0; c < NU; ++c) {
-                    double a = r[R::YV + c];
-#pragma unroll
-                    for (int j = 0; j < NX; ++j) a += r[R::LXU + j * NU + c] * s.dx[cur][j];
-                    t[c] = a;
+                    t[c] = dot2<NX>(r + R::LXU + c, NU, s.dx[cur], 1, r[R::YV + c]);
                 }
 #pragma unroll
                 for (int c = NU - 1; c >= 0; --c) {
@@ -930,9 +934,7 @@ struct WarpSolver {
             }
             FOR_LANES
             if (lane < NX) {
-                double a = r[R::RB + lane];
-#pragma unroll
-                for (int j = 0; j < NX; ++j) a += r[R::BAT + (NU + j) * NX + lane] * s.dx[cur][j];
+                double a = dot2<NX>(r + R::BAT + NU * NX + lane, NX, s.dx[cur], 1, r[R::RB + lane]);
 #pragma unroll
                 for (int c = 0; c < NU; ++c) a += r[R::BAT + c * NX + lane] * du[c];
                 s.dx[cur ^ 1][lane] = a;
@@ -997,6 +999,18 @@ struct WarpSolver {
             int k = idx / NZ, i = idx - k * NZ;
             double *rk = rec(k);
             double q1 = 0.0, q2 = 0.0;
+            {
+                const int nidx = idx + 32, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
+                if (nidx < (N + 1) * NZ) {
+                    VB_PREFETCH(w.DV + nidx);
+                    VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
+                    VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.TQ + nc + NZ);
+                    VB_PREFETCH(w.RMB + nc), VB_PREFETCH(w.RMB + nc + NZ);
+                    VB_PREFETCH(w.RD + nc), VB_PREFETCH(w.RD + nc + NZ);
+                    if (mode == 1) VB_PREFETCH(w.RM + nc), VB_PREFETCH(w.RM + nc + NZ);
+                    if (mode == 0) VB_PREFETCH(rec(nk) + R::RR + (nidx - nk * NZ));
+                }
+            }
             if (active(k, i)) {
                 double dvv = w.DV[idx];
 #pragma unroll
@@ -1074,10 +1088,19 @@ struct WarpSolver {
             // update; the multiplier step of the dynamics is recovered here from the value functions:
             // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
             FOR_LANES
-            for (int idx = lane; idx < (N + 1) * NZ; idx += 32) w.DZ[idx] += as * w.DV[idx];
+            for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
+                if (idx + 32 < (N + 1) * NZ) VB_PREFETCH(w.DZ + idx + 32), VB_PREFETCH(w.DV + idx + 32);
+                w.DZ[idx] += as * w.DV[idx];
+            }
             for (int idx = lane; idx < N * NX; idx += 32) {
                 int k = idx / NX, mI = idx - k * NX;
                 const double *dxn = w.DV + (size_t)(k + 1) * NZ + NU;
+                if (idx + 32 < N * NX) {
+                    const int nk = (idx + 32) / NX, nm = idx + 32 - nk * NX;
+                    VB_PREFETCH(w.PP + (size_t)(nk + 1) * Work<NQ>::PPS + nm * NX);
+                    VB_PREFETCH(w.PP + (size_t)(nk + 1) * Work<NQ>::PPS + NX * NX + nm);
+                    VB_PREFETCH(w.PIQ + idx + 32);
+                }
                 double a;
                 if (k + 1 < N) {
                     const double *pp = w.PP + (size_t)(k + 1) * Work<NQ>::PPS;
@@ -1093,6 +1116,10 @@ struct WarpSolver {
             }
             for (int idx = lane; idx < (N + 1) * NC; idx += 32) {
                 int k = idx / NC, c = idx - k * NC, i = c >= NZ ? c - NZ : c;
+                if (idx + 32 < (N + 1) * NC) {
+                    VB_PREFETCH(w.LAMQ + idx + 32), VB_PREFETCH(w.DLAM + idx + 32);
+                    VB_PREFETCH(w.TQ + idx + 32), VB_PREFETCH(w.DT + idx + 32);
+                }
                 if (active(k, i)) {
                     w.LAMQ[idx] = fmax(w.LAMQ[idx] + as * w.DLAM[idx], o.qp_lam_min);
                     w.TQ[idx] = fmax(w.TQ[idx] + as * w.DT[idx], o.qp_t_min);

@@ -95,6 +95,18 @@ __global__ void sim_kernel(int batch, const double *x, const double *u, double T
     for (int i = 0; i < 2 * NQ; ++i) xn[(size_t)b * 2 * NQ + i] = xo[i];
 }
 
+// FP64 FMA peak probe: 8 independent DFMA chains per thread, enough warps to fill every SM
+__global__ void dfma_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c), a1 = fma(a1, m, c), a2 = fma(a2, m, c), a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c), a5 = fma(a5, m, c), a6 = fma(a6, m, c), a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 }  // namespace
 
 struct vboc_solver {
@@ -160,7 +172,7 @@ static size_t work_doubles_for(int n, int Nmax) {
 
 int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device, vboc_solver **out) {
     if (!out || n_dof < 1 || n_dof > 3 || (family != VBOC_FAMILY_VBOC && family != VBOC_FAMILY_AL) ||
-        batch_capacity < 1 || N_max < 1 || N_max > 1024)
+        batch_capacity < 1 || N_max < 1 || N_max > (int)Work<3>::SMAX - 1)
         return fail(VBOC_ERR_ARG, "vboc_create: bad argument");
     int ndev = 0;
     CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -361,7 +373,7 @@ int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
     return 0;
 }
 
-int vboc_solve_resident(vboc_solver *s, int mode) {
+int vboc_solve_resident_async(vboc_solver *s, int mode) {
     if (!s) return fail(VBOC_ERR_ARG, "vboc_solve_resident: null handle");
     if (!s->batch) return fail(VBOC_ERR_ARG, "vboc_solve_resident: nothing uploaded");
     if (mode != VBOC_MODE_SQP && mode != VBOC_MODE_RTI) return fail(VBOC_ERR_ARG, "bad mode");
@@ -384,11 +396,25 @@ int vboc_solve_resident(vboc_solver *s, int mode) {
 #undef GO
     if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("solve_kernel launch: ") + cudaGetErrorString(e));
     CUDA_OK(cudaEventRecord(s->ev1, s->stream));
-    CUDA_OK(cudaStreamSynchronize(s->stream));
-    float ms = 0.f;
-    CUDA_OK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    s->last_ms = ms;
+    s->last_ms = -1.0;
     return 0;
+}
+
+int vboc_sync(vboc_solver *s) {
+    if (!s) return fail(VBOC_ERR_ARG, "vboc_sync: null handle");
+    CUDA_OK(cudaSetDevice(s->device));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    if (s->last_ms < 0.0 && s->batch) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_ms = ms;
+        cudaGetLastError();
+    }
+    return 0;
+}
+
+int vboc_solve_resident(vboc_solver *s, int mode) {
+    int rc = vboc_solve_resident_async(s, mode);
+    return rc ? rc : vboc_sync(s);
 }
 
 double vboc_last_kernel_ms(vboc_solver *s) { return s ? s->last_ms : -1.0; }
@@ -414,6 +440,33 @@ int vboc_solve_batch(vboc_solver *s, int mode, int batch, const int *N, const do
     if (rc) return rc;
     if ((rc = vboc_solve_resident(s, mode))) return rc;
     return vboc_download(s, x, u, stats);
+}
+
+int vboc_fp64_peak(int device, double *tflops) {
+    if (!tflops) return fail(VBOC_ERR_ARG, "vboc_fp64_peak: null argument");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double *out = nullptr;
+    CUDA_OK(cudaMalloc((void **)&out, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_OK(cudaEventRecord(e0));
+        dfma_peak_kernel<<<blocks, threads>>>(out, iters);
+        CUDA_OK(cudaEventRecord(e1));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(out);
+    *tflops = best;
+    return 0;
 }
 
 int vboc_sim_step(int n_dof, int device, int batch, const double *x, const double *u, double T,

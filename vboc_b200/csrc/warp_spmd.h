@@ -31,6 +31,10 @@
 #define LV(type, name) type name
 #define L(name) name
 #define UNIFORM_SYNC() __syncwarp()
+#define VB_RSQRT(x) rsqrt(x)
+// software prefetch of the next lane-strided iteration (the flat passes are latency bound)
+__device__ __forceinline__ void vb_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#define VB_PREFETCH(p) vb_prefetch(p)
 
 // out of line on purpose: ~20 call sites share one copy (instruction-cache footprint)
 __device__ __noinline__ double vb_warp_max(double v) {
@@ -119,6 +123,8 @@ __device__ __forceinline__ void vb_ring_wait(VbRing &r, int slot) {
 #define LV(type, name) type name[32]
 #define L(name) name[lane]
 #define UNIFORM_SYNC() ((void)0)
+#define VB_RSQRT(x) (1.0 / std::sqrt(x))
+#define VB_PREFETCH(p) ((void)(p))
 
 // the same butterfly order as the shuffle versions, so sums round identically
 inline double vb_emu_max(const double *a) {

@@ -88,6 +88,13 @@ class BatchSolver:
         check(_lib.lib().vboc_solve_resident(self._h, int(mode)))
         return _lib.lib().vboc_last_kernel_ms(self._h)
 
+    def solve_resident_async(self, mode=MODE_SQP):
+        check(_lib.lib().vboc_solve_resident_async(self._h, int(mode)))
+
+    def sync(self):
+        check(_lib.lib().vboc_sync(self._h))
+        return _lib.lib().vboc_last_kernel_ms(self._h)
+
     def download(self):
         B = self._batch
         x = np.empty((B, self.N_max + 1, self.nx))
@@ -127,3 +134,10 @@ def sim_step(n, x, u, T, device=0):
     xn = np.empty_like(x)
     check(_lib.lib().vboc_sim_step(int(n), int(device), x.shape[0], _dp(x), _dp(u), float(T), _dp(xn)))
     return xn
+
+
+def fp64_peak_tflops(device=0):
+    """Measured DFMA peak of the device (roofline denominator)."""
+    v = C.c_double(0.0)
+    check(_lib.lib().vboc_fp64_peak(int(device), C.byref(v)))
+    return v.value

@@ -1,0 +1,41 @@
+"""The warp solver's lane program (vboc_b200/csrc/ocp_warp.h) compiled for the host by tools/emu
+(32 lanes of every lane region run as a loop) against the oracle: same statuses and iteration counts,
+trajectories to 1e-6.  This is the CPU-side check of the kernel SOURCE; the GPU parity tests check the
+compiled kernel."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from vboc_b200 import problems as pr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools", "emu"))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu as e
+    e.build()
+    return e
+
+
+def _opts(emu, oo):
+    o = emu.Opts()
+    for f, _ in emu.Opts._fields_:
+        setattr(o, f, getattr(oo, f))
+    return o
+
+
+@pytest.mark.parametrize("n,fam,mode", [(3, 0, 0), (2, 0, 0), (3, 1, 1), (2, 1, 1), (1, 1, 1)])
+def test_lane_program_matches_oracle(oracle, emu, n, fam, mode):
+    bp = pr.sample_vboc(n, 6, seed=1) if fam == 0 else pr.sample_al(n, 24, seed=2)
+    oo = oracle.default_opts(fam)
+    ref = oracle.solve_batch(n, fam, mode, bp, oo)
+    out = emu.solve_batch(n, fam, mode, bp, _opts(emu, oo))
+    assert (ref["status"] == out["status"]).all()
+    assert (ref["sqp_iter"] == out["sqp_iter"]).all() and (ref["qp_iter"] == out["qp_iter"]).all()
+    ok = out["status"] == 0
+    assert ok.any()
+    assert np.abs(ref["x"] - out["x"])[ok].max() < 1e-6

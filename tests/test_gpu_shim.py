@@ -1,0 +1,88 @@
+"""The drop-in classes called the way the reference's drivers call them, against the oracle."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from vboc_b200 import problems as pr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(sub, mod):
+    path = os.path.join(ROOT, "vboc_b200", "shim", sub)
+    sys.path.insert(0, path)
+    try:
+        sys.modules.pop(mod, None)
+        return importlib.import_module(mod)
+    finally:
+        sys.path.remove(path)
+
+
+def test_ocp_solve_like_data_generation(oracle):
+    """VBOC/triplependulum_vboc.py:86-129: guess, OCP_solve, get_cost, get(i, 'x'), then one extension step."""
+    m = _load("VBOC", "triplependulum_class_vboc")
+    ocp = m.OCPtriplependulumINIT()
+    bp = pr.sample_vboc(3, 3, seed=9)
+    for b in range(3):
+        one = pr.take(bp, b)
+        N = 100
+        ocp.N = N
+        ocp.ocp_solver.set_new_time_steps(np.full((N,), 1.))
+        ocp.ocp_solver.update_qp_solver_cond_N(N)
+        status = ocp.OCP_solve(one["x_guess"][:N], one["u_guess"], one["p"], one["lbx"], one["ubx"], one["lbu"],
+                               one["ubu"], one["lbx0"], one["ubx0"], one["lbxN"], one["ubxN"])
+        ref = oracle.solve(3, 0, 0, one)
+        assert status == ref["status"]
+        if status != 0:
+            continue
+        x_sol = np.array([ocp.ocp_solver.get(i, "x") for i in range(N + 1)])
+        u_sol = np.array([ocp.ocp_solver.get(i, "u") for i in range(N)])
+        assert np.abs(x_sol - ref["x"]).max() < 1e-5 and np.abs(u_sol - ref["u"]).max() < 1e-4
+        assert abs(ocp.ocp_solver.get_cost() - ref["cost"]) < 1e-6
+        # horizon extension with warm start (:119-136)
+        x_g = np.vstack([x_sol, x_sol[-1]])
+        u_g = np.vstack([u_sol, np.zeros(3)])
+        ocp.N = N + 1
+        ocp.ocp_solver.set_new_time_steps(np.full((N + 1,), 1.))
+        st2 = ocp.OCP_solve(x_g, u_g, one["p"], one["lbx"], one["ubx"], one["lbu"], one["ubu"], one["lbx0"],
+                            one["ubx0"], one["lbxN"], one["ubxN"])
+        one2 = dict(one)
+        one2["x_guess"], one2["u_guess"] = pr.expand_guess(x_g, u_g, N + 1)
+        ref2 = oracle.solve(3, 0, 0, one2)
+        assert st2 == ref2["status"]
+        if st2 == 0:
+            assert abs(ocp.ocp_solver.get_cost() - ref2["cost"]) < 1e-6
+            assert ocp.ocp_solver.get_cost() <= ref["cost"] + 1e-6  # a longer horizon cannot do worse
+
+
+def test_sim_integrator_like_the_driver(oracle):
+    """VBOC/triplependulum_vboc.py:348-352"""
+    m = _load("VBOC", "triplependulum_class_vboc")
+    sim = m.SYMtriplependulumINIT()
+    x = np.array([3.0, 3.2, 2.9, 1.0, -2.0, 0.5])
+    u = np.array([1.0, -3.0, 2.0])
+    sim.acados_integrator.set("u", u)
+    sim.acados_integrator.set("x", x)
+    sim.acados_integrator.set("T", 1e-2)
+    assert sim.acados_integrator.solve() == 0
+    assert np.abs(sim.acados_integrator.get("x") - oracle.rk4(3, 1, x, u, 1e-2)).max() < 1e-12
+
+
+@pytest.mark.parametrize("mod,cls,n", [("doublependulum_class_al", "OCPdoublependulumINIT", 2),
+                                       ("triplependulum_class_al", "OCPtriplependulumINIT", 3)])
+def test_compute_problem_labels(oracle, mod, cls, n):
+    """AL/triplependulum_al.py:24-41 `testing`"""
+    ocp = getattr(_load("AL", mod), cls)()
+    bp = pr.sample_al(n, 12, seed=6)
+    ref = oracle.solve_batch(n, 1, 1, bp)
+    for b in range(12):
+        lab = ocp.compute_problem(bp["x0"][b, :n], bp["x0"][b, n:])
+        want = 1 if ref["status"][b] == 0 else (0 if ref["status"][b] == 4 else 2)
+        assert lab == want
+        if lab == 1:
+            traj = np.array([ocp.ocp_solver.get(i, "x") for i in range(ocp.N + 1)])
+            assert np.abs(traj - ref["x"][b]).max() < 1e-6

@@ -254,3 +254,15 @@ def take(bp, i):
     for k in ("p", "lbx0", "ubx0", "lbx", "ubx", "lbxN", "ubxN", "lbu", "ubu", "C0"):
         out[k] = None if bp.get(k) is None else np.ascontiguousarray(bp[k][i])
     return out
+
+
+def from_ocp_solve_args(n, N, x_sol_guess, u_sol_guess, p, q_lb, q_ub, u_lb, u_ub, q_init_lb, q_init_ub,
+                        q_fin_lb, q_fin_ub):
+    """Batch-of-one problem data from the arguments of the reference's `OCP_solve`
+    (VBOC/triplependulum_class_vboc.py:155-191)."""
+    xg, ug = expand_guess(x_sol_guess, u_sol_guess, N)
+    one = lambda a: np.ascontiguousarray(np.asarray(a, dtype=float)[None])
+    p = np.asarray(p, dtype=float)
+    return dict(n=n, family="vboc", N=np.array([N], dtype=np.int32), x_guess=one(xg), u_guess=one(ug), p=one(p),
+                lbx0=one(q_init_lb), ubx0=one(q_init_ub), lbx=one(q_lb), ubx=one(q_ub), lbxN=one(q_fin_lb),
+                ubxN=one(q_fin_ub), lbu=one(u_lb), ubu=one(u_ub), C0=stage0_projector(p[None, :n], 2 * n + 1))

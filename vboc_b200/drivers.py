@@ -1,0 +1,339 @@
+"""Batched per-problem worker logic of the reference's drivers.
+
+The reference runs `data_generation(v)` / `testing(v)` once per problem inside `multiprocessing.Pool`
+workers; each worker interleaves host decisions (horizon extension, retries with perturbed data,
+the walk along the optimal trajectory with sub-OCPs and the simulated "unviable twin") with blocking
+solver calls.  Here every problem is a Python generator that YIELDS its next request -- an OCP to solve
+(`SolveReq`, the arguments of `OCP_solve`) or one RK4 step to simulate (`SimReq`) -- and is resumed with
+the answer.  `run_workers` advances all live generators round by round and serves each round's
+requests with ONE batched GPU call per kind (`BatchSolver.solve`, `sim_step`), so the host control flow
+stays per-problem and faithful while the solves of a round run side by side on the GPU.
+
+  testing_worker           triplependulum_testdata.py:9-125, doublependulum_testdata.py:10-121
+  data_generation_worker   VBOC/triplependulum_vboc.py:19-370 (VBOC/doublependulum_vboc.py:19-402 has the
+                           same structure; its gravity-compensation torque guess :84 is applied for n = 2)
+
+The random draws follow the reference's distributions but come from a per-problem Philox stream
+(seed, problem id): the reference uses the unseeded `random` module.
+Deliberate deviation: `testing` retries forever in the reference (`while True`); here a problem gives up
+after `max_solves` solves and is reported as failed.
+"""
+import numpy as np
+
+from . import problems as pr
+from ._lib import MODE_SQP
+
+N_CAP = 128  # largest horizon the engine is created for (reference horizons stay below ~115)
+
+
+class SolveReq:
+    """Arguments of `OCP_solve` (VBOC/triplependulum_class_vboc.py:155) for the current `ocp.N`."""
+    __slots__ = ("N", "x_guess", "u_guess", "p", "q_lb", "q_ub", "u_lb", "u_ub", "q_init_lb", "q_init_ub",
+                 "q_fin_lb", "q_fin_ub")
+
+    def __init__(self, N, x_guess, u_guess, p, q_lb, q_ub, u_lb, u_ub, q_init_lb, q_init_ub, q_fin_lb, q_fin_ub):
+        self.N, self.x_guess, self.u_guess, self.p = N, x_guess, u_guess, p
+        self.q_lb, self.q_ub, self.u_lb, self.u_ub = q_lb, q_ub, u_lb, u_ub
+        self.q_init_lb, self.q_init_ub, self.q_fin_lb, self.q_fin_ub = q_init_lb, q_init_ub, q_fin_lb, q_fin_ub
+
+
+class SimReq:
+    """`sim.acados_integrator` set x / u / T, solve, get x (VBOC/triplependulum_vboc.py:347-352)."""
+    __slots__ = ("x", "u", "T")
+
+    def __init__(self, x, u, T):
+        self.x, self.u, self.T = x, u, T
+
+
+class SolveAns:
+    __slots__ = ("status", "cost", "x", "u")
+
+    def __init__(self, status, cost, x, u):
+        self.status, self.cost, self.x, self.u = status, cost, x, u
+
+
+def _rng(seed, pid):
+    return np.random.Generator(np.random.Philox(key=int(seed), counter=[0, 0, 0, int(pid)]))
+
+
+def _pm(rng):
+    return -1.0 if rng.random() < 0.5 else 1.0
+
+
+def _pack(n, reqs):
+    """SolveReq list -> batched problem dict for `BatchSolver.solve` (stage N takes the last guess row)."""
+    B, nx = len(reqs), 2 * n + 1
+    bp = dict(n=n, family="vboc", N=np.array([r.N for r in reqs], dtype=np.int32),
+              x_guess=np.zeros((B, N_CAP + 1, nx)), u_guess=np.zeros((B, N_CAP, n)),
+              p=np.stack([r.p for r in reqs]))
+    for b, r in enumerate(reqs):
+        xg, ug = pr.expand_guess(r.x_guess, r.u_guess, r.N)
+        bp["x_guess"][b, :r.N + 1] = xg
+        bp["u_guess"][b, :r.N] = ug
+    for key, attr in (("lbx0", "q_init_lb"), ("ubx0", "q_init_ub"), ("lbx", "q_lb"), ("ubx", "q_ub"),
+                      ("lbxN", "q_fin_lb"), ("ubxN", "q_fin_ub"), ("lbu", "u_lb"), ("ubu", "u_ub")):
+        bp[key] = np.stack([getattr(r, attr) for r in reqs])
+    bp["C0"] = pr.stage0_projector(bp["p"][:, :n], nx)
+    return bp
+
+
+def run_workers(n, workers, solver, sim_step, stats=None):
+    """Advance the generators until all have returned; returns their return values in order.
+
+    solver.solve(bp, mode) -> dict(status, cost, x, u) (a `BatchSolver`, or the oracle in the CPU tests);
+    sim_step(n, X, U, T) -> X_next."""
+    results = [None] * len(workers)
+    pending = {}
+    for i, w in enumerate(workers):
+        try:
+            pending[i] = next(w)
+        except StopIteration as e:
+            results[i] = e.value
+    rounds = 0
+    while pending:
+        rounds += 1
+        answers = {}
+        sol_ids = [i for i, r in pending.items() if isinstance(r, SolveReq)]
+        sim_ids = [i for i, r in pending.items() if isinstance(r, SimReq)]
+        if sol_ids:
+            out = solver.solve(_pack(n, [pending[i] for i in sol_ids]), MODE_SQP)
+            for b, i in enumerate(sol_ids):
+                N = pending[i].N
+                answers[i] = SolveAns(int(out["status"][b]), float(out["cost"][b]), out["x"][b, :N + 1].copy(),
+                                      out["u"][b, :N].copy())
+            if stats is not None:
+                stats["solves"] = stats.get("solves", 0) + len(sol_ids)
+                stats["converged"] = stats.get("converged", 0) + int((out["status"] == 0).sum())
+        if sim_ids:
+            T = pending[sim_ids[0]].T
+            Xn = sim_step(n, np.stack([pending[i].x for i in sim_ids]), np.stack([pending[i].u for i in sim_ids]), T)
+            for b, i in enumerate(sim_ids):
+                answers[i] = Xn[b]
+        for i, ans in answers.items():
+            try:
+                pending[i] = workers[i].send(ans)
+            except StopIteration as e:
+                results[i] = e.value
+                del pending[i]
+    if stats is not None:
+        stats["rounds"] = rounds
+    return results
+
+
+# ------------------------------------------------------------------------------------------------
+def _limits(n, mdl, dt_sym):
+    q_min, q_max, v_max, tau = mdl.thetamin, mdl.thetamax, mdl.dthetamax, mdl.umax
+    q_lb = np.array([q_min] * n + [-v_max] * n + [dt_sym])
+    q_ub = np.array([q_max] * n + [v_max] * n + [dt_sym])
+    q_fin_lb = np.array([q_min] * n + [0.0] * n + [dt_sym])
+    q_fin_ub = np.array([q_max] * n + [0.0] * n + [dt_sym])
+    return q_lb, q_ub, np.full(n, -tau), np.full(n, tau), q_fin_lb, q_fin_ub
+
+
+def _extended_guess(ans, n):
+    """Warm start for N+1 intervals: the solution plus its last state / a zero control
+    (VBOC/triplependulum_vboc.py:121-129)."""
+    return np.vstack([ans.x, ans.x[-1:]]), np.vstack([ans.u, np.zeros((2, n))])[:ans.u.shape[0] + 1]
+
+
+def testing_worker(n, rng, N0=100, dt_sym=1e-2, max_solves=60):
+    """One test-set point: maximise the initial velocity along a random direction from a uniformly random
+    position; extend the horizon while the (3-decimal rounded) cost still decreases by > cost_tol; on a
+    solver failure restart with the direction and position perturbed by <= 0.01."""
+    mdl = pr.Model(n)
+    # triplependulum_testdata.py:82 compares with the cost rounded to 3 decimals minus 1e-3,
+    # doublependulum_testdata.py:80 with 4 decimals minus 1e-4
+    digits, cost_tol = (4, 1e-4) if n == 2 else (3, 1e-3)
+    q_lb, q_ub, u_lb, u_ub, q_fin_lb, q_fin_ub = _limits(n, mdl, dt_sym)
+    ran = np.array([_pm(rng) * rng.random() for _ in range(n)])
+    q_init = mdl.thetamin + rng.random(n) * (mdl.thetamax - mdl.thetamin)
+
+    def fresh(N):
+        xg = np.tile(np.concatenate([q_init, np.zeros(n), [dt_sym]]), (N, 1))
+        ug = np.tile(mdl.gravity_comp(q_init) if n == 2 else np.zeros(n), (N, 1))
+        return xg, ug
+
+    N, cost = N0, 1e6
+    xg, ug = fresh(N)
+    last = None
+    for _ in range(max_solves):
+        p = np.concatenate([ran / np.linalg.norm(ran), [0.0]])
+        lb0 = np.concatenate([q_init, np.full(n, -mdl.dthetamax), [dt_sym]])
+        ub0 = np.concatenate([q_init, np.full(n, mdl.dthetamax), [dt_sym]])
+        ans = yield SolveReq(N, xg, ug, p, q_lb, q_ub, u_lb, u_ub, lb0, ub0, q_fin_lb, q_fin_ub)
+        if ans.status == 0:
+            last = ans
+            if ans.cost > round(cost, digits) - cost_tol or N + 1 > N_CAP:
+                return ans.x[0, :2 * n].copy()
+            cost = ans.cost
+            xg, ug = _extended_guess(ans, n)
+            N += 1
+        else:
+            N = N0
+            ran = ran + np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
+            q_init = q_init + np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
+            xg, ug = fresh(N)
+            cost = 1e6
+    return None if last is None else last.x[0, :2 * n].copy()
+
+
+def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
+    """One VBOC problem: an extreme trajectory from a position limit of a randomly selected joint, then the
+    walk along it that classifies every state (on the boundary of the viability kernel, on a state limit,
+    or inside) with sub-OCPs and the simulated unviable twin.  Returns the list of saved rows [q, v] or None."""
+    mdl = pr.Model(n)
+    eps = 10 * tol
+    q_min, q_max, v_max = mdl.thetamin, mdl.thetamax, mdl.dthetamax
+    q_lb, q_ub, u_lb, u_ub, q_fin_lb, q_fin_ub = _limits(n, mdl, dt_sym)
+
+    def nudge(q):
+        q = q - eps if q > q_max - eps else q
+        return q + eps if q < q_min + eps else q
+
+    joint_sel = int(rng.integers(0, n))
+    vel_sel = _pm(rng)
+    q_init_sel, q_fin_sel = (q_min, q_max) if vel_sel < 0 else (q_max, q_min)
+    ran = np.array([vel_sel * rng.random()] + [_pm(rng) * rng.random() for _ in range(n - 1)])
+    ran = ran / np.linalg.norm(ran)
+    others = [j for j in range(n) if j != joint_sel]
+    p = np.zeros(n + 1)
+    p[joint_sel] = ran[0]
+    p[others] = ran[1:]
+    q0 = np.array([nudge(q_min + rng.random() * (q_max - q_min)) for _ in range(n)])
+    lb0 = np.concatenate([q0, np.full(n, -v_max), [dt_sym]])
+    ub0 = np.concatenate([q0, np.full(n, v_max), [dt_sym]])
+    lb0[joint_sel] = ub0[joint_sel] = q_min + eps if vel_sel < 0 else q_max - eps
+
+    def ramp_guess(N):
+        tau = np.linspace(0, 1, N)
+        xg = np.tile(np.concatenate([lb0[:n], np.zeros(n), [dt_sym]]), (N, 1))
+        xg[:, joint_sel] = (1 - tau) * q_init_sel + tau * q_fin_sel
+        xg[:, n + joint_sel] = 2 * (1 - tau) * (q_fin_sel - q_init_sel)
+        ug = np.stack([mdl.gravity_comp(x[:n]) for x in xg]) if n == 2 else np.zeros((N, n))
+        return xg, ug
+
+    # ---- extreme trajectory: at most 10 solves, horizon + 1 while the cost decreases by more than tol
+    N, cost, sol = N0, 1e6, None
+    xg, ug = ramp_guess(N)
+    for _ in range(10):
+        ans = yield SolveReq(N, xg, ug, p, q_lb, q_ub, u_lb, u_ub, lb0, ub0, q_fin_lb, q_fin_ub)
+        if ans.status == 0:
+            if ans.cost > cost - tol or N + 1 > N_CAP:
+                sol = ans
+                break
+            cost = ans.cost
+            xg, ug = _extended_guess(ans, n)
+            N += 1
+        else:
+            N = N0
+            d = p[:n] + np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
+            p = np.concatenate([d / np.linalg.norm(d), [0.0]])
+            dev = rng.random() * _pm(rng) * 0.01
+            for j in others:
+                lb0[j] = ub0[j] = nudge(lb0[j] + dev)
+            xg, ug = ramp_guess(N)
+            cost = 1e6
+    if sol is None:
+        return None
+
+    x_sol, u_sol = sol.x[:, :2 * n].copy(), sol.u.copy()
+    rows = [x_sol[0].copy()]
+    x_sym = [None] * (N + 1)
+
+    def v_out_of_box(x):
+        return bool(np.any(x[n:] > v_max) or np.any(x[n:] < -v_max))
+
+    def q_near_limit(x):
+        return bool(np.any(x[:n] > q_max - eps) or np.any(x[:n] < q_min + eps))
+
+    x_out = x_sol[0].copy()
+    x_out[n:] -= eps * p[:n]
+    at_limit = v_out_of_box(x_out)
+    if not at_limit:
+        x_sym[0] = x_out
+
+    for f in range(1, N):
+        if at_limit:
+            x_out = x_sol[f].copy()
+            x_out[n:] += eps * x_out[n:] / np.linalg.norm(x_out[n:])
+            if q_near_limit(x_sol[f]) or v_out_of_box(x_out):
+                at_limit = True
+            else:
+                at_limit = False
+                if q_near_limit(x_sol[f - 1]):
+                    break  # leaving a position limit the trajectory usually enters the kernel
+                # sub-OCP from x_sol[f]: is the rest of the trajectory on the boundary or inside?
+                N_t = N - f
+                vf = x_sol[f, n:]
+                p = np.concatenate([-vf / np.linalg.norm(vf), [0.0]])
+                lb_s = np.concatenate([x_sol[f, :n], np.full(n, -v_max), [dt_sym]])
+                ub_s = np.concatenate([x_sol[f, :n], np.full(n, v_max), [dt_sym]])
+                dtc = np.full((N - f + 1, 1), dt_sym)
+                xg = np.hstack([x_sol[f:N + 1], dtc])
+                ug = np.vstack([u_sol[f:N], np.zeros((1, n))])
+                norm_old, norm_bef, norm_new, ok, sub = np.linalg.norm(vf), 0.0, 0.0, False, None
+                for _ in range(5):
+                    ans = yield SolveReq(N_t, xg, ug, p, q_lb, q_ub, u_lb, u_ub, lb_s, ub_s, q_fin_lb, q_fin_ub)
+                    if ans.status != 0:
+                        break
+                    sub = ans
+                    norm_new = np.linalg.norm(ans.x[0, n:2 * n])
+                    if norm_new < norm_bef + tol or N_t + 1 > N_CAP:
+                        ok = True
+                        break
+                    norm_bef = norm_new
+                    xg, ug = _extended_guess(ans, n)
+                    N_t += 1
+                if ok:
+                    if norm_new > norm_old + tol:  # the state is inside the kernel: adopt the better tail
+                        x_sol[f:N] = sub.x[:N - f, :2 * n]
+                        u_sol[f:N] = sub.u[:N - f]
+                        x_out = x_sol[f].copy()
+                        x_out[n:] += eps * x_out[n:] / norm_new
+                        at_limit = v_out_of_box(x_out)
+                        if not at_limit:
+                            x_sym[f] = x_out
+                    else:  # on the boundary: the unviable twin lies in the cost direction
+                        x_out = x_sol[f].copy()
+                        x_out[n:] -= eps * p[:n]
+                        x_out[n + joint_sel] = min(max(x_out[n + joint_sel], -v_max), v_max)
+                        x_sym[f] = x_out
+                else:  # undecided: keep the state once per later state at a velocity limit, then stop
+                    for r in range(f, N):
+                        if np.any(np.abs(x_sol[r, n:]) > v_max - eps):
+                            rows.append(x_sol[f].copy())
+                    break
+        else:
+            x_out = yield SimReq(x_sym[f - 1].copy(), u_sol[f - 1].copy(), dt_sym)
+            x_sym[f] = x_out
+            at_limit = bool(np.any(x_out[:n] > q_max) or np.any(x_out[:n] < q_min) or v_out_of_box(x_out))
+        if not q_near_limit(x_sol[f]) and np.all(np.abs(x_sol[f, n:]) > tol):
+            rows.append(x_sol[f].copy())
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------
+def _gpu_backend(n, capacity, device):
+    from . import engine
+    solver = engine.BatchSolver(n, "vboc", capacity, N_CAP, device=device)
+    return solver, (lambda n_, X, U, T: engine.sim_step(n_, X, U, T, device))
+
+
+def testing_batch(n, num_prob, seed, device=0, backend=None, stats=None):
+    """`Pool.map(testing, range(num_prob))` (triplependulum_testdata.py:141-142) -> X_test (rows [q, v]);
+    failed problems are dropped."""
+    solver, sim = backend or _gpu_backend(n, num_prob, device)
+    res = run_workers(n, [testing_worker(n, _rng(seed, i)) for i in range(num_prob)], solver, sim, stats)
+    return np.array([r for r in res if r is not None]).reshape(-1, 2 * n)
+
+
+def data_generation_batch(n, num_prob, seed, device=0, backend=None, stats=None):
+    """`Pool.map(data_generation, range(num_prob))` + the flattening of `traj`
+    (VBOC/triplependulum_vboc.py:399-405) -> X_save (rows [q, v])."""
+    solver, sim = backend or _gpu_backend(n, num_prob, device)
+    res = run_workers(n, [data_generation_worker(n, _rng(seed, i)) for i in range(num_prob)], solver, sim, stats)
+    rows = [np.asarray(r) for r in res if r is not None and len(r)]
+    if stats is not None:
+        stats["problems"] = num_prob
+        stats["problems_ok"] = len(rows)
+    return np.concatenate(rows).reshape(-1, 2 * n) if rows else np.empty((0, 2 * n))

@@ -21,6 +21,8 @@
  *                                (VBOC/triplependulum_vboc.py:399-402)
  *   vboc_upload / vboc_solve_resident / vboc_download
  *                                the same three steps split so that inputs may stay resident in HBM
+ *   vboc_mlp_create / _forward   model_dir(...) / sigmoid(model(...)) + entropy: my_nn.py:4-34,
+ *                                VBOC/triplependulum_vboc.py:604-620, AL/triplependulum_al.py:253-264
  *   vboc_sim_step                SYMtriplependulumINIT.acados_integrator set/solve/get
  *                                VBOC/triplependulum_class_vboc.py:194-239, VBOC/triplependulum_vboc.py:348-352
  */
@@ -127,6 +129,25 @@ double vboc_last_kernel_ms(vboc_solver *s);
  * x [batch][2n], u [batch][n], x_next [batch][2n]. */
 int vboc_sim_step(int n_dof, int device, int batch, const double *x, const double *u, double T,
                   double *x_next);
+
+/*
+ * Inference of the reference's MLPs (my_nn.py:4-34; hidden 100/300/500, n_in = 2n, n_out 1 or 2) with the
+ * drivers' input normalisation and label / margin / entropy epilogues fused in.  Weights are HOST float
+ * arrays in PyTorch nn.Linear layout ([out_features][in_features]); final_relu = 1 for NeuralNetDIR.
+ * vboc_mlp_forward: x HOST [batch][n_in] raw states, out [batch][n_out];
+ *   mode 0: x already normalised;
+ *   mode 1 (VBOC/triplependulum_vboc.py:604-620): in = [(q-mean)/std, v/|v|]; label = |v| > phi ? 0 : 1;
+ *          aux = phi*(100-safety_margin)/100 - |v|;
+ *   mode 2 (AL/triplependulum_al.py:253-264): in = (x-mean)/std; aux = entropy of the renormalised
+ *          sigmoid(logits).   aux / label may be NULL.
+ */
+typedef struct vboc_mlp vboc_mlp;
+int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu, const float *W1,
+                    const float *b1, const float *W2, const float *b2, const float *W3, const float *b3,
+                    vboc_mlp **out);
+void vboc_mlp_destroy(vboc_mlp *m);
+int vboc_mlp_forward(vboc_mlp *m, int batch, const float *x, int mode, double mean, double stdv,
+                     double safety_margin, float *out, float *aux, int *label);
 
 /* Measured FP64 FMA peak of the device in TFLOP/s (dependent-free DFMA chains on every SM): the
  * roofline denominator bench.py reports against (MEASURED_PEAKS.json has no FP64 entry). */

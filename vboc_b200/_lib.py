@@ -18,7 +18,7 @@ EXPORTS = (
     "vboc_default_opts", "vboc_create", "vboc_destroy", "vboc_set_opts", "vboc_set_stream",
     "vboc_solve_batch", "vboc_upload", "vboc_solve_resident", "vboc_solve_resident_async", "vboc_sync",
     "vboc_download", "vboc_last_kernel_ms",
-    "vboc_sim_step", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
+    "vboc_sim_step", "vboc_mlp_create", "vboc_mlp_destroy", "vboc_mlp_forward", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
 )
 
 
@@ -79,6 +79,11 @@ def lib():
         L.vboc_last_kernel_ms.argtypes = [vp]
         L.vboc_last_kernel_ms.restype = C.c_double
         L.vboc_sim_step.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, dp]
+        fp = C.POINTER(C.c_float)
+        L.vboc_mlp_create.argtypes = [C.c_int] * 5 + [fp] * 6 + [C.POINTER(vp)]
+        L.vboc_mlp_destroy.argtypes = [vp]
+        L.vboc_mlp_destroy.restype = None
+        L.vboc_mlp_forward.argtypes = [vp, C.c_int, fp, C.c_int, C.c_double, C.c_double, C.c_double, fp, fp, ip]
         L.vboc_fp64_peak.argtypes = [C.c_int, dp]
         L.vboc_last_error.restype = C.c_char_p
         L.vboc_version.restype = C.c_char_p

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/vboc_b200.h"
+#include "mlp_forward.cuh"
 #include "ocp_warp.h"
 
 using namespace vboc;
@@ -440,6 +441,74 @@ int vboc_solve_batch(vboc_solver *s, int mode, int batch, const int *N, const do
     if (rc) return rc;
     if ((rc = vboc_solve_resident(s, mode))) return rc;
     return vboc_download(s, x, u, stats);
+}
+
+struct vboc_mlp {
+    int device, n_in, hidden, n_out, final_relu;
+    float *W1, *b1, *W2T, *b2, *W3, *b3;
+};
+
+int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu, const float *W1,
+                    const float *b1, const float *W2, const float *b2, const float *W3, const float *b3,
+                    vboc_mlp **out) {
+    if (!out || n_in < 2 || n_in > MLP_MAX_IN || hidden < 1 || hidden > 1024 || n_out < 1 || n_out > MLP_MAX_OUT ||
+        !W1 || !b1 || !W2 || !b2 || !W3 || !b3)
+        return fail(VBOC_ERR_ARG, "vboc_mlp_create: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    vboc_mlp *m = new vboc_mlp();
+    m->device = device, m->n_in = n_in, m->hidden = hidden, m->n_out = n_out, m->final_relu = final_relu;
+    std::vector<float> w2t((size_t)hidden * hidden);
+    for (int j = 0; j < hidden; ++j)
+        for (int k = 0; k < hidden; ++k) w2t[(size_t)k * hidden + j] = W2[(size_t)j * hidden + k];
+#define UPF(ptr, src, count)                                                         \
+    CUDA_OK(cudaMalloc((void **)&m->ptr, (size_t)(count) * sizeof(float)));         \
+    CUDA_OK(cudaMemcpy(m->ptr, src, (size_t)(count) * sizeof(float), cudaMemcpyHostToDevice))
+    UPF(W1, W1, hidden * n_in);
+    UPF(b1, b1, hidden);
+    UPF(W2T, w2t.data(), (size_t)hidden * hidden);
+    UPF(b2, b2, hidden);
+    UPF(W3, W3, n_out * hidden);
+    UPF(b3, b3, n_out);
+#undef UPF
+    *out = m;
+    return 0;
+}
+
+void vboc_mlp_destroy(vboc_mlp *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->W1), cudaFree(m->b1), cudaFree(m->W2T), cudaFree(m->b2), cudaFree(m->W3), cudaFree(m->b3);
+    delete m;
+}
+
+int vboc_mlp_forward(vboc_mlp *m, int batch, const float *x, int mode, double mean, double stdv,
+                     double safety_margin, float *out, float *aux, int *label) {
+    if (!m || batch < 1 || !x || !out || mode < 0 || mode > 2) return fail(VBOC_ERR_ARG, "vboc_mlp_forward: bad argument");
+    CUDA_OK(cudaSetDevice(m->device));
+    float *dx = nullptr, *dout = nullptr, *daux = nullptr;
+    int *dlab = nullptr;
+    size_t B = batch;
+    CUDA_OK(cudaMalloc((void **)&dx, B * m->n_in * sizeof(float)));
+    CUDA_OK(cudaMalloc((void **)&dout, B * m->n_out * sizeof(float)));
+    CUDA_OK(cudaMalloc((void **)&daux, B * sizeof(float)));
+    CUDA_OK(cudaMalloc((void **)&dlab, B * sizeof(int)));
+    CUDA_OK(cudaMemcpy(dx, x, B * m->n_in * sizeof(float), cudaMemcpyHostToDevice));
+    MlpParams P;
+    P.batch = batch, P.n_in = m->n_in, P.hidden = m->hidden, P.n_out = m->n_out, P.mode = mode;
+    P.final_relu = m->final_relu;
+    P.mean = (float)mean, P.stdv = (float)stdv, P.margin_scale = (float)((100.0 - safety_margin) / 100.0);
+    P.W1 = m->W1, P.b1 = m->b1, P.W2T = m->W2T, P.b2 = m->b2, P.W3 = m->W3, P.b3 = m->b3;
+    P.x = dx, P.out = dout, P.aux = daux, P.label = dlab;
+    size_t smem = mlp_smem_bytes(m->hidden);
+    CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (batch + MLP_ROWS - 1) / MLP_ROWS;
+    mlp_forward_kernel<<<grid, MLP_THREADS, smem>>>(P);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(out, dout, B * m->n_out * sizeof(float), cudaMemcpyDeviceToHost));
+    if (aux) CUDA_OK(cudaMemcpy(aux, daux, B * sizeof(float), cudaMemcpyDeviceToHost));
+    if (label) CUDA_OK(cudaMemcpy(label, dlab, B * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dx), cudaFree(dout), cudaFree(daux), cudaFree(dlab);
+    return 0;
 }
 
 int vboc_fp64_peak(int device, double *tflops) {

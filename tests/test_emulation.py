@@ -28,9 +28,12 @@ def _opts(emu, oo):
     return o
 
 
-@pytest.mark.parametrize("n,fam,mode", [(3, 0, 0), (2, 0, 0), (3, 1, 1), (2, 1, 1), (1, 1, 1)])
+@pytest.mark.parametrize("n,fam,mode", [(3, 0, 0), (2, 0, 0), (1, 0, 0), (3, 1, 1), (2, 1, 1), (1, 1, 1)])
 def test_lane_program_matches_oracle(oracle, emu, n, fam, mode):
-    bp = pr.sample_vboc(n, 6, seed=1) if fam == 0 else pr.sample_al(n, 24, seed=2)
+    if fam == 0:
+        bp = pr.sample_vboc(n, 6, seed=1) if n > 1 else pr.sample_testdata(1, 6, seed=1)
+    else:
+        bp = pr.sample_al(n, 24, seed=2)
     oo = oracle.default_opts(fam)
     ref = oracle.solve_batch(n, fam, mode, bp, oo)
     out = emu.solve_batch(n, fam, mode, bp, _opts(emu, oo))

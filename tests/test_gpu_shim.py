@@ -86,3 +86,43 @@ def test_compute_problem_labels(oracle, mod, cls, n):
         if lab == 1:
             traj = np.array([ocp.ocp_solver.get(i, "x") for i in range(ocp.N + 1)])
             assert np.abs(traj - ref["x"][b]).max() < 1e-6
+
+
+def test_pendulum_testdata_like_the_script(oracle):
+    """pendulum_testdata.py:7-53: pinned dt, p = [+-1, 0], one solve, N = 50; and the free-dt OCP_solve of
+    VBOC/pendulum_vboc.py is refused, not mis-solved."""
+    from vboc_b200._lib import VbocError
+    ocp = _load("VBOC", "pendulum_class_vboc").OCPpendulum()
+    N, dt = ocp.N, 1e-2
+    q_min, q_max, v_max = ocp.thetamin, ocp.thetamax, ocp.dthetamax
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        p = np.array([rng.choice([-1.0, 1.0]), 0.0])
+        q_init = q_min + rng.random() * (q_max - q_min)
+        xg = np.full((N, 3), np.array([q_init, 0.0, dt]))
+        s = ocp.ocp_solver
+        s.reset()
+        for i in range(N):
+            s.set(i, "x", xg[i])
+            s.set(i, "p", p)
+            s.constraints_set(i, "lbx", np.array([q_min, -v_max, dt]))
+            s.constraints_set(i, "ubx", np.array([q_max, v_max, dt]))
+        s.constraints_set(0, "lbx", np.array([q_init, -v_max, dt]))
+        s.constraints_set(0, "ubx", np.array([q_init, v_max, dt]))
+        s.constraints_set(N, "lbx", np.array([q_min, 0.0, dt]))
+        s.constraints_set(N, "ubx", np.array([q_max, 0.0, dt]))
+        s.set(N, "x", xg[-1])
+        s.set(N, "p", p)
+        status = s.solve()
+        prob = dict(x_guess=np.vstack([xg, xg[-1:]]), u_guess=np.zeros((N, 1)), p=p,
+                    lbx0=np.array([q_init, -v_max, dt]), ubx0=np.array([q_init, v_max, dt]),
+                    lbx=np.array([q_min, -v_max, dt]), ubx=np.array([q_max, v_max, dt]),
+                    lbxN=np.array([q_min, 0.0, dt]), ubxN=np.array([q_max, 0.0, dt]),
+                    lbu=np.array([-3.0]), ubu=np.array([3.0]), C0=None)
+        ref = oracle.solve(1, 0, 0, prob)
+        assert status == ref["status"]
+        if status == 0:
+            assert np.abs(s.get(0, "x") - ref["x"][0]).max() < 1e-5
+    with pytest.raises(VbocError):
+        ocp.OCP_solve(np.tile([3.0, 0.0, 1e-2], (N + 1, 1)), np.zeros((N, 1)), 1.0,
+                      np.array([q_min, -v_max, 0.0]), np.array([q_max, v_max, 1e-2]), 3.0, 3.2)

@@ -51,7 +51,8 @@ def test_al_classes(mod, cls, n):
     assert (s.lbx[100, n:] == 0).all() and (s.ubx[100, n:] == 0).all()  # terminal zero velocity
 
 
-def test_free_dt_pendulum_is_refused_loudly():
+def test_pendulum_vboc_class_surface():
     m = _load("VBOC", "pendulum_class_vboc")
-    with pytest.raises(NotImplementedError):
-        m.OCPpendulum()
+    ocp = m.OCPpendulum()
+    assert ocp.N == 50 and ocp.Fmax == 3 and ocp.ocp.dims.nx == 3
+    assert callable(ocp.OCP_solve) and callable(ocp.ocp_solver.solve)

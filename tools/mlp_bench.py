@@ -1,0 +1,23 @@
+"""Throughput and cross-check of the two MLP inference kernels (tcgen05 3xTF32 vs FP32 CUDA cores)."""
+import os, sys, time
+sys.path.insert(0, '.')
+import numpy as np, torch, torch.nn as nn
+from vboc_b200 import nn as vnn
+n, H, B = 3, 500, 1 << 20
+torch.manual_seed(0)
+m = nn.Module(); m.linear_relu_stack = nn.Sequential(nn.Linear(2*n, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU(), nn.Linear(H, 2))
+rng = np.random.default_rng(0)
+X = np.concatenate([rng.uniform(2.36, 3.93, (B, n)), rng.uniform(-10.5, 10.5, (B, n))], axis=1).astype(np.float32)
+with torch.no_grad():
+    ref = m.linear_relu_stack((torch.from_numpy(X[:65536]) - 3.0) / 5.0).numpy()
+res = {}
+for name, env in (("tcgen05_3xtf32", "0"), ("fp32_cuda_cores", "1")):
+    os.environ["VBOC_MLP_CUDA_CORES"] = env
+    net = vnn.MLP.from_torch(m)
+    net.entropy(X[:4096], 3.0, 5.0)
+    t = time.perf_counter(); out, etp = net.entropy(X, 3.0, 5.0); dt = time.perf_counter() - t
+    flops = 2.0 * B * (2*n*H + H*H + H*2)
+    print(f"{name}: {dt*1e3:.1f} ms for {B} rows incl. H2D/D2H  ({flops/dt/1e12:.2f} TFLOP/s algorithmic), max|out-torch| = {np.abs(out[:65536]-ref).max():.2e}")
+    res[name] = out
+    net.close()
+print("max |tc - fp32| =", np.abs(res["tcgen05_3xtf32"] - res["fp32_cuda_cores"]).max())

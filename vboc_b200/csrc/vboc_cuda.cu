@@ -16,6 +16,7 @@
 
 #include "../../include/vboc_b200.h"
 #include "mlp_forward.cuh"
+#include "mlp_tc.cuh"
 #include "ocp_warp.h"
 
 using namespace vboc;
@@ -445,7 +446,9 @@ int vboc_solve_batch(vboc_solver *s, int mode, int batch, const int *N, const do
 
 struct vboc_mlp {
     int device, n_in, hidden, n_out, final_relu;
-    float *W1, *b1, *W2T, *b2, *W3, *b3;
+    float *W1, *b1, *W2T, *b2, *W3, *b3;  // CUDA-core kernel (W2 transposed)
+    int Hp;                               // hidden size padded to a multiple of 32 (tensor-core kernel)
+    float *W1p, *b1p, *W2p, *b2p, *W3p;   // zero padded
 };
 
 int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu, const float *W1,
@@ -469,6 +472,23 @@ int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu,
     UPF(b2, b2, hidden);
     UPF(W3, W3, n_out * hidden);
     UPF(b3, b3, n_out);
+    {   // zero-padded copies for the tcgen05 kernel
+        const int Hp = (hidden + 31) / 32 * 32;
+        m->Hp = Hp;
+        std::vector<float> w1p((size_t)Hp * n_in, 0.f), b1p(Hp, 0.f), w2p((size_t)Hp * Hp, 0.f), b2p(Hp, 0.f),
+            w3p((size_t)n_out * Hp, 0.f);
+        for (int j = 0; j < hidden; ++j) {
+            for (int i = 0; i < n_in; ++i) w1p[(size_t)j * n_in + i] = W1[(size_t)j * n_in + i];
+            b1p[j] = b1[j], b2p[j] = b2[j];
+            for (int k = 0; k < hidden; ++k) w2p[(size_t)j * Hp + k] = W2[(size_t)j * hidden + k];
+            for (int o = 0; o < n_out; ++o) w3p[(size_t)o * Hp + j] = W3[(size_t)o * hidden + j];
+        }
+        UPF(W1p, w1p.data(), w1p.size());
+        UPF(b1p, b1p.data(), b1p.size());
+        UPF(W2p, w2p.data(), w2p.size());
+        UPF(b2p, b2p.data(), b2p.size());
+        UPF(W3p, w3p.data(), w3p.size());
+    }
 #undef UPF
     *out = m;
     return 0;
@@ -478,6 +498,7 @@ void vboc_mlp_destroy(vboc_mlp *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaFree(m->W1), cudaFree(m->b1), cudaFree(m->W2T), cudaFree(m->b2), cudaFree(m->W3), cudaFree(m->b3);
+    cudaFree(m->W1p), cudaFree(m->b1p), cudaFree(m->W2p), cudaFree(m->b2p), cudaFree(m->W3p);
     delete m;
 }
 
@@ -499,11 +520,25 @@ int vboc_mlp_forward(vboc_mlp *m, int batch, const float *x, int mode, double me
     P.mean = (float)mean, P.stdv = (float)stdv, P.margin_scale = (float)((100.0 - safety_margin) / 100.0);
     P.W1 = m->W1, P.b1 = m->b1, P.W2T = m->W2T, P.b2 = m->b2, P.W3 = m->W3, P.b3 = m->b3;
     P.x = dx, P.out = dout, P.aux = daux, P.label = dlab;
-    size_t smem = mlp_smem_bytes(m->hidden);
-    CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (batch + MLP_ROWS - 1) / MLP_ROWS;
-    mlp_forward_kernel<<<grid, MLP_THREADS, smem>>>(P);
+    // tensor cores (tcgen05, 3xTF32) for hidden sizes the 512-column TMEM holds; VBOC_MLP_CUDA_CORES=1 selects
+    // the plain FP32 kernel (kept as the cross-check of the tensor-core path)
+    const char *force = getenv("VBOC_MLP_CUDA_CORES");
+    if (m->Hp <= 512 && !(force && atoi(force))) {
+        P.W1 = m->W1p, P.b1 = m->b1p, P.W2T = m->W2p, P.b2 = m->b2p, P.W3 = m->W3p;
+        TcLayout lay(m->Hp);
+        int cols = 32;
+        while (cols < m->Hp) cols *= 2;
+        CUDA_OK(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total()));
+        int grid = (batch + TC_ROWS - 1) / TC_ROWS;
+        mlp_tc_kernel<<<grid, TC_THREADS, lay.total()>>>(P, m->Hp, cols);
+    } else {
+        size_t smem = mlp_smem_bytes(m->hidden);
+        CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = (batch + MLP_ROWS - 1) / MLP_ROWS;
+        mlp_forward_kernel<<<grid, MLP_THREADS, smem>>>(P);
+    }
     CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(out, dout, B * m->n_out * sizeof(float), cudaMemcpyDeviceToHost));
     if (aux) CUDA_OK(cudaMemcpy(aux, daux, B * sizeof(float), cudaMemcpyDeviceToHost));
     if (label) CUDA_OK(cudaMemcpy(label, dlab, B * sizeof(int), cudaMemcpyDeviceToHost));

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../vboc_b200/csrc/ocp_warp.h"
+#include "../../vboc_b200/csrc/ocp_lane.h"
 
 using namespace vboc;
 
@@ -43,6 +44,59 @@ static void run(int mode, int batch, int Nmax, const int *N, const double *xg, c
         }
         delete sm;
     }
+}
+
+// the lane-per-OCP solver with W = 1 (one "lane" at a time)
+template <int NQ, int FAM>
+static void run_lane(int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug,
+                     const double *p, const double *lbx0, const double *ubx0, const double *lbx,
+                     const double *ubx, const double *lbxN, const double *ubxN, const double *lbu,
+                     const double *ubu, const double *dir, const double *h, const vboc_opts *o, double *x,
+                     double *u, vboc_stats *st) {
+    const int nxr = 2 * NQ + (FAM == VBOC_FAMILY_VBOC), nu = NQ;
+#pragma omp parallel
+    {
+        std::vector<double> buf(LaneLayout<NQ>::TOTAL);
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < batch; ++b) {
+            Prob pb;
+            pb.N = N[b], pb.nxr = nxr, pb.h = h[b];
+            pb.wt = p ? p[(size_t)b * (NQ + 1) + NQ] : 0.0;
+            pb.xg = xg + (size_t)b * (Nmax + 1) * nxr, pb.ug = ug + (size_t)b * Nmax * nu;
+            pb.p = p ? p + (size_t)b * (NQ + 1) : nullptr;
+            pb.lbx0 = lbx0 + (size_t)b * nxr, pb.ubx0 = ubx0 + (size_t)b * nxr;
+            pb.lbx = lbx + (size_t)b * nxr, pb.ubx = ubx + (size_t)b * nxr;
+            pb.lbxN = lbxN + (size_t)b * nxr, pb.ubxN = ubxN + (size_t)b * nxr;
+            pb.lbu = lbu + (size_t)b * nu, pb.ubu = ubu + (size_t)b * nu;
+            pb.dir = dir ? dir + (size_t)b * NQ : nullptr;
+            pb.x = x + (size_t)b * (Nmax + 1) * nxr, pb.u = u + (size_t)b * Nmax * nu;
+            pb.st = st + b;
+            LaneSolver<NQ, FAM, 1> sol(buf.data(), 0, *o);
+            LaneState ls;
+            sol.begin(ls, pb);
+            while (!sol.sqp_iteration(ls, mode)) {
+            }
+            sol.finish(ls, pb);
+        }
+    }
+}
+
+extern "C" int emu_lane_solve_batch(int n, int family, int mode, int batch, int Nmax, const int *N,
+                                    const double *xg, const double *ug, const double *p,
+                                    const double *lbx0, const double *ubx0, const double *lbx,
+                                    const double *ubx, const double *lbxN, const double *ubxN,
+                                    const double *lbu, const double *ubu, const double *dir,
+                                    const double *h, const vboc_opts *o, double *x, double *u,
+                                    vboc_stats *st) {
+#define GO(NQ, FAM)                                                                                   \
+    if (n == NQ && family == FAM) {                                                                   \
+        run_lane<NQ, FAM>(mode, batch, Nmax, N, xg, ug, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu, ubu, \
+                          dir, h, o, x, u, st);                                                       \
+        return 0;                                                                                     \
+    }
+    GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
+#undef GO
+    return -1;
 }
 
 extern "C" int emu_solve_batch(int n, int family, int mode, int batch, int Nmax, const int *N,

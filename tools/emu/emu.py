@@ -39,7 +39,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def solve_batch(n, family, mode, bp, opts):
+def solve_batch(n, family, mode, bp, opts, kernel="warp"):
     lib = C.CDLL(build() if not os.path.exists(os.path.join(_HERE, "libemu.so")) else os.path.join(_HERE, "libemu.so"))
     c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
     xg, ug = c(bp["x_guess"]), c(bp["u_guess"])
@@ -55,7 +55,8 @@ def solve_batch(n, family, mode, bp, opts):
         d = None
     x, u = np.zeros_like(xg), np.zeros_like(ug)
     st = (Stats * B)()
-    lib.emu_solve_batch(n, family, mode, B, Nmax, Nv.ctypes.data_as(C.POINTER(C.c_int)), _p(xg), _p(ug),
+    fn = lib.emu_solve_batch if kernel == "warp" else lib.emu_lane_solve_batch
+    fn(n, family, mode, B, Nmax, Nv.ctypes.data_as(C.POINTER(C.c_int)), _p(xg), _p(ug),
                         *[_p(a) for a in keep], _p(d), _p(h), C.byref(opts), _p(x), _p(u), st)
     f = lambda name: np.array([getattr(s_, name) for s_ in st])
     return dict(status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),

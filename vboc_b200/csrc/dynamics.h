@@ -143,4 +143,150 @@ VB_HD void rk4_step(const T *x, const T *u, double h, T *xn) {
     for (int i = 0; i < NX; ++i) xn[i] = x[i] + (h / 6.0) * acc[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Analytic Jacobian of the accelerations (one thread evaluates a whole interval in the lane-per-OCP
+// kernel, where carrying nz forward tangents through the model would not fit the register file).
+//   M a = r  =>  da/dtheta = M^-1 (dr/dtheta - (dM/dtheta) a)
+// Ja is [NQ][3 NQ] in column order (q, v, u).
+template <int NQ>
+VB_HD void accel_jac(const double *q, const double *v, const double *u, double *a, double (*Ja)[3 * NQ]) {
+    if constexpr (NQ == 1) {
+        double s, c;
+        sincos_t(q[0], s, c);
+        const double inv = 1.0 / (Pend1::d * Pend1::d * Pend1::m);
+        a[0] = inv * ((Pend1::m * Pend1::g * Pend1::d) * s + (u[0] - Pend1::b * v[0]));
+        Ja[0][0] = inv * (Pend1::m * Pend1::g * Pend1::d) * c;
+        Ja[0][1] = -inv * Pend1::b;
+        Ja[0][2] = inv;
+    } else {
+        constexpr double ll = PendN::l * PendN::l;
+        double M[NQ][NQ], S[NQ][NQ], K[NQ][NQ], r[NQ], cq[NQ], v2[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            double si;
+            sincos_t(q[i], si, cq[i]);
+            v2[i] = v[i] * v[i];
+            r[i] = u[i] - (PendN::m * (NQ - i) * PendN::g * PendN::l) * si;
+            M[i][i] = PendN::m * (NQ - i) * ll;
+            S[i][i] = 0.0, K[i][i] = 1.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+#pragma unroll
+            for (int j = i + 1; j < NQ; ++j) {
+                double s, c;
+                sincos_t(q[i] - q[j], s, c);
+                const double cf = PendN::m * (NQ - j) * ll;
+                S[i][j] = cf * s, S[j][i] = -cf * s;  // c_ij sin(q_i - q_j)
+                K[i][j] = cf * c, K[j][i] = cf * c;   // c_ij cos(q_i - q_j)
+                M[i][j] = cf * c, M[j][i] = cf * c;
+                r[i] -= S[i][j] * v2[j];
+                r[j] -= S[j][i] * v2[i];
+            }
+        // LU of M without pivoting (SPD); reciprocal pivots kept on the diagonal
+        double Lf[NQ][NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) Lf[i][j] = M[i][j];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            Lf[k][k] = 1.0 / Lf[k][k];
+#pragma unroll
+            for (int i = k + 1; i < NQ; ++i) {
+                Lf[i][k] *= Lf[k][k];
+#pragma unroll
+                for (int j = k + 1; j < NQ; ++j) Lf[i][j] -= Lf[i][k] * Lf[k][j];
+            }
+        }
+        auto solve = [&](double *b) {  // in place: b <- M^-1 b
+#pragma unroll
+            for (int i = 1; i < NQ; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j) b[i] -= Lf[i][j] * b[j];
+#pragma unroll
+            for (int i = NQ - 1; i >= 0; --i) {
+#pragma unroll
+                for (int j = i + 1; j < NQ; ++j) b[i] -= Lf[i][j] * b[j];
+                b[i] *= Lf[i][i];
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) a[i] = r[i];
+        solve(a);
+        // columns of D = dr/dtheta - (dM/dtheta) a, then Ja = M^-1 D
+#pragma unroll
+        for (int m = 0; m < NQ; ++m) {
+            double dq[NQ], dv[NQ], du[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                if (i == m) {
+                    double t = -(PendN::m * (NQ - i) * PendN::g * PendN::l) * cq[i];
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j)
+                        if (j != i) t -= K[i][j] * v2[j] - S[i][j] * a[j];
+                    dq[i] = t;
+                    dv[i] = 0.0;
+                } else {
+                    dq[i] = K[i][m] * v2[m] - S[i][m] * a[m];
+                    dv[i] = -2.0 * S[i][m] * v[m];
+                }
+                du[i] = (i == m) ? 1.0 : 0.0;
+            }
+            solve(dq), solve(dv), solve(du);
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) Ja[i][m] = dq[i], Ja[i][NQ + m] = dv[i], Ja[i][2 * NQ + m] = du[i];
+        }
+    }
+}
+
+// One RK4 step with forward sensitivities: xn = Phi_h(x, u) and Phi = d xn / d z, z = [u; x]
+// ([2 NQ][3 NQ], column order (u, q, v)) -- what acados' ERK integrator returns as [B A].
+template <int NQ>
+VB_HD void rk4_sens(const double *x, const double *u, double h, double *xn, double (*Phi)[3 * NQ]) {
+    constexpr int NX = 2 * NQ, NZ = 3 * NQ;
+    double xt[NX], acc[NX], St[NX][NZ];  // stage point and its sensitivity d xt / d z
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        xt[i] = x[i], acc[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) St[i][j] = (j == NQ + i) ? 1.0 : 0.0, Phi[i][j] = 0.0;
+    }
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        double a[NQ], Ja[NQ][3 * NQ], Kx[NX], Ks[NX][NZ];
+        accel_jac<NQ>(xt, xt + NQ, u, a, Ja);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            Kx[i] = xt[NQ + i], Kx[NQ + i] = a[i];
+#pragma unroll
+            for (int j = 0; j < NZ; ++j) {
+                Ks[i][j] = St[NQ + i][j];  // d v / d z
+                double t = (j < NQ) ? Ja[i][2 * NQ + j] : 0.0;  // direct dependence on u
+#pragma unroll
+                for (int m = 0; m < NX; ++m) t += Ja[i][m] * St[m][j];
+                Ks[NQ + i][j] = t;
+            }
+        }
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0, adv = st == 2 ? h : 0.5 * h;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            acc[i] += wgt * Kx[i];
+            xt[i] = x[i] + adv * Kx[i];
+#pragma unroll
+            for (int j = 0; j < NZ; ++j) {
+                Phi[i][j] += wgt * Ks[i][j];
+                St[i][j] = ((j == NQ + i) ? 1.0 : 0.0) + adv * Ks[i][j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        xn[i] = x[i] + (h / 6.0) * acc[i];
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) Phi[i][j] = ((j == NQ + i) ? 1.0 : 0.0) + (h / 6.0) * Phi[i][j];
+    }
+}
+
 }  // namespace vboc

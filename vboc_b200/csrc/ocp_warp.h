@@ -69,6 +69,9 @@ struct Rec {
 };
 
 constexpr int RING_DEPTH = 4;
+#ifndef VB_PF_DIST
+#define VB_PF_DIST 64  // software prefetch distance of the flat passes: two lane-strided iterations ahead
+#endif
 
 // dot product with strides and two accumulators (halves the dependent FP64 chain of the sweeps)
 template <int LEN>
@@ -444,7 +447,7 @@ struct WarpSolver {
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             {
-                const int nidx = idx + 32, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
+                const int nidx = idx + VB_PF_DIST, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
                 if (nidx < (N + 1) * NZ) {
                     VB_PREFETCH(w.DZ + nidx), VB_PREFETCH(w.Z + nidx);
                     VB_PREFETCH(rec(nk) + R::BAT + (nidx - nk * NZ) * NX), VB_PREFETCH(w.PIQ + nk * NX);
@@ -1000,7 +1003,7 @@ struct WarpSolver {
             double *rk = rec(k);
             double q1 = 0.0, q2 = 0.0;
             {
-                const int nidx = idx + 32, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
+                const int nidx = idx + VB_PF_DIST, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
                 if (nidx < (N + 1) * NZ) {
                     VB_PREFETCH(w.DV + nidx);
                     VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
@@ -1089,17 +1092,17 @@ struct WarpSolver {
             // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
             FOR_LANES
             for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
-                if (idx + 32 < (N + 1) * NZ) VB_PREFETCH(w.DZ + idx + 32), VB_PREFETCH(w.DV + idx + 32);
+                if (idx + VB_PF_DIST < (N + 1) * NZ) VB_PREFETCH(w.DZ + idx + VB_PF_DIST), VB_PREFETCH(w.DV + idx + VB_PF_DIST);
                 w.DZ[idx] += as * w.DV[idx];
             }
             for (int idx = lane; idx < N * NX; idx += 32) {
                 int k = idx / NX, mI = idx - k * NX;
                 const double *dxn = w.DV + (size_t)(k + 1) * NZ + NU;
-                if (idx + 32 < N * NX) {
-                    const int nk = (idx + 32) / NX, nm = idx + 32 - nk * NX;
+                if (idx + VB_PF_DIST < N * NX) {
+                    const int nk = (idx + VB_PF_DIST) / NX, nm = idx + VB_PF_DIST - nk * NX;
                     VB_PREFETCH(w.PP + (size_t)(nk + 1) * Work<NQ>::PPS + nm * NX);
                     VB_PREFETCH(w.PP + (size_t)(nk + 1) * Work<NQ>::PPS + NX * NX + nm);
-                    VB_PREFETCH(w.PIQ + idx + 32);
+                    VB_PREFETCH(w.PIQ + idx + VB_PF_DIST);
                 }
                 double a;
                 if (k + 1 < N) {
@@ -1116,9 +1119,9 @@ struct WarpSolver {
             }
             for (int idx = lane; idx < (N + 1) * NC; idx += 32) {
                 int k = idx / NC, c = idx - k * NC, i = c >= NZ ? c - NZ : c;
-                if (idx + 32 < (N + 1) * NC) {
-                    VB_PREFETCH(w.LAMQ + idx + 32), VB_PREFETCH(w.DLAM + idx + 32);
-                    VB_PREFETCH(w.TQ + idx + 32), VB_PREFETCH(w.DT + idx + 32);
+                if (idx + VB_PF_DIST < (N + 1) * NC) {
+                    VB_PREFETCH(w.LAMQ + idx + VB_PF_DIST), VB_PREFETCH(w.DLAM + idx + VB_PF_DIST);
+                    VB_PREFETCH(w.TQ + idx + VB_PF_DIST), VB_PREFETCH(w.DT + idx + VB_PF_DIST);
                 }
                 if (active(k, i)) {
                     w.LAMQ[idx] = fmax(w.LAMQ[idx] + as * w.DLAM[idx], o.qp_lam_min);

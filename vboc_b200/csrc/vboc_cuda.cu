@@ -17,6 +17,7 @@
 #include "../../include/vboc_b200.h"
 #include "mlp_forward.cuh"
 #include "mlp_tc.cuh"
+#include "ocp_lane.h"
 #include "ocp_warp.h"
 
 using namespace vboc;
@@ -82,6 +83,48 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) solve_kernel(const B
     }
 }
 
+// solve_lane_kernel: one LANE per OCP (ocp_lane.h).  The 32 lanes of a warp advance 32 problems in
+// lockstep, one SQP iteration per trip of the loop; a lane whose problem finished pulls the next index
+// at the top of the loop, so the warp stays full until the queue is empty.
+constexpr int LANE_THREADS = 128;
+template <int NQ, int FAM>
+__global__ void __launch_bounds__(LANE_THREADS, 2) solve_lane_kernel(const Batch B) {
+    const int lane = threadIdx.x & 31;
+    const size_t wslot = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double *base = B.work + wslot * LaneLayout<NQ>::TOTAL * 32;
+    LaneSolver<NQ, FAM, 32> sol(base, lane, B.opts);
+    LaneState ls;
+    ls.have = 0, ls.it = 0;
+    Prob pb;
+    bool exhausted = false;
+    const int nu = NQ;
+    for (;;) {
+        if (!ls.have && !exhausted) {
+            unsigned int b = atomicAdd(B.counter, 1u);
+            if (b < (unsigned)B.batch) {
+                pb.N = B.N[b], pb.nxr = B.nxr, pb.h = B.h[b];
+                pb.p = B.p ? B.p + (size_t)b * (NQ + 1) : nullptr;
+                pb.wt = B.p ? pb.p[NQ] : 0.0;
+                pb.xg = B.xg + (size_t)b * (B.Nmax + 1) * B.nxr, pb.ug = B.ug + (size_t)b * B.Nmax * nu;
+                pb.lbx0 = B.lbx0 + (size_t)b * B.nxr, pb.ubx0 = B.ubx0 + (size_t)b * B.nxr;
+                pb.lbx = B.lbx + (size_t)b * B.nxr, pb.ubx = B.ubx + (size_t)b * B.nxr;
+                pb.lbxN = B.lbxN + (size_t)b * B.nxr, pb.ubxN = B.ubxN + (size_t)b * B.nxr;
+                pb.lbu = B.lbu + (size_t)b * nu, pb.ubu = B.ubu + (size_t)b * nu;
+                pb.dir = B.dir ? B.dir + (size_t)b * NQ : nullptr;
+                pb.x = B.x + (size_t)b * (B.Nmax + 1) * B.nxr, pb.u = B.u + (size_t)b * B.Nmax * nu;
+                pb.st = B.st + b;
+                sol.begin(ls, pb);
+            } else {
+                exhausted = true;
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, ls.have)) break;
+        if (ls.have && sol.sqp_iteration(ls, B.mode)) sol.finish(ls, pb);
+        __syncwarp();
+    }
+}
+
 // one RK4 step of the unscaled model per thread (the reference's AcadosSimSolver)
 template <int NQ>
 __global__ void sim_kernel(int batch, const double *x, const double *u, double T, double *xn) {
@@ -113,7 +156,7 @@ __global__ void dfma_peak_kernel(double *out, int iters) {
 
 struct vboc_solver {
     int n, family, cap, Nmax, device, nxr, nu;
-    int slots, grid, ctas_per_sm;
+    int slots, grid, ctas_per_sm, lane_kernel;
     cudaStream_t stream;
     vboc_opts opts;
     // device buffers
@@ -134,8 +177,14 @@ struct vboc_solver {
 
 template <int NQ, int FAM>
 static cudaError_t launch(vboc_solver *s, const Batch &B) {
+    if (s->lane_kernel) {
+        solve_lane_kernel<NQ, FAM><<<s->grid, LANE_THREADS, 0, s->stream>>>(B);
+        return cudaGetLastError();
+    }
     if (s->ctas_per_sm >= 6)
         solve_kernel<NQ, FAM, 6><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+    else if (s->ctas_per_sm == 5)
+        solve_kernel<NQ, FAM, 5><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
     else
         solve_kernel<NQ, FAM, 4><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
     return cudaGetLastError();
@@ -188,15 +237,28 @@ int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device
     vboc_default_opts(family, &s->opts);
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    // resident CTAs per SM: 4 (128 registers / thread) or 6 (85); VBOC_CTAS_PER_SM overrides for tuning
-    int ctas_per_sm = 4;
-    if (const char *e = getenv("VBOC_CTAS_PER_SM")) ctas_per_sm = atoi(e) >= 6 ? 6 : 4;
+    // resident CTAs per SM: 4 (128 registers / thread), 5 (96, measured best: 2.40 M vs 2.25 M IPM iterations/s)
+    // or 6 (80, spills); VBOC_CTAS_PER_SM overrides for tuning
+    int ctas_per_sm = 5;
+    if (const char *e = getenv("VBOC_CTAS_PER_SM")) ctas_per_sm = atoi(e) >= 6 ? 6 : (atoi(e) == 5 ? 5 : 4);
     s->ctas_per_sm = ctas_per_sm;
     int max_grid = prop.multiProcessorCount * ctas_per_sm;
     int need = (batch_capacity + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     s->grid = need < max_grid ? need : max_grid;
     s->slots = s->grid * WARPS_PER_CTA;
     s->work_doubles = work_doubles_for(n_dof, N_max);
+    // kernel mapping: VBOC_KERNEL=lane selects one lane per OCP (ocp_lane.h), default one warp per OCP
+    s->lane_kernel = 0;
+    if (const char *e = getenv("VBOC_KERNEL")) s->lane_kernel = strcmp(e, "lane") == 0;
+    if (s->lane_kernel) {
+        size_t per_lane = n_dof == 1 ? LaneLayout<1>::TOTAL : (n_dof == 2 ? LaneLayout<2>::TOTAL : LaneLayout<3>::TOTAL);
+        int warps_per_cta = LANE_THREADS / 32;
+        int max_g = prop.multiProcessorCount * 2;
+        int need_g = (batch_capacity + LANE_THREADS - 1) / LANE_THREADS;
+        s->grid = need_g < max_g ? need_g : max_g;
+        s->slots = s->grid * warps_per_cta;  // warp slots
+        s->work_doubles = per_lane * 32;     // per warp slot
+    }
     size_t B = (size_t)batch_capacity, nxr = s->nxr, nu = s->nu;
 #define DEV_ALLOC(ptr, count) CUDA_OK(cudaMalloc((void **)&s->ptr, (size_t)(count) * sizeof(*s->ptr)))
     DEV_ALLOC(dN, B);

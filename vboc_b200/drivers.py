@@ -337,3 +337,68 @@ def data_generation_batch(n, num_prob, seed, device=0, backend=None, stats=None)
         stats["problems"] = num_prob
         stats["problems_ok"] = len(rows)
     return np.concatenate(rows).reshape(-1, 2 * n) if rows else np.empty((0, 2 * n))
+
+
+# ------------------------------------------------------------------------------------------------
+# AL: feasibility labels and the active-learning query
+def al_label_batch(n, X, device=0, solver=None, N=100, Tf=1.0, x_guess=None):
+    """Batched `testing(s0)` / `testing_guess(s0)` of the AL drivers (AL/triplependulum_al.py:24-62):
+    states outside the position / velocity box are labelled unviable without solving (:27-28), the others
+    get one SQP_RTI solve (`compute_problem`, AL/triplependulum_class_al.py:148-169): label 1 if status 0,
+    0 if status 4 (QP failure), 2 otherwise.  `x_guess` (B, N+1, 2n) replaces the constant guess
+    (`compute_problem_nnguess`, :171-201).  Returns labels (B,) and the (N+1) x 2n trajectories (NaN rows
+    where no viable trajectory exists)."""
+    from . import engine
+    from ._lib import MODE_RTI
+    mdl = pr.Model(n)
+    X = np.asarray(X, dtype=float)
+    B = X.shape[0]
+    inside = (np.all(X[:, :n] >= mdl.thetamin, axis=1) & np.all(X[:, :n] <= mdl.thetamax, axis=1)
+              & np.all(np.abs(X[:, n:]) <= mdl.dthetamax, axis=1))
+    labels = np.zeros(B, dtype=np.int64)
+    traj = np.full((B, N + 1, 2 * n), np.nan)
+    idx = np.where(inside)[0]
+    if idx.size:
+        bp = pr.al_problems(n, X[idx], N=N, Tf=Tf, x_guess=None if x_guess is None else np.asarray(x_guess)[idx])
+        own = solver is None
+        sol = solver or engine.BatchSolver(n, "al", idx.size, N, device=device)
+        out = sol.solve(bp, MODE_RTI)
+        if own:
+            sol.close()
+        st = out["status"]
+        labels[idx] = np.where(st == 0, 1, np.where(st == 4, 0, 2))
+        ok = st == 0
+        traj[idx[ok]] = out["x"][ok][:, :N + 1]
+    return labels, traj
+
+
+def al_query(net, pool, mean, std, B, world_offset=0):
+    """Entropy of sigmoid(model((x - mean)/std)) over the unlabeled pool on the GPU and the B most
+    uncertain samples, largest index first (AL/triplependulum_al.py:253-281).  Returns (indices, entropy
+    of the pool); under torch.distributed the selection is global (`distributed.global_topk`)."""
+    import torch.distributed as dist
+    from . import distributed as vd
+    from . import nn as vnn
+    _, etp = net.entropy(pool, mean, std)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        idx, _ = vd.global_topk(etp, B, index_offset=world_offset)
+        return sorted(idx.tolist(), reverse=True), etp
+    return vnn.select_max_entropy(etp, B), etp
+
+
+# ------------------------------------------------------------------------------------------------
+# on-disk formats read by the untouched *_comparison.py scripts (SURVEY 8(f)3)
+def save_testdata(n, X_test, directory="."):
+    """`np.save('data3_test.npy', X_test)` (triplependulum_testdata.py:144-145): rows [q, v]."""
+    import os
+    path = os.path.join(directory, f"data{n}_test.npy")
+    np.save(path, np.asarray(X_test, dtype=float))
+    return path
+
+
+def save_vboc_data(n, X_save, directory="."):
+    """`np.save('data_3dof_vboc', np.asarray(X_save))` (VBOC/triplependulum_vboc.py:575-584): rows [q, v]."""
+    import os
+    path = os.path.join(directory, f"data_{n}dof_vboc.npy")
+    np.save(path, np.asarray(X_save, dtype=float))
+    return path

@@ -2,10 +2,11 @@
 function of ocp_warp.h / file, and the hottest source lines."""
 import collections, csv, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = open(os.path.join(ROOT, "vboc_b200", "csrc", "ocp_warp.h")).read().split("\n")
+SRC = sys.argv[3] if len(sys.argv) > 3 else "ocp_warp.h"
+src = open(os.path.join(ROOT, "vboc_b200", "csrc", SRC)).read().split("\n")
 meth, name = {}, "?"
 for i, l in enumerate(src, 1):
-    m = re.match(r"\s+VB_DEV\s+[\w:<>,\s\*&]+?\s+(\w+)\(", l)
+    m = re.match(r"\s+VB_(?:DEV|HD)\s+[\w:<>,\s\*&]+?\s+(\w+)\(", l)
     if m:
         name = m.group(1)
     meth[i] = name
@@ -32,7 +33,7 @@ for r in csv.reader(open(sys.argv[1])):
             return 0
     n = num(r[col["# Samples"]])
     ex = num(r[col["Instructions Executed"]])
-    key = meth.get(ln, "?") if cur_file == "ocp_warp.h" else cur_file
+    key = meth.get(ln, "?") if cur_file == SRC else cur_file
     by_fn[key]["samples"] += n
     by_fn[key]["inst"] += ex
     for st in hdr:

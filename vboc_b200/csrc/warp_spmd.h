@@ -35,6 +35,8 @@
 // software prefetch of the next lane-strided iteration (the flat passes are latency bound)
 __device__ __forceinline__ void vb_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #define VB_PREFETCH(p) vb_prefetch(p)
+__device__ __forceinline__ void vb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#define VB_PREFETCH_L2(p) vb_prefetch_l2(p)
 
 // out of line on purpose: ~20 call sites share one copy (instruction-cache footprint)
 __device__ __noinline__ double vb_warp_max(double v) {
@@ -125,6 +127,7 @@ __device__ __forceinline__ void vb_ring_wait(VbRing &r, int slot) {
 #define UNIFORM_SYNC() ((void)0)
 #define VB_RSQRT(x) (1.0 / std::sqrt(x))
 #define VB_PREFETCH(p) ((void)(p))
+#define VB_PREFETCH_L2(p) ((void)(p))
 
 // the same butterfly order as the shuffle versions, so sums round identically
 inline double vb_emu_max(const double *a) {

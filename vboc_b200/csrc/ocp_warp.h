@@ -69,6 +69,27 @@ struct Rec {
 };
 
 constexpr int RING_DEPTH = 4;
+
+// dot product of two contiguous, 16-byte aligned vectors of even length: 128-bit shared-memory loads
+// (LDS.128) and two accumulators
+template <int LEN>
+VB_HD double dotv(const double *a, const double *b, double init = 0.0) {
+    static_assert(LEN % 2 == 0, "even length");
+#if defined(__CUDA_ARCH__)
+    const double2 *a2 = reinterpret_cast<const double2 *>(a), *b2 = reinterpret_cast<const double2 *>(b);
+    double a0 = init, a1 = 0.0;
+#pragma unroll
+    for (int m = 0; m < LEN / 2; ++m) {
+        const double2 x = a2[m], y = b2[m];
+        a0 += x.x * y.x, a1 += x.y * y.y;
+    }
+    return a0 + a1;
+#else
+    double a0 = init, a1 = 0.0;
+    for (int m = 0; m < LEN; m += 2) a0 += a[m] * b[m], a1 += a[m + 1] * b[m + 1];
+    return a0 + a1;
+#endif
+}
 #ifndef VB_PF_DIST
 #define VB_PF_DIST 64  // software prefetch distance of the flat passes: two lane-strided iterations ahead
 #endif
@@ -136,8 +157,11 @@ struct alignas(16) Smem {
     double h, wtdt;
     int N, fixed0, fixedN, termfix, nact;
     // Riccati staging
-    double P[D::NX][D::NX], PBAT[D::NZ][D::NX], M[D::NZ][D::NZ];
-    double tb[D::NX], m[D::NZ], pvec[D::NX], dx[2][D::NX];
+    alignas(16) double P[D::NX][D::NX];
+    alignas(16) double PBAT[D::NZ][D::NX];
+    alignas(16) double tb[D::NX];
+    alignas(16) double pvec[D::NX];
+    double M[D::NZ][D::NZ], m[D::NZ], dx[2][D::NX];
     double e0[D::NX], eN[D::NX], hhN[D::NX], rN[D::NX], nuv[D::NX], Lz[D::NX][D::NX], dzi[D::NX], Pe[D::NX];
     double K[D::NU][D::NX], tz[D::NZ], va[D::NX], vb[D::NX], vc[D::NX], vt[D::NX];
     // merit weights / multipliers of the eliminated equalities
@@ -580,10 +604,10 @@ struct WarpSolver {
                 FOR_LANES
                 for (int idx = lane; idx < NZ * NX; idx += 32) {
                     int j = idx / NX, i = idx - j * NX;
-                    s.PBAT[j][i] = dot2<NX>(&s.P[i][0], 1, r + R::BAT + j * NX, 1);
+                    s.PBAT[j][i] = dotv<NX>(&s.P[i][0], r + R::BAT + j * NX);
                 }
                 if (lane < NX) {
-                    s.tb[lane] = dot2<NX>(&s.P[lane][0], 1, r + R::RB, 1);
+                    s.tb[lane] = dotv<NX>(&s.P[lane][0], r + R::RB);
                 }
                 END_LANES
             }
@@ -594,7 +618,7 @@ struct WarpSolver {
                     // row of the idx-th entry of the row-major lower triangle: floor((sqrt(8 idx + 1) - 1) / 2),
                     // exact in FP32 for idx < 2^20
                     int a_ = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f), b_ = idx - a_ * (a_ + 1) / 2;
-                    double a = dot2<NX>(r + R::BAT + a_ * NX, 1, &s.PBAT[b_][0], 1, (a_ == b_) ? r[R::HH + a_] : 0.0);
+                    double a = dotv<NX>(r + R::BAT + a_ * NX, &s.PBAT[b_][0], (a_ == b_) ? r[R::HH + a_] : 0.0);
                     s.M[a_][b_] = a, s.M[b_][a_] = a;
                 }
             } else if (last) {
@@ -603,12 +627,12 @@ struct WarpSolver {
             if (lane < NZ) {
                 double mb;
                 if (factor) {
-                    mb = dot2<NX>(r + R::BAT + lane * NX, 1, s.tb, 1);
+                    mb = dotv<NX>(r + R::BAT + lane * NX, s.tb);
                     gk[R::MB + lane] = mb;
                 } else {
                     mb = r[R::MB + lane];
                 }
-                s.m[lane] = dot2<NX>(r + R::BAT + lane * NX, 1, s.pvec, 1, rhs_of(r, lane, mode, sm) + mb);
+                s.m[lane] = dotv<NX>(r + R::BAT + lane * NX, s.pvec, rhs_of(r, lane, mode, sm) + mb);
             }
             END_LANES
             // D: eliminate the controls

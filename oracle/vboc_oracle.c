@@ -274,6 +274,11 @@ typedef struct {
     double c0[NXI];
     int fixedN[NXI], nfN, nqN, ivN[NXI], iqN[NXI];
     double cN[NXI];
+    /* terminal equalities the last control cannot absorb (e.g. theta_N and dtheta_N fixed with one control,
+     * VBOC/pendulum_class_vboc.py:123-124) are handled by BORDERING: the Riccati system is solved for the rhs
+     * and for one unit terminal gradient per fixed component; the terminal multipliers follow from a small
+     * dense system.  elimN = 1: eliminated through the last control; nb, bidx: bordered components. */
+    int elimN, nb, bidx[NXI];
 } iocp;
 
 static inline int stage_class(const iocp *P, int k) { return k == 0 ? 0 : (k == P->N ? 2 : 1); }
@@ -339,6 +344,7 @@ typedef struct {
     double *rg, *rb, *rd, *rm; /* residuals: (N+1)nz, N nx, (N+1)2nz, (N+1)2nz          */
     double *dv, *dpi, *dlam, *dt;
     double *rmb, *hheff, *rr, *lbd, *ubd;
+    double *dvb, *dpib, *zr, *zb; /* border basis solves: NXI x (N+1)nz, NXI x N nx; zero rhs vectors */
     double e0[NXI], eN[NXI];
     /* merit */
     double *wdyn, *wb; /* N nx, (N+1) 2nz */
@@ -359,6 +365,7 @@ static work *work_alloc(int N, int nx, int nu) {
     AL_(dv, S * nz), AL_(dpi, S * nx), AL_(dlam, S * 2 * nz), AL_(dt, S * 2 * nz);
     AL_(rmb, S * 2 * nz), AL_(hheff, S * nz), AL_(rr, S * nz), AL_(lbd, S * nz), AL_(ubd, S * nz);
     AL_(wdyn, S * nx), AL_(wb, S * 2 * nz), AL_(Xt, S * nx), AL_(Ut, S * nu);
+    AL_(dvb, NXI * S * nz), AL_(dpib, NXI * S * nx), AL_(zr, S * nz), AL_(zb, S * nx);
 #undef AL_
     return W;
 }
@@ -367,7 +374,7 @@ static void work_free(work *W) {
                      &W->hd,  &W->DZ,  &W->PIQ,  &W->LAMQ, &W->TQ, &W->L,     &W->pv,  &W->yv,
                      &W->rg,  &W->rb,  &W->rd,   &W->rm,  &W->dv,  &W->dpi,   &W->dlam, &W->dt,
                      &W->rmb, &W->hheff, &W->rr, &W->lbd, &W->ubd, &W->wdyn,  &W->wb,  &W->Xt,
-                     &W->Ut};
+                     &W->Ut,  &W->dvb, &W->dpib, &W->zr, &W->zb};
     for (size_t i = 0; i < sizeof(ps) / sizeof(ps[0]); ++i) free(*ps[i]);
     free(W);
 }
@@ -555,13 +562,13 @@ static int riccati_factor(const iocp *P, work *W, const double *hh) {
             double (*Mf)[NZI] = W->Mlast;
             for (int i = 0; i < nz; ++i)
                 for (int j = 0; j < nz; ++j) Mf[i][j] = (i == j) ? hh[k * nz + i] : 0.0;
-            for (int q = 0; q < P->nqN; ++q) {
-                int c = P->iqN[q];
+            for (int c = 0; c < nx; ++c) {
+                if (P->elimN && P->fixedN[c]) continue;
                 for (int i = 0; i < nz; ++i)
                     for (int j = 0; j < nz; ++j)
                         Mf[i][j] += W->hhN[c] * BAE(A, B, c, i) * BAE(A, B, c, j);
             }
-            if (P->nfN) {
+            if (P->elimN) {
                 double G[NUI][NUI];
                 for (int a = 0; a < nu; ++a)
                     for (int b = 0; b < nu; ++b) G[a][b] = B[P->ivN[a] * nu + b];
@@ -662,7 +669,7 @@ static void riccati_solve(const iocp *P, work *W, const double *r, const double 
         double t2[NXI], m[NZI];
         if (k == N - 1) {
             for (int i = 0; i < nx; ++i)
-                t2[i] = P->fixedN[i] ? 0.0 : W->hhN[i] * beta[k * nx + i] + pv[(k + 1) * nx + i];
+                t2[i] = (P->elimN && P->fixedN[i]) ? 0.0 : W->hhN[i] * beta[k * nx + i] + pv[(k + 1) * nx + i];
         } else {
             P_times(W, k + 1, beta + k * nx, t2);
             for (int i = 0; i < nx; ++i) t2[i] += pv[(k + 1) * nx + i];
@@ -672,7 +679,7 @@ static void riccati_solve(const iocp *P, work *W, const double *r, const double 
             for (int i = 0; i < nx; ++i) s += BAE(A, B, i, j) * t2[i];
             m[j] = s;
         }
-        if (k == N - 1 && P->nfN) {
+        if (k == N - 1 && P->elimN) {
             /* du = K dx + k0 with G k0 = -(eN + beta_v) */
             double tmp[NZI];
             for (int a = 0; a < nu; ++a) {
@@ -734,7 +741,7 @@ static void riccati_solve(const iocp *P, work *W, const double *r, const double 
     for (int k = 0; k < N; ++k) {
         const double *A = W->A + k * nx * nx, *B = W->B + k * nx * nu, *L = W->L + k * nz * nz;
         double *z = dv + k * nz, *zn = dv + (k + 1) * nz;
-        if (k == N - 1 && P->nfN) {
+        if (k == N - 1 && P->elimN) {
             for (int a = 0; a < nu; ++a) {
                 double s = W->k0[a];
                 for (int j = 0; j < nx; ++j) s += W->Kfb[a][j] * z[nu + j];
@@ -762,8 +769,8 @@ static void riccati_solve(const iocp *P, work *W, const double *r, const double 
         if (k == N - 1) {
             for (int i = 0; i < nu; ++i) zn[i] = 0.0;
             for (int i = 0; i < nx; ++i)
-                dpi[k * nx + i] = P->fixedN[i] ? 0.0 : W->hhN[i] * zn[nu + i] + pv[(k + 1) * nx + i];
-            if (P->nfN) {
+                dpi[k * nx + i] = (P->elimN && P->fixedN[i]) ? 0.0 : W->hhN[i] * zn[nu + i] + pv[(k + 1) * nx + i];
+            if (P->elimN) {
                 /* multiplier of the eliminated rows from the u-stationarity of the last stage */
                 double tu[NUI];
                 for (int a = 0; a < nu; ++a) {
@@ -877,6 +884,43 @@ static double ipm_step(const iocp *P, const orc_opts *o, work *W, int factor, co
         return 0.0;
     }
     riccati_solve(P, W, W->rr, W->rb, W->e0, W->eN, W->dv, W->dpi);
+    if (P->nb) {
+        int nx = P->nx, nu = P->nu, nb = P->nb, S = N + 1;
+        double ze[NXI] = {0};
+        if (factor) /* basis solves: unit terminal gradient on one fixed component, everything else zero */
+            for (int j = 0; j < nb; ++j) {
+                memset(W->zr, 0, sizeof(double) * S * nz);
+                W->zr[N * nz + nu + P->bidx[j]] = 1.0;
+                riccati_solve(P, W, W->zr, W->zb, ze, ze, W->dvb + (size_t)j * S * nz, W->dpib + (size_t)j * S * nx);
+            }
+        double Sm[NXI][NXI + 1], nuv[NXI];
+        for (int i = 0; i < nb; ++i) {
+            for (int j = 0; j < nb; ++j) Sm[i][j] = W->dvb[(size_t)j * S * nz + N * nz + nu + P->bidx[i]];
+            Sm[i][nb] = -(W->eN[P->bidx[i]] + W->dv[N * nz + nu + P->bidx[i]]);
+        }
+        for (int c = 0; c < nb; ++c) {
+            int pr = c;
+            for (int i = c + 1; i < nb; ++i)
+                if (fabs(Sm[i][c]) > fabs(Sm[pr][c])) pr = i;
+            for (int j = 0; j <= nb; ++j) {
+                double t = Sm[c][j];
+                Sm[c][j] = Sm[pr][j], Sm[pr][j] = t;
+            }
+            for (int i = c + 1; i < nb; ++i) {
+                double f = Sm[i][c] / Sm[c][c];
+                for (int j = c; j <= nb; ++j) Sm[i][j] -= f * Sm[c][j];
+            }
+        }
+        for (int i = nb - 1; i >= 0; --i) {
+            double a = Sm[i][nb];
+            for (int j = i + 1; j < nb; ++j) a -= Sm[i][j] * nuv[j];
+            nuv[i] = a / Sm[i][i];
+        }
+        for (int j = 0; j < nb; ++j) {
+            for (int c = 0; c < S * nz; ++c) W->dv[c] += nuv[j] * W->dvb[(size_t)j * S * nz + c];
+            for (int c = 0; c < N * nx; ++c) W->dpi[c] += nuv[j] * W->dpib[(size_t)j * S * nx + c];
+        }
+    }
     double alpha = 1.0;
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nz; ++i) {
@@ -1268,7 +1312,16 @@ static work *prepare(prep *pp, int n, int family, int N, const double *xg, const
         else
             P->iqN[P->nqN++] = i;
     }
-    if (P->nfN != 0 && P->nfN != nu) return NULL;
+    {
+        int velonly = P->nfN == nu;
+        for (int i = 0; i < nx; ++i)
+            if (P->fixedN[i] && !(i >= n && i < 2 * n)) velonly = 0;
+        P->elimN = P->nfN > 0 && velonly;
+        P->nb = 0;
+        if (!P->elimN)
+            for (int i = 0; i < nx; ++i)
+                if (P->fixedN[i]) P->bidx[P->nb++] = i;
+    }
     work *W = work_alloc(N, nx, nu);
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nx; ++i) W->X[k * nx + i] = xg[k * nxr + i];

@@ -42,3 +42,20 @@ def test_lane_program_matches_oracle(oracle, emu, n, fam, mode):
     ok = out["status"] == 0
     assert ok.any()
     assert np.abs(ref["x"] - out["x"])[ok].max() < 1e-6
+
+
+def test_free_dt_lane_program_matches_oracle(oracle, emu):
+    """1-DOF VBOC with the dt state kept (VBOC/pendulum_vboc.py): lane-per-OCP program with bordering of the
+    two terminal equalities against the oracle's square-root Riccati + bordering."""
+    bp = pr.pendulum_free_dt_problems(10, seed=3)
+    oo = oracle.default_opts(0)
+    ref = oracle.solve_batch(1, 0, 0, bp, oo)
+    out = emu.solve_batch(1, 0, 0, bp, _opts(emu, oo), "lane_dts")
+    assert (ref["status"] == out["status"]).all() and (out["status"] == 0).sum() >= 8
+    assert (ref["sqp_iter"] == out["sqp_iter"]).all()
+    ok = out["status"] == 0
+    assert np.abs(ref["x"] - out["x"])[ok].max() < 1e-6
+    # the optimal dt is interior (time costs) and constant along the horizon
+    x = out["x"][ok]
+    assert (x[:, 0, 2] > 1e-4).all() and (x[:, 0, 2] < 1e-2).all()
+    assert np.abs(np.diff(x[:, :, 2], axis=1)).max() < 1e-9

@@ -117,3 +117,21 @@ def test_unsupported_inputs_are_refused():
     with pytest.raises(VbocError):
         sol.solve(bad)
     sol.close()
+
+
+def test_pendulum_free_dt_matches_oracle(oracle):
+    """configs[0] (VBOC/pendulum_vboc.py): dt a free state; GPU lane kernel (dt state kept, bordered terminal
+    equalities) against the oracle."""
+    from vboc_b200 import engine
+    bp = pr.pendulum_free_dt_problems(64, seed=9)
+    oo = oracle.default_opts(0)
+    ref = oracle.solve_batch(1, 0, 0, bp, oo)
+    sol = engine.BatchSolver(1, "vboc", 64, 50)
+    sol.set_opts(_copy_opts(engine.Opts(), oo))
+    out = sol.solve(bp)
+    sol.close()
+    assert (ref["status"] == out["status"]).all()
+    ok = (out["status"] == 0) & (ref["sqp_iter"] == out["sqp_iter"])
+    assert ok.mean() > 0.8
+    assert np.abs(ref["x"] - out["x"])[ok].max() < TOL_X_LOOSE
+    assert np.abs(ref["cost"] - out["cost"])[ok].max() < TOL_X_LOOSE

@@ -123,6 +123,28 @@ def test_pendulum_testdata_like_the_script(oracle):
         assert status == ref["status"]
         if status == 0:
             assert np.abs(s.get(0, "x") - ref["x"][0]).max() < 1e-5
-    with pytest.raises(VbocError):
-        ocp.OCP_solve(np.tile([3.0, 0.0, 1e-2], (N + 1, 1)), np.zeros((N, 1)), 1.0,
-                      np.array([q_min, -v_max, 0.0]), np.array([q_max, v_max, 1e-2]), 3.0, 3.2)
+
+
+def test_pendulum_vboc_free_dt_like_the_driver():
+    """VBOC/pendulum_vboc.py:54-140: the two extreme trajectories with dt a free state in [0, 1e-2] and a
+    unit weight on time; checked against the NLP itself (constraints, bang-bang structure) and against the
+    semi-analytic boundary: from (q_max, v) with full braking torque the pendulum must stop exactly at q_min."""
+    ocp = _load("VBOC", "pendulum_class_vboc").OCPpendulum()
+    N = ocp.N
+    q_min, q_max, v_max = ocp.thetamin, ocp.thetamax, ocp.dthetamax
+    for v_sel in (-v_max, v_max):
+        if v_sel < 0:
+            q_init, q_fin, lb, ub, cd = q_max, q_min, np.array([q_min, -v_max, 0.]), np.array([q_max, 0., 1e-2]), 1.
+        else:
+            q_init, q_fin, lb, ub, cd = q_min, q_max, np.array([q_min, 0., 0.]), np.array([q_max, v_max, 1e-2]), -1.
+        xg = np.empty((N + 1, 3))
+        xg[:, 0], xg[:, 1], xg[:, 2] = np.linspace(q_init, q_fin, N + 1), v_sel, 1e-2
+        status = ocp.OCP_solve(xg, np.zeros((N, 1)), cd, lb, ub, q_init, q_fin)
+        assert status == 0
+        x = np.array([ocp.ocp_solver.get(i, "x") for i in range(N + 1)])
+        u = np.array([ocp.ocp_solver.get(i, "u") for i in range(N)])
+        assert abs(x[0, 0] - q_init) < 1e-8 and abs(x[N, 0] - q_fin) < 1e-6 and abs(x[N, 1]) < 1e-6
+        assert np.abs(u).max() <= 3.0 + 1e-9 and (x[:, 2] >= -1e-12).all() and (x[:, 2] <= 1e-2 + 1e-12).all()
+        assert np.abs(np.diff(x[:, 2])).max() < 1e-9          # dt is constant along the horizon (dt' = 0)
+        assert abs(abs(x[0, 1]) - v_max) < 1e-6               # the velocity limit is reachable from the far limit
+        assert abs(ocp.ocp_solver.get_cost() - (cd * x[0, 1] + x[:N, 2].sum())) < 1e-9

@@ -47,7 +47,7 @@ static void run(int mode, int batch, int Nmax, const int *N, const double *xg, c
 }
 
 // the lane-per-OCP solver with W = 1 (one "lane" at a time)
-template <int NQ, int FAM>
+template <int NQ, int FAM, int DTS = 0>
 static void run_lane(int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug,
                      const double *p, const double *lbx0, const double *ubx0, const double *lbx,
                      const double *ubx, const double *lbxN, const double *ubxN, const double *lbu,
@@ -56,7 +56,7 @@ static void run_lane(int mode, int batch, int Nmax, const int *N, const double *
     const int nxr = 2 * NQ + (FAM == VBOC_FAMILY_VBOC), nu = NQ;
 #pragma omp parallel
     {
-        std::vector<double> buf(LaneLayout<NQ>::TOTAL);
+        std::vector<double> buf(LaneLayout<NQ, DTS>::TOTAL);
 #pragma omp for schedule(dynamic, 1)
         for (int b = 0; b < batch; ++b) {
             Prob pb;
@@ -71,7 +71,7 @@ static void run_lane(int mode, int batch, int Nmax, const int *N, const double *
             pb.dir = dir ? dir + (size_t)b * NQ : nullptr;
             pb.x = x + (size_t)b * (Nmax + 1) * nxr, pb.u = u + (size_t)b * Nmax * nu;
             pb.st = st + b;
-            LaneSolver<NQ, FAM, 1> sol(buf.data(), 0, *o);
+            LaneSolver<NQ, FAM, 1, DTS> sol(buf.data(), 0, *o);
             LaneState ls;
             sol.begin(ls, pb);
             while (!sol.sqp_iteration(ls, mode)) {
@@ -97,6 +97,20 @@ extern "C" int emu_lane_solve_batch(int n, int family, int mode, int batch, int 
     GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
 #undef GO
     return -1;
+}
+
+// 1-DOF VBOC with the dt state kept (free dt)
+extern "C" int emu_lane_dts_solve_batch(int n, int family, int mode, int batch, int Nmax, const int *N,
+                                        const double *xg, const double *ug, const double *p,
+                                        const double *lbx0, const double *ubx0, const double *lbx,
+                                        const double *ubx, const double *lbxN, const double *ubxN,
+                                        const double *lbu, const double *ubu, const double *dir,
+                                        const double *h, const vboc_opts *o, double *x, double *u,
+                                        vboc_stats *st) {
+    if (n != 1 || family != 0) return -1;
+    run_lane<1, 0, 1>(mode, batch, Nmax, N, xg, ug, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu, ubu, dir, h, o, x, u,
+                      st);
+    return 0;
 }
 
 extern "C" int emu_solve_batch(int n, int family, int mode, int batch, int Nmax, const int *N,

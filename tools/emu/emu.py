@@ -55,7 +55,7 @@ def solve_batch(n, family, mode, bp, opts, kernel="warp"):
         d = None
     x, u = np.zeros_like(xg), np.zeros_like(ug)
     st = (Stats * B)()
-    fn = lib.emu_solve_batch if kernel == "warp" else lib.emu_lane_solve_batch
+    fn = {"warp": lib.emu_solve_batch, "lane": lib.emu_lane_solve_batch, "lane_dts": lib.emu_lane_dts_solve_batch}[kernel]
     fn(n, family, mode, B, Nmax, Nv.ctypes.data_as(C.POINTER(C.c_int)), _p(xg), _p(ug),
                         *[_p(a) for a in keep], _p(d), _p(h), C.byref(opts), _p(x), _p(u), st)
     f = lambda name: np.array([getattr(s_, name) for s_ in st])

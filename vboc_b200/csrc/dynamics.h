@@ -289,4 +289,68 @@ VB_HD void rk4_sens(const double *x, const double *u, double h, double *xn, doub
     }
 }
 
+// The VBOC models with a FREE dt state (VBOC/pendulum_class_vboc.py:35-39): x = [q; v; dt],
+// xdot = dt [v; a(q, v, u); 0], integrated over a unit step.  xn and Phi = d xn / d [u; x]
+// ([2 NQ + 1][3 NQ + 1], column order (u, q, v, dt)).
+template <int NQ>
+VB_HD void rk4_sens_dts(const double *x, const double *u, double *xn, double (*Phi)[3 * NQ + 1]) {
+    constexpr int NX = 2 * NQ + 1, NZ = 3 * NQ + 1;
+    const double h = 1.0;
+    double xt[NX], acc[NX], St[NX][NZ];
+    for (int i = 0; i < NX; ++i) {
+        xt[i] = x[i], acc[i] = 0.0;
+        for (int j = 0; j < NZ; ++j) St[i][j] = (j == NQ + i) ? 1.0 : 0.0, Phi[i][j] = 0.0;
+    }
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        double a[NQ], Ja[NQ][3 * NQ], Kx[NX], Ks[NX][NZ];
+        accel_jac<NQ>(xt, xt + NQ, u, a, Ja);
+        const double dt = xt[2 * NQ];
+        for (int i = 0; i < NQ; ++i) {
+            Kx[i] = dt * xt[NQ + i], Kx[NQ + i] = dt * a[i];
+            for (int j = 0; j < NZ; ++j) {
+                // d(dt v_i)/dz = dt dv_i/dz + v_i ddt/dz ; d(dt a_i)/dz = dt da_i/dz + a_i ddt/dz
+                double dv = St[NQ + i][j], da = (j < NQ) ? Ja[i][2 * NQ + j] : 0.0;
+                for (int m = 0; m < 2 * NQ; ++m) da += Ja[i][m] * St[m][j];
+                const double ddt = St[2 * NQ][j];
+                Ks[i][j] = dt * dv + xt[NQ + i] * ddt;
+                Ks[NQ + i][j] = dt * da + a[i] * ddt;
+            }
+        }
+        Kx[2 * NQ] = 0.0;
+        for (int j = 0; j < NZ; ++j) Ks[2 * NQ][j] = 0.0;
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0, adv = st == 2 ? h : 0.5 * h;
+        for (int i = 0; i < NX; ++i) {
+            acc[i] += wgt * Kx[i];
+            xt[i] = x[i] + adv * Kx[i];
+            for (int j = 0; j < NZ; ++j) {
+                Phi[i][j] += wgt * Ks[i][j];
+                St[i][j] = ((j == NQ + i) ? 1.0 : 0.0) + adv * Ks[i][j];
+            }
+        }
+    }
+    for (int i = 0; i < NX; ++i) {
+        xn[i] = x[i] + (h / 6.0) * acc[i];
+        for (int j = 0; j < NZ; ++j) Phi[i][j] = ((j == NQ + i) ? 1.0 : 0.0) + (h / 6.0) * Phi[i][j];
+    }
+}
+
+// value only (merit function)
+template <int NQ>
+VB_HD void rk4_step_dts(const double *x, const double *u, double *xn) {
+    constexpr int NX = 2 * NQ + 1;
+    double xt[NX], acc[NX], k[NX];
+    for (int i = 0; i < NX; ++i) xt[i] = x[i], acc[i] = 0.0;
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        double a[NQ];
+        accel<NQ, double>(xt, xt + NQ, u, a);
+        for (int i = 0; i < NQ; ++i) k[i] = xt[2 * NQ] * xt[NQ + i], k[NQ + i] = xt[2 * NQ] * a[i];
+        k[2 * NQ] = 0.0;
+        const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0, adv = st == 2 ? 1.0 : 0.5;
+        for (int i = 0; i < NX; ++i) acc[i] += wgt * k[i], xt[i] = x[i] + adv * k[i];
+    }
+    for (int i = 0; i < NX; ++i) xn[i] = x[i] + acc[i] / 6.0;
+}
+
 }  // namespace vboc

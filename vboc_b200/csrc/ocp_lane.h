@@ -20,17 +20,23 @@
 
 namespace vboc {
 
-template <int NQ>
+// DTS = 1: the dt state of the VBOC models is kept (free dt, VBOC/pendulum_class_vboc.py); nx = 2n + 1 and the
+// dynamics are the dt-scaled ones over a unit step.  Terminal equalities that the last control cannot absorb
+// (there: theta_N and dtheta_N fixed with one control) are handled by BORDERING: the Riccati system is solved
+// for the rhs and for one unit terminal gradient per fixed component, and the terminal multipliers follow
+// from a small dense system.
+template <int NQ, int DTS = 0>
 struct LaneLayout {
-    using D = Dim<NQ>;
-    static constexpr int NX = D::NX, NU = D::NU, NZ = D::NZ, NC = D::NC;
+    static constexpr int NX = 2 * NQ + DTS, NU = NQ, NZ = NX + NU, NC = 2 * NZ;
+    static constexpr int NB = DTS ? NX : 0;  // room for the border basis solves
     // per stage (element offsets)
     static constexpr size_t Z = 0, PI = Z + NZ, LAM = PI + NX, BD = LAM + NC;
     static constexpr size_t BA = BD + NX, RB = BA + NX * NZ, HH = RB + NX, RR = HH + NZ, Q1 = RR + NZ, Q2 = Q1 + NZ;
     static constexpr size_t MB = Q2 + NZ, LUU = MB + NZ, LXU = LUU + NU * NU, YV = LXU + NX * NU, P = YV + NU;
     static constexpr size_t PV = P + NX * NX, DZ = PV + NX, PIQ = DZ + NZ, LAMQ = PIQ + NX, TQ = LAMQ + NC;
     static constexpr size_t DV = TQ + NC, DPI = DV + NZ, PROD = DPI + NX, DLAM = PROD + NC, DT = DLAM + NC;
-    static constexpr size_t WDYN = DT + NC, WB = WDYN + NX, ZT = WB + NC, SREC = ZT + NZ;
+    static constexpr size_t WDYN = DT + NC, WB = WDYN + NX, ZT = WB + NC, DVB = ZT + NZ, DPIB = DVB + NB * NZ;
+    static constexpr size_t SREC = DPIB + NB * NX;
     static constexpr size_t SMAX = 129;
     // per OCP
     static constexpr size_t O0 = SMAX * SREC;
@@ -47,9 +53,9 @@ struct LaneState {
     vboc_stats st;
 };
 
-template <int NQ, int FAM, int W>
+template <int NQ, int FAM, int W, int DTS = 0>
 struct LaneSolver {
-    using L = LaneLayout<NQ>;
+    using L = LaneLayout<NQ, DTS>;
     static constexpr int NX = L::NX, NU = L::NU, NZ = L::NZ, NC = L::NC;
 
     double *base;
@@ -57,7 +63,8 @@ struct LaneSolver {
     const vboc_opts &o;
     // per-OCP scalars
     int N, fixed0, fixedN, termfix, nact;
-    double h, wtdt, wcost[NQ];
+    int nb, bidx[NX];  // border mode: number and indices of the fixed terminal components
+    double h, wtdt, wt, wcost[NQ];
 
     VB_HD LaneSolver(double *base_, int lane_, const vboc_opts &o_) : base(base_), lane(lane_), o(o_), N(0) {}
 
@@ -76,7 +83,11 @@ struct LaneSolver {
     VB_HD double lb(int k, int i) const { return g(L::LB + sclass(k) * NZ + i); }
     VB_HD double ub(int k, int i) const { return g(L::UB + sclass(k) * NZ + i); }
     VB_HD double cost_g(int k, int i, double zval) const {
-        if (FAM == VBOC_FAMILY_VBOC) return (k == 0 && i >= NU + NQ) ? wcost[i - NU - NQ] : 0.0;
+        if (FAM == VBOC_FAMILY_VBOC) {
+            if (k == 0 && i >= NU + NQ && i < NU + 2 * NQ) return wcost[i - NU - NQ];
+            if (DTS && i == NU + 2 * NQ && k < N) return wt;  // wt * dt at stages 0..N-1
+            return 0.0;
+        }
         return (i >= NU + NQ) ? 2.0 * (k < N ? h : 1.0) * zval : 0.0;
     }
     VB_HD double cost_h(int k, int i) const {
@@ -116,7 +127,8 @@ struct LaneSolver {
     // ---------------------------------------------------------------- problem load / store
     VB_HD void load_problem(const Prob &pb) {
         N = pb.N, h = pb.h;
-        wtdt = (FAM == VBOC_FAMILY_VBOC) ? pb.wt * pb.h * N : 0.0;
+        wt = pb.wt;
+        wtdt = (FAM == VBOC_FAMILY_VBOC && !DTS) ? pb.wt * pb.h * N : 0.0;
         int f0 = 0, fN = 0, nf0 = 0, nfN = 0;
         for (int i = 0; i < NX; ++i) {
             bool a = pb.lbx0[i] == pb.ubx0[i], b = pb.lbxN[i] == pb.ubxN[i];
@@ -129,14 +141,20 @@ struct LaneSolver {
         int ny = 0;
         for (int i = 0; i < NX; ++i) {
             if ((f0 >> i) & 1) continue;
-            if (pb.dir && i >= NQ) continue;
+            if (pb.dir && i >= NQ && i < 2 * NQ) continue;
             g(L::Z0 + i * NX + ny++) = 1.0;
         }
         if (pb.dir) {
             for (int i = 0; i < NQ; ++i) g(L::Z0 + (NQ + i) * NX + ny) = pb.dir[i];
             ++ny;
         }
-        fixed0 = f0, fixedN = fN, termfix = nfN != 0;
+        fixed0 = f0, fixedN = fN;
+        // the last control absorbs the terminal equalities iff they are exactly the n velocities
+        termfix = fN == (((1 << NQ) - 1) << NQ);
+        nb = 0;
+        if (!termfix)
+            for (int i = 0; i < NX; ++i)
+                if ((fN >> i) & 1) bidx[nb++] = i;
         nact = (N + 1) * NZ - NU - nf0 - nfN;
         for (int i = 0; i < NQ; ++i) wcost[i] = (FAM == VBOC_FAMILY_VBOC) ? pb.p[i] : 0.0;
         for (int sc = 0; sc < 3; ++sc) {
@@ -171,7 +189,10 @@ struct LaneSolver {
             double x[NX], u[NU], xn[NX], Phi[NX][NZ];
             for (int i = 0; i < NU; ++i) u[i] = s(k, L::Z + i);
             for (int i = 0; i < NX; ++i) x[i] = s(k, L::Z + NU + i);
-            rk4_sens<NQ>(x, u, h, xn, Phi);
+            if constexpr (DTS)
+                rk4_sens_dts<NQ>(x, u, xn, Phi);
+            else
+                rk4_sens<NQ>(x, u, h, xn, Phi);
             for (int i = 0; i < NX; ++i) {
                 for (int j = 0; j < NZ; ++j) s(k, L::BA + i * NZ + j) = Phi[i][j];
                 s(k, L::BD + i) = xn[i] - s(k + 1, L::Z + NU + i);
@@ -325,17 +346,21 @@ struct LaneSolver {
     }
 
     VB_HD double rhs_of(int k, int i, int mode, double sm) const {
+        if (mode == 3) return 0.0;
         if (mode == 0) return s(k, L::RR + i);
         return (mode == 1 ? s(k, L::Q1 + i) : s(k, L::RR + i)) - sm * s(k, L::Q2 + i);
     }
 
     // ---------------------------------------------------------------- Riccati: backward sweep
-    VB_HD bool backward(int mode, double sm, double *dx0) {
+    // mode 0 factorise + predictor rhs, 1 corrector, 2 centering only, 3 border basis solve for the
+    // fixed terminal component bidx[bj] (unit terminal gradient, all other right-hand sides zero)
+    VB_HD bool backward(int mode, double sm, double *dx0, int bj = 0) {
         const bool factor = mode == 0;
         double P[NX][NX], pv[NX];
         for (int i = 0; i < NX; ++i) {
-            bool fx = (fixedN >> i) & 1;
+            bool fx = termfix && ((fixedN >> i) & 1);
             double hh = s(N, L::HH + NU + i), rr = rhs_of(N, NU + i, mode, sm);
+            if (mode == 3) rr = (i == bidx[bj]) ? 1.0 : 0.0;
             g(L::HHN + i) = fx ? 0.0 : hh;
             g(L::RN + i) = fx ? 0.0 : rr;
             pv[i] = fx ? 0.0 : rr;
@@ -373,7 +398,7 @@ struct LaneSolver {
                     m[a_] = mb;
                 }
             } else {
-                for (int a_ = 0; a_ < NZ; ++a_) m[a_] = s(k, L::MB + a_);
+                for (int a_ = 0; a_ < NZ; ++a_) m[a_] = mode == 3 ? 0.0 : s(k, L::MB + a_);
                 if (last)
                     for (int a_ = 0; a_ < NZ; ++a_)
                         for (int b_ = 0; b_ < NZ; ++b_) M[a_][b_] = g(L::MF + a_ * NZ + b_);
@@ -527,9 +552,10 @@ struct LaneSolver {
         }
         {
             double y[NX], dy[NX];
+            const double e0s = mode == 3 ? 0.0 : 1.0;  // the basis solves are homogeneous
             for (int i = 0; i < NX; ++i) {
                 double a = 0.0;
-                for (int mm = 0; mm < NX; ++mm) a -= g(L::Z0 + mm * NX + i) * (pv[mm] - g(L::PE + mm));
+                for (int mm = 0; mm < NX; ++mm) a -= g(L::Z0 + mm * NX + i) * (pv[mm] - e0s * g(L::PE + mm));
                 for (int j = 0; j < i; ++j) a -= g(L::LZ + i * NX + j) * y[j];
                 y[i] = a * g(L::DZI + i);
             }
@@ -539,7 +565,7 @@ struct LaneSolver {
                 dy[i] = a * g(L::DZI + i);
             }
             for (int i = 0; i < NX; ++i) {
-                double a = -g(L::E0 + i);
+                double a = -e0s * g(L::E0 + i);
                 for (int c = 0; c < NX; ++c) a += g(L::Z0 + i * NX + c) * dy[c];
                 dx0[i] = a;
             }
@@ -574,38 +600,10 @@ struct LaneSolver {
     // DV, DPI, the slack / multiplier steps, the maximum step to the boundary and the sums of
     // mu(alpha) = (S0 + alpha S1 + alpha^2 S2) / nc.  mode 0 stores the second-order products and the
     // corrector gradient pieces Q1, Q2; modes 1/2 store DT, DLAM.
-    VB_HD double forward(int mode, double sm, const double *dx0, double &S0, double &S1, double &S2) {
-        double dx[NX], al = 1.0, s0 = 0, s1 = 0, s2 = 0;
-        for (int i = 0; i < NX; ++i) dx[i] = dx0[i];
-#pragma unroll 1
-        for (int k = 0; k <= N; ++k) {
-            const bool last = (k == N - 1) && termfix;
-            double dz[NZ];
-            for (int i = 0; i < NX; ++i) dz[NU + i] = dx[i];
-            for (int c = 0; c < NU; ++c) dz[c] = 0.0;
-            if (k < N) {
-                if (!last) {
-                    double t[NU];
-                    for (int c = 0; c < NU; ++c) {
-                        double a = s(k, L::YV + c);
-                        for (int j = 0; j < NX; ++j) a += s(k, L::LXU + j * NU + c) * dx[j];
-                        t[c] = a;
-                    }
-                    for (int c = NU - 1; c >= 0; --c) {
-                        double a = -t[c];
-                        for (int c2 = c + 1; c2 < NU; ++c2) a -= s(k, L::LUU + c2 * NU + c) * dz[c2];
-                        dz[c] = a * s(k, L::LUU + c * NU + c);
-                    }
-                } else {
-                    for (int a_ = 0; a_ < NU; ++a_) {
-                        double a = g(L::K0 + a_);
-                        for (int j = 0; j < NX; ++j) a += s(k, L::LXU + j * NU + a_) * dx[j];
-                        dz[a_] = a;
-                    }
-                }
-            }
-            for (int i = 0; i < NZ; ++i) s(k, L::DV + i) = dz[i];
-            // constraints of stage k
+    // slack / multiplier steps of the bound constraints of stage k for the primal step dz: ratio test and
+    // the sums of mu(alpha); mode 0 stores the second-order products and Q1, Q2, modes 1/2 store DT, DLAM
+    VB_HD void con_stage(int k, const double *dz, int mode, double sm, double &al, double &s0, double &s1,
+                         double &s2) {
             for (int i = 0; i < NZ; ++i) {
                 double q1 = 0.0, q2 = 0.0;
                 if (active(k, i)) {
@@ -635,10 +633,96 @@ struct LaneSolver {
                 }
                 if (mode == 0) s(k, L::Q1 + i) = s(k, L::RR + i) + q1, s(k, L::Q2 + i) = q2;
             }
+    }
+    VB_HD double con_pass(int mode, double sm, double &S0, double &S1, double &S2) {
+        double al = 1.0, s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll 1
+        for (int k = 0; k <= N; ++k) {
+            double dz[NZ];
+            for (int i = 0; i < NZ; ++i) dz[i] = s(k, L::DV + i);
+            con_stage(k, dz, mode, sm, al, s0, s1, s2);
+        }
+        S0 = s0, S1 = s1, S2 = s2;
+        return al;
+    }
+
+    // border mode: terminal multipliers from the basis solves, then DV, DPI of the full step
+    VB_HD bool border_combine() {
+        double Sm[NX][NX + 1], nuv[NX];
+        for (int i = 0; i < nb; ++i) {
+            for (int j = 0; j < nb; ++j) Sm[i][j] = s(N, L::DVB + (size_t)j * NZ + NU + bidx[i]);
+            Sm[i][nb] = -(g(L::EN + bidx[i]) + s(N, L::DV + NU + bidx[i]));
+        }
+        for (int c = 0; c < nb; ++c) {  // Gaussian elimination with partial pivoting
+            int p = c;
+            for (int i = c + 1; i < nb; ++i)
+                if (fabs(Sm[i][c]) > fabs(Sm[p][c])) p = i;
+            if (Sm[p][c] == 0.0 || Sm[p][c] != Sm[p][c]) return false;
+            for (int j = 0; j <= nb; ++j) {
+                double t = Sm[c][j];
+                Sm[c][j] = Sm[p][j], Sm[p][j] = t;
+            }
+            for (int i = c + 1; i < nb; ++i) {
+                double f = Sm[i][c] / Sm[c][c];
+                for (int j = c; j <= nb; ++j) Sm[i][j] -= f * Sm[c][j];
+            }
+        }
+        for (int i = nb - 1; i >= 0; --i) {
+            double a = Sm[i][nb];
+            for (int j = i + 1; j < nb; ++j) a -= Sm[i][j] * nuv[j];
+            nuv[i] = a / Sm[i][i];
+        }
+#pragma unroll 1
+        for (int k = 0; k <= N; ++k)
+            for (int j = 0; j < nb; ++j) {
+                for (int i = 0; i < NZ; ++i) s(k, L::DV + i) += nuv[j] * s(k, L::DVB + (size_t)j * NZ + i);
+                if (k < N)
+                    for (int i = 0; i < NX; ++i) s(k, L::DPI + i) += nuv[j] * s(k, L::DPIB + (size_t)j * NX + i);
+            }
+        return true;
+    }
+
+    // raw: only the recurrence (DV, DPI, or the basis arrays DVB / DPIB when mode == 3); the constraint
+    // steps are then done by con_pass after the border combination.
+    VB_HD double forward(int mode, double sm, const double *dx0, double &S0, double &S1, double &S2, bool raw = false,
+                         int bj = 0) {
+        const size_t fDV = mode == 3 ? L::DVB + (size_t)bj * NZ : L::DV;
+        const size_t fDPI = mode == 3 ? L::DPIB + (size_t)bj * NX : L::DPI;
+        double dx[NX], al = 1.0, s0 = 0, s1 = 0, s2 = 0;
+        for (int i = 0; i < NX; ++i) dx[i] = dx0[i];
+#pragma unroll 1
+        for (int k = 0; k <= N; ++k) {
+            const bool last = (k == N - 1) && termfix;
+            double dz[NZ];
+            for (int i = 0; i < NX; ++i) dz[NU + i] = dx[i];
+            for (int c = 0; c < NU; ++c) dz[c] = 0.0;
+            if (k < N) {
+                if (!last) {
+                    double t[NU];
+                    for (int c = 0; c < NU; ++c) {
+                        double a = s(k, L::YV + c);
+                        for (int j = 0; j < NX; ++j) a += s(k, L::LXU + j * NU + c) * dx[j];
+                        t[c] = a;
+                    }
+                    for (int c = NU - 1; c >= 0; --c) {
+                        double a = -t[c];
+                        for (int c2 = c + 1; c2 < NU; ++c2) a -= s(k, L::LUU + c2 * NU + c) * dz[c2];
+                        dz[c] = a * s(k, L::LUU + c * NU + c);
+                    }
+                } else {
+                    for (int a_ = 0; a_ < NU; ++a_) {
+                        double a = g(L::K0 + a_);
+                        for (int j = 0; j < NX; ++j) a += s(k, L::LXU + j * NU + a_) * dx[j];
+                        dz[a_] = a;
+                    }
+                }
+            }
+            for (int i = 0; i < NZ; ++i) s(k, fDV + i) = dz[i];
+            if (!raw) con_stage(k, dz, mode, sm, al, s0, s1, s2);
             if (k < N) {
                 double dxn[NX];
                 for (int i = 0; i < NX; ++i) {
-                    double a = s(k, L::RB + i);
+                    double a = mode == 3 ? 0.0 : s(k, L::RB + i);
                     for (int j = 0; j < NZ; ++j) a += s(k, L::BA + i * NZ + j) * dz[j];
                     dxn[i] = a;
                 }
@@ -647,7 +731,7 @@ struct LaneSolver {
                     for (int i = 0; i < NX; ++i) {
                         double a = s(k + 1, L::PV + i);
                         for (int j = 0; j < NX; ++j) a += s(k + 1, L::P + i * NX + j) * dxn[j];
-                        s(k, L::DPI + i) = a;
+                        s(k, fDPI + i) = a;
                     }
                 } else {
                     double nuv[NU];
@@ -667,7 +751,7 @@ struct LaneSolver {
                     for (int i = 0; i < NX; ++i) {
                         double a = g(L::HHN + i) * dxn[i] + g(L::RN + i);
                         if (last && i >= NQ) a = nuv[i - NQ];
-                        s(k, L::DPI + i) = a;
+                        s(k, fDPI + i) = a;
                     }
                 }
                 for (int i = 0; i < NX; ++i) dx[i] = dxn[i];
@@ -696,7 +780,20 @@ struct LaneSolver {
                 double S0, S1, S2, dx0[NX];
                 ok = backward(ph, sm, dx0) && ok;
                 if (!ok) break;
-                alpha = forward(ph, sm, dx0, S0, S1, S2);
+                if (nb == 0) {
+                    alpha = forward(ph, sm, dx0, S0, S1, S2);
+                } else {
+                    forward(ph, sm, dx0, S0, S1, S2, true);
+                    if (ph == 0)
+                        for (int j = 0; j < nb; ++j) {
+                            double dxb[NX], d0, d1, d2;
+                            backward(3, 0.0, dxb, j);
+                            forward(3, 0.0, dxb, d0, d1, d2, true, j);
+                        }
+                    ok = border_combine() && ok;
+                    if (!ok) break;
+                    alpha = con_pass(ph, sm, S0, S1, S2);
+                }
                 double m_a = (S0 + alpha * S1 + alpha * alpha * S2) / nc;
                 if (ph == 0) {
                     m_aff = m_a;
@@ -752,6 +849,8 @@ struct LaneSolver {
         if (FAM == VBOC_FAMILY_VBOC) {
             double c = wtdt;
             for (int i = 0; i < NQ; ++i) c += wcost[i] * s(0, zf + NU + NQ + i);
+            if (DTS)
+                for (int k = 0; k < N; ++k) c += wt * s(k, zf + NU + 2 * NQ);
             return c;
         }
         double a = 0.0;
@@ -770,7 +869,10 @@ struct LaneSolver {
                 double x[NX], u[NU], xn[NX];
                 for (int i = 0; i < NU; ++i) u[i] = s(k, zf + i);
                 for (int i = 0; i < NX; ++i) x[i] = s(k, zf + NU + i);
-                rk4_step<NQ, double>(x, u, h, xn);
+                if constexpr (DTS)
+                    rk4_step_dts<NQ>(x, u, xn);
+                else
+                    rk4_step<NQ, double>(x, u, h, xn);
                 for (int i = 0; i < NX; ++i) m += s(k, L::WDYN + i) * fabs(xn[i] - s(k + 1, zf + NU + i));
             }
             for (int i = 0; i < NZ; ++i)

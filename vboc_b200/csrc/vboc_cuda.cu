@@ -87,12 +87,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) solve_kernel(const B
 // lockstep, one SQP iteration per trip of the loop; a lane whose problem finished pulls the next index
 // at the top of the loop, so the warp stays full until the queue is empty.
 constexpr int LANE_THREADS = 128;
-template <int NQ, int FAM>
+template <int NQ, int FAM, int DTS>
 __global__ void __launch_bounds__(LANE_THREADS, 2) solve_lane_kernel(const Batch B) {
     const int lane = threadIdx.x & 31;
     const size_t wslot = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    double *base = B.work + wslot * LaneLayout<NQ>::TOTAL * 32;
-    LaneSolver<NQ, FAM, 32> sol(base, lane, B.opts);
+    double *base = B.work + wslot * LaneLayout<NQ, DTS>::TOTAL * 32;
+    LaneSolver<NQ, FAM, 32, DTS> sol(base, lane, B.opts);
     LaneState ls;
     ls.have = 0, ls.it = 0;
     Prob pb;
@@ -157,6 +157,8 @@ __global__ void dfma_peak_kernel(double *out, int iters) {
 struct vboc_solver {
     int n, family, cap, Nmax, device, nxr, nu;
     int slots, grid, ctas_per_sm, lane_kernel;
+    int free_dt, grid_free_dt;  // 1-DOF VBOC with a free dt state: lane kernel with the dt state kept
+    double *dwork_free_dt;
     cudaStream_t stream;
     vboc_opts opts;
     // device buffers
@@ -178,7 +180,7 @@ struct vboc_solver {
 template <int NQ, int FAM>
 static cudaError_t launch(vboc_solver *s, const Batch &B) {
     if (s->lane_kernel) {
-        solve_lane_kernel<NQ, FAM><<<s->grid, LANE_THREADS, 0, s->stream>>>(B);
+        solve_lane_kernel<NQ, FAM, 0><<<s->grid, LANE_THREADS, 0, s->stream>>>(B);
         return cudaGetLastError();
     }
     if (s->ctas_per_sm >= 6)
@@ -297,6 +299,7 @@ void vboc_destroy(vboc_solver *s) {
                     s->dx,    s->du,    s->dst,  s->dcounter, s->dwork};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (s->dwork_free_dt) cudaFree(s->dwork_free_dt);
     if (s->stage) cudaFreeHost(s->stage);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -355,6 +358,7 @@ int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
     // ---- validation and host-side preparation (what the shim's OCP_solve would otherwise do
     // stage by stage through ocp_solver.set / constraints_set)
     std::vector<double> h(batch), dir;
+    bool free_dt = false;
     if (C0) dir.resize((size_t)batch * n);
     for (int b = 0; b < batch; ++b) {
         if (N[b] < 1 || N[b] > Nmax) return fail(VBOC_ERR_ARG, "vboc_upload: horizon out of range");
@@ -368,10 +372,19 @@ int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
                           uN[2 * n] == dt;
             const double *xg = x_guess + (size_t)b * (Nmax + 1) * nxr;
             for (int k = 0; k <= N[b] && pinned; ++k) pinned = xg[(size_t)k * nxr + 2 * n] == dt;
-            if (!pinned || !(dt > 0.0))
-                return fail(VBOC_ERR_UNSUPPORTED,
-                            "vboc_upload: the dt state must be pinned to one positive value at every "
-                            "stage and in the guess (free-dt problems are not supported)");
+            if (!pinned) {
+                // free dt (VBOC/pendulum_vboc.py:69-70): 1-DOF only, whole batch
+                if (n != 1 || (b > 0 && !free_dt))
+                    return fail(VBOC_ERR_UNSUPPORTED,
+                                "vboc_upload: the dt state must be pinned to one positive value at every "
+                                "stage and in the guess (a free dt is supported for the 1-DOF model only, "
+                                "and not mixed with pinned problems in one batch)");
+                free_dt = true;
+                h[b] = 1.0;
+                continue;
+            }
+            if (free_dt || !(dt > 0.0))
+                return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: pinned and free dt mixed in one batch, or dt <= 0");
             h[b] = dt;
         } else {
             h[b] = Tf / N[b];
@@ -434,6 +447,15 @@ int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
     if (C0) UP(ddir, dir.data(), B * n);
 #undef UP
     s->batch = batch, s->has_dir = C0 != nullptr, s->has_p = p != nullptr;
+    s->free_dt = free_dt;
+    if (free_dt && !s->dwork_free_dt) {
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, s->device));
+        int max_g = prop.multiProcessorCount * 2, need_g = (s->cap + LANE_THREADS - 1) / LANE_THREADS;
+        s->grid_free_dt = need_g < max_g ? need_g : max_g;
+        size_t doubles = (size_t)s->grid_free_dt * (LANE_THREADS / 32) * 32 * LaneLayout<1, 1>::TOTAL;
+        CUDA_OK(cudaMalloc((void **)&s->dwork_free_dt, doubles * sizeof(double)));
+    }
     return 0;
 }
 
@@ -454,10 +476,16 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
     CUDA_OK(cudaMemsetAsync(s->dcounter, 0, sizeof(unsigned int), s->stream));
     CUDA_OK(cudaEventRecord(s->ev0, s->stream));
     cudaError_t e = cudaErrorInvalidValue;
+    if (s->free_dt) {
+        B.work = s->dwork_free_dt;
+        solve_lane_kernel<1, VBOC_FAMILY_VBOC, 1><<<s->grid_free_dt, LANE_THREADS, 0, s->stream>>>(B);
+        e = cudaGetLastError();
+    } else {
 #define GO(NQ, FAM) \
     if (s->n == NQ && s->family == FAM) e = launch<NQ, FAM>(s, B);
-    GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
+        GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
 #undef GO
+    }
     if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("solve_kernel launch: ") + cudaGetErrorString(e));
     CUDA_OK(cudaEventRecord(s->ev1, s->stream));
     s->last_ms = -1.0;

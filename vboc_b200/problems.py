@@ -266,3 +266,40 @@ def from_ocp_solve_args(n, N, x_sol_guess, u_sol_guess, p, q_lb, q_ub, u_lb, u_u
     return dict(n=n, family="vboc", N=np.array([N], dtype=np.int32), x_guess=one(xg), u_guess=one(ug), p=one(p),
                 lbx0=one(q_init_lb), ubx0=one(q_init_ub), lbx=one(q_lb), ubx=one(q_ub), lbxN=one(q_fin_lb),
                 ubxN=one(q_fin_ub), lbu=one(u_lb), ubu=one(u_ub), C0=stage0_projector(p[None, :n], 2 * n + 1))
+
+
+def pendulum_free_dt_problems(batch, seed, N=50):
+    """1-DOF VBOC OCPs with the dt state FREE in [0, 1e-2] and a unit weight on time, in the shape
+    `OCP_solve` of VBOC/pendulum_class_vboc.py:107-130 builds them: theta_0 = q_init fixed, theta_N = q_fin and
+    dtheta_N = 0 fixed, the velocity sign restricted by the path bounds (VBOC/pendulum_vboc.py:63-87).
+    Problem 0 / 1 are the driver's two extreme trajectories (q_max -> q_min and q_min -> q_max); the others
+    start and end at seeded random positions in between (the sub-OCPs of the trajectory walk, :171-181)."""
+    mdl = Model(1)
+    q_min, q_max, v_max, dt = mdl.thetamin, mdl.thetamax, mdl.dthetamax, 1e-2
+    rng = _rng(seed)
+    R = rng.random((batch, 3))
+    xg = np.zeros((batch, N + 1, 3))
+    p = np.zeros((batch, 2))
+    lbx = np.zeros((batch, 3)); ubx = np.zeros((batch, 3))
+    lbx0 = np.zeros((batch, 3)); ubx0 = np.zeros((batch, 3))
+    lbxN = np.zeros((batch, 3)); ubxN = np.zeros((batch, 3))
+    for b in range(batch):
+        down = (b % 2 == 0)  # v_sel = v_min: move from the upper to the lower position limit
+        if b < 2:
+            q_init, q_fin = (q_max, q_min) if down else (q_min, q_max)
+        else:
+            a, c = sorted(q_min + R[b, :2] * (q_max - q_min))
+            c = max(c, a + 0.05)
+            q_init, q_fin = (c, a) if down else (a, c)
+        v_sel = -v_max if down else v_max
+        lbx[b] = [q_min, -v_max if down else 0.0, 0.0]
+        ubx[b] = [q_max, 0.0 if down else v_max, dt]
+        p[b] = [1.0 if down else -1.0, 1.0]
+        xg[b, :, 0] = np.linspace(q_init, q_fin, N + 1)
+        xg[b, :, 1] = v_sel
+        xg[b, :, 2] = dt
+        lbx0[b] = [q_init, -v_max, 0.0]; ubx0[b] = [q_init, v_max, dt]
+        lbxN[b] = [q_fin, 0.0, 0.0]; ubxN[b] = [q_fin, 0.0, dt]
+    return dict(n=1, family="vboc", N=np.full(batch, N, dtype=np.int32), x_guess=xg, u_guess=np.zeros((batch, N, 1)),
+                p=p, lbx0=lbx0, ubx0=ubx0, lbx=lbx, ubx=ubx, lbxN=lbxN, ubxN=ubxN,
+                lbu=np.full((batch, 1), -mdl.umax), ubu=np.full((batch, 1), mdl.umax), C0=None)

@@ -1,9 +1,9 @@
 """Mirror of the reference's `VBOC/pendulum_class_vboc.py:8-130` (1-DOF).
 
-Supported: the pinned-`dt` use of `pendulum_testdata.py:7-53` (`lbx = ubx = dt_sym` on the third state at
-every stage, `p = [+-1, 0]`).  NOT supported yet: `OCP_solve` as `VBOC/pendulum_vboc.py` calls it, where `dt`
-is a free state in [0, 1e-2] with cost weight 1 -- the engine refuses it with VBOC_ERR_UNSUPPORTED at
-`solve()` instead of silently solving something else."""
+Both uses work: the pinned-`dt` one of `pendulum_testdata.py:7-53` (`lbx = ubx = dt_sym` on the third state at
+every stage, `p = [+-1, 0]`; the dt state is eliminated) and `OCP_solve` as `VBOC/pendulum_vboc.py:91` calls it,
+where `dt` is a free state in [0, 1e-2] with cost weight 1 (lane-per-OCP kernel with the dt state kept and
+the two terminal equalities handled by bordering, vboc_b200/csrc/ocp_lane.h)."""
 import os
 import sys
 
@@ -47,4 +47,4 @@ class OCPpendulum:
         s.constraints_set(self.N, "ubx", np.array([q_fin, 0., 1e-2]))
         s.set(self.N, "x", np.array(x_sol_guess[self.N]))
         s.set(self.N, 'p', np.array([cost_dir, 1.]))
-        return s.solve()  # raises VbocError(VBOC_ERR_UNSUPPORTED): free dt
+        return s.solve()

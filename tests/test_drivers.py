@@ -56,3 +56,31 @@ def test_workers_are_deterministic(backend):
     a = drivers.testing_batch(2, 3, seed=5, backend=backend(2))
     b = drivers.testing_batch(2, 3, seed=5, backend=backend(2))
     assert np.array_equal(a, b)
+
+
+def test_pendulum_data_generation(backend):
+    """configs[0]: the 1-DOF VBOC driver end to end on the oracle backend.  Known answer (K6): every saved
+    state lies on the boundary of the viability kernel, i.e. full braking torque from it stops exactly at the
+    position limit: checked by integrating the bang-bang arc with the golden-pinned RK4 map."""
+    st = {}
+    X = drivers.pendulum_data_generation(backend=backend(1), stats=st)
+    mdl = pr.Model(1)
+    assert X.shape[1] == 2 and X.shape[0] > 40 and st["solves"] >= 2
+    assert (X[:, 0] >= mdl.thetamin - 1e-9).all() and (X[:, 0] <= mdl.thetamax + 1e-9).all()
+    assert (np.abs(X[:, 1]) <= mdl.dthetamax + 1e-6).all()
+    ob, _ = backend(1)
+    checked = 0
+    for q, v in X[::7]:
+        if abs(abs(v) - mdl.dthetamax) < 1e-3 or abs(v) < 0.5:
+            continue  # on the velocity limit (boundary of X, not of V) or nearly at rest
+        x = np.array([q, v])
+        u = np.array([mdl.umax if v < 0 else -mdl.umax])  # brake
+        for _ in range(4000):
+            xn = ob.oracle.rk4(1, 1, x, u, 1e-3)
+            if xn[1] * v <= 0:
+                break
+            x = xn
+        lim = mdl.thetamin if v < 0 else mdl.thetamax
+        assert abs(x[0] - lim) < 5e-3, (q, v, x)
+        checked += 1
+    assert checked >= 3

@@ -68,3 +68,10 @@ def test_al_query_selects_most_uncertain():
     assert len(idx) == 50 and idx == sorted(idx, reverse=True)
     assert etp[idx].min() >= np.sort(etp)[-50] - 1e-7
     net.close()
+
+
+def test_pendulum_data_generation_matches_oracle_run(oracle):
+    ob = OracleBackend(oracle, 1)
+    ref = drivers.pendulum_data_generation(backend=(ob, ob.sim))
+    out = drivers.pendulum_data_generation()
+    assert ref.shape == out.shape and np.abs(ref - out).max() < 1e-5

@@ -73,7 +73,7 @@ def _pack(n, reqs):
     for key, attr in (("lbx0", "q_init_lb"), ("ubx0", "q_init_ub"), ("lbx", "q_lb"), ("ubx", "q_ub"),
                       ("lbxN", "q_fin_lb"), ("ubxN", "q_fin_ub"), ("lbu", "u_lb"), ("ubu", "u_ub")):
         bp[key] = np.stack([getattr(r, attr) for r in reqs])
-    bp["C0"] = pr.stage0_projector(bp["p"][:, :n], nx)
+    bp["C0"] = pr.stage0_projector(bp["p"][:, :n], nx) if n > 1 else None
     return bp
 
 
@@ -312,6 +312,71 @@ def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
     return rows
 
 
+def pendulum_worker(v_sel, N0=50, eps=1e-3):
+    """1-DOF VBOC data generation for one side (VBOC/pendulum_vboc.py:54-223): the extreme trajectory with
+    a free dt state (horizon + 1 while the initial velocity norm still grows by > 1e-4), then the
+    simplified walk: while the state sits on a velocity limit either keep it or re-solve from it.
+    Mirrors the driver, except that the status of the sub-OCP solve is the one of that solve (the reference
+    tests the stale status of the first solve, :181-183).  Returns rows [q, v]; raises like the driver when
+    a solve fails."""
+    mdl = pr.Model(1)
+    q_min, q_max, v_max, dt = mdl.thetamin, mdl.thetamax, mdl.dthetamax, 1e-2
+    if v_sel < 0:
+        q_init, q_fin, lb, ub, cost_dir = q_max, q_min, np.array([q_min, -v_max, 0.]), np.array([q_max, 0., dt]), 1.
+    else:
+        q_init, q_fin, lb, ub, cost_dir = q_min, q_max, np.array([q_min, 0., 0.]), np.array([q_max, v_max, dt]), -1.
+    u_lb, u_ub = np.array([-mdl.umax]), np.array([mdl.umax])
+
+    def req(N, xg, ug, q0):
+        return SolveReq(N, xg, ug, np.array([cost_dir, 1.]), lb, ub, u_lb, u_ub, np.array([q0, -v_max, 0.]),
+                        np.array([q0, v_max, dt]), np.array([q_fin, 0., 0.]), np.array([q_fin, 0., dt]))
+
+    N = N0
+    xg = np.stack([np.linspace(q_init, q_fin, N + 1), np.full(N + 1, v_sel), np.full(N + 1, dt)], axis=1)
+    ug = np.zeros((N, 1))
+    norm_old = v_max
+    while True:
+        ans = yield req(N, xg, ug, q_init)
+        if ans.status != 0:
+            raise RuntimeError("Sorry, the solver failed")
+        norm_new = abs(ans.x[0, 1])
+        if norm_new > norm_old + 1e-4 and N + 1 <= N_CAP:
+            norm_old = norm_new
+            xg, ug = ans.x.copy(), np.vstack([ans.u, np.zeros((1, 1))])
+            N += 1
+        else:
+            break
+    x_sol, u_sol = ans.x.copy(), ans.u.copy()
+    rows = [x_sol[0, :2].copy()]
+    v_out = x_sol[0, 1] - eps * cost_dir
+    at_limit = v_out > v_max or v_out < -v_max
+    for f in range(1, N):
+        if at_limit:
+            v_out = x_sol[f, 1] - eps * cost_dir
+            if v_out > v_max or v_out < -v_max:
+                rows.append(x_sol[f, :2].copy())
+            else:
+                norm_old = abs(x_sol[f, 1])
+                N_t = N - f
+                sub = yield req(N_t, x_sol[:N_t + 1], u_sol[:N_t], x_sol[f, 0])  # unshifted guess, as the driver
+                if sub.status != 0:
+                    raise RuntimeError("Sorry, the solver failed")
+                norm_new = abs(sub.x[0, 1])
+                if norm_new > norm_old + 1e-4:
+                    x_sol[f:N] = sub.x[:N - f]
+                    u_sol[f:N] = sub.u[:N - f]
+                    v_out = sub.x[0, 1] - eps * cost_dir
+                    at_limit = v_out > v_max or v_out < -v_max
+                else:
+                    at_limit = False
+                rows.append(x_sol[f, :2].copy())
+        else:
+            if abs(x_sol[f, 0] - q_fin) <= 1e-3:
+                break
+            rows.append(x_sol[f, :2].copy())
+    return rows
+
+
 # ------------------------------------------------------------------------------------------------
 def _gpu_backend(n, capacity, device):
     from . import engine
@@ -402,3 +467,11 @@ def save_vboc_data(n, X_save, directory="."):
     path = os.path.join(directory, f"data_{n}dof_vboc.npy")
     np.save(path, np.asarray(X_save, dtype=float))
     return path
+
+
+def pendulum_data_generation(device=0, backend=None, stats=None):
+    """The 1-DOF driver's data generation (VBOC/pendulum_vboc.py:54-223): both sides -> X_save (rows [q, v])."""
+    mdl = pr.Model(1)
+    solver, sim = backend or _gpu_backend(1, 2, device)
+    res = run_workers(1, [pendulum_worker(-mdl.dthetamax), pendulum_worker(mdl.dthetamax)], solver, sim, stats)
+    return np.concatenate([np.asarray(r) for r in res]).reshape(-1, 2)

@@ -71,7 +71,8 @@ static void run_lane(int mode, int batch, int Nmax, const int *N, const double *
             pb.dir = dir ? dir + (size_t)b * NQ : nullptr;
             pb.x = x + (size_t)b * (Nmax + 1) * nxr, pb.u = u + (size_t)b * Nmax * nu;
             pb.st = st + b;
-            LaneSolver<NQ, FAM, 1, DTS> sol(buf.data(), 0, *o);
+            double scratch[LaneSolver<NQ, FAM, 1, DTS>::SM_TOTAL];
+            LaneSolver<NQ, FAM, 1, DTS> sol(buf.data(), scratch, 0, *o);
             LaneState ls;
             sol.begin(ls, pb);
             while (!sol.sqp_iteration(ls, mode)) {

@@ -18,6 +18,10 @@
 #include "dynamics.h"
 #include "ocp_warp.h"  // Prob, Dim
 
+#ifndef VB_LANE_PREFETCH
+#define VB_LANE_PREFETCH 0
+#endif
+
 namespace vboc {
 
 // DTS = 1: the dt state of the VBOC models is kept (free dt, VBOC/pendulum_class_vboc.py); nx = 2n + 1 and the
@@ -58,7 +62,9 @@ struct LaneSolver {
     using L = LaneLayout<NQ, DTS>;
     static constexpr int NX = L::NX, NU = L::NU, NZ = L::NZ, NC = L::NC;
 
+    static constexpr int SMS = W == 1 ? 1 : 128;  // stride of the per-thread shared-memory scratch (= CTA size)
     double *base;
+    double *sm;  // per-thread scratch: element idx at sm[idx * SMS]
     int lane;
     const vboc_opts &o;
     // per-OCP scalars
@@ -66,10 +72,18 @@ struct LaneSolver {
     int nb, bidx[NX];  // border mode: number and indices of the fixed terminal components
     double h, wtdt, wt, wcost[NQ];
 
-    VB_HD LaneSolver(double *base_, int lane_, const vboc_opts &o_) : base(base_), lane(lane_), o(o_), N(0) {}
+    VB_HD LaneSolver(double *base_, double *sm_, int lane_, const vboc_opts &o_)
+        : base(base_), sm(sm_), lane(lane_), o(o_), N(0) {}
 
     VB_HD double &g(size_t off) const { return base[off * W + lane]; }
     VB_HD double &s(int k, size_t f) const { return base[((size_t)k * L::SREC + f) * W + lane]; }
+
+    // The 32 lanes' copies of one field element share one 256-byte line: lane l prefetches line l of the
+    // range into L2, so a stage costs each lane a handful of prefetch instructions.
+    VB_HD void prefetch_l2(int k, size_t f0, size_t f1) const {
+        if (W == 1 || !VB_LANE_PREFETCH || k < 0 || k > N) return;
+        for (size_t f = f0 + lane; f < f1; f += 32) VB_PREFETCH_L2(base + ((size_t)k * L::SREC + f) * W);
+    }
 
     VB_HD int sclass(int k) const { return k == 0 ? 0 : (k == N ? 2 : 1); }
     VB_HD bool active(int k, int i) const {
@@ -291,47 +305,88 @@ struct LaneSolver {
         bool bad = false;
 #pragma unroll 1
         for (int k = 0; k <= N; ++k) {
-            double r[NZ], bar[NZ];
-            for (int i = 0; i < NZ; ++i) {
-                double v = s(k, L::DZ + i), z = s(k, L::Z + i);
-                double hd = cost_h(k, i), hh = hd + o.qp_reg_prim, b = 0.0;
-                double a = hd * v + cost_g(k, i, z);
-                if (k < N)
-                    for (int m = 0; m < NX; ++m) a += s(k, L::BA + m * NZ + i) * s(k, L::PIQ + m);
-                if (k > 0 && i >= NU) a -= s(k - 1, L::PIQ + i - NU);
-                if (active(k, i)) {
-                    double ll = s(k, L::LAMQ + i), lu = s(k, L::LAMQ + NZ + i);
-                    double tl = s(k, L::TQ + i), tu = s(k, L::TQ + NZ + i);
-                    a += lu - ll;
-                    double dl = (lb(k, i) - z) - v + tl, du = v - (ub(k, i) - z) + tu;
-                    double ml = ll * tl, mu_ = lu * tu;
-                    bad |= (dl != dl) | (du != du) | (ml != ml) | (mu_ != mu_);
-                    vd = fmax(vd, fmax(fabs(dl), fabs(du)));
-                    vm = fmax(vm, fmax(fabs(ml), fabs(mu_)));
-                    mu += ml + mu_;
-                    double itl = 1.0 / tl, itu = 1.0 / tu;
-                    hh += ll * itl + lu * itu;
-                    b = (ml - ll * dl) * itl - (mu_ - lu * du) * itu;
-                } else if (k == N) {
-                    a = 0.0;
+            prefetch_l2(k + 2, L::Z, L::Z + NZ);
+            prefetch_l2(k + 2, L::BD, L::BA + NX * NZ);
+            prefetch_l2(k + 3, L::DZ, L::DV);
+            const double *sk = &s(k, 0);
+            double *skw = &s(k, 0);
+            const int sc = sclass(k);
+            double r[NZ], v[NZ], z[NZ];
+            // block A: loads of [B A], the multipliers and the iterate, then r = H v + g + [B A]'pi - pi_{k-1}
+            // and the dynamics residual
+            {
+                double c[NX][NZ], pi[NX], pim[NX], dzn[NX], bd[NX];
+#pragma unroll
+                for (int i = 0; i < NZ; ++i) v[i] = sk[(L::DZ + i) * W], z[i] = sk[(L::Z + i) * W];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) {
+                    pi[i] = k < N ? sk[(L::PIQ + i) * W] : 0.0;
+                    pim[i] = k > 0 ? s(k - 1, L::PIQ + i) : 0.0;
+                    dzn[i] = k < N ? s(k + 1, L::DZ + NU + i) : 0.0;
+                    bd[i] = k < N ? sk[(L::BD + i) * W] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < NZ; ++j) c[i][j] = k < N ? sk[(L::BA + i * NZ + j) * W] : 0.0;
                 }
-                r[i] = a, bar[i] = b;
-                s(k, L::HH + i) = hh;
+#pragma unroll
+                for (int i = 0; i < NZ; ++i) {
+                    double a = cost_h(k, i) * v[i] + cost_g(k, i, z[i]);
+#pragma unroll
+                    for (int m = 0; m < NX; ++m) a += c[m][i] * pi[m];
+                    if (i >= NU) a -= pim[i - NU];
+                    r[i] = a;
+                }
+                if (k < N) {
+                    double rb[NX];
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
+                        double a = bd[i] - dzn[i];
+#pragma unroll
+                        for (int j = 0; j < NZ; ++j) a += c[i][j] * v[j];
+                        rb[i] = a;
+                        bad |= (a != a);
+                        vb = fmax(vb, fabs(a));
+                    }
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) skw[(L::RB + i) * W] = rb[i];
+                }
+            }
+            // block B: the bound constraints
+            double hh[NZ], bar[NZ];
+            {
+                double ll[NZ], lu[NZ], tl[NZ], tu[NZ], bl[NZ], bu[NZ];
+#pragma unroll
+                for (int i = 0; i < NZ; ++i) {
+                    ll[i] = sk[(L::LAMQ + i) * W], lu[i] = sk[(L::LAMQ + NZ + i) * W];
+                    tl[i] = sk[(L::TQ + i) * W], tu[i] = sk[(L::TQ + NZ + i) * W];
+                    bl[i] = g(L::LB + sc * NZ + i), bu[i] = g(L::UB + sc * NZ + i);
+                }
+#pragma unroll
+                for (int i = 0; i < NZ; ++i) {
+                    hh[i] = cost_h(k, i) + o.qp_reg_prim, bar[i] = 0.0;
+                    if (active(k, i)) {
+                        r[i] += lu[i] - ll[i];
+                        double dl = (bl[i] - z[i]) - v[i] + tl[i], du = v[i] - (bu[i] - z[i]) + tu[i];
+                        double ml = ll[i] * tl[i], mu_ = lu[i] * tu[i];
+                        bad |= (dl != dl) | (du != du) | (ml != ml) | (mu_ != mu_);
+                        vd = fmax(vd, fmax(fabs(dl), fabs(du)));
+                        vm = fmax(vm, fmax(fabs(ml), fabs(mu_)));
+                        mu += ml + mu_;
+                        double itl = 1.0 / tl[i], itu = 1.0 / tu[i];
+                        hh[i] += ll[i] * itl + lu[i] * itu;
+                        bar[i] = (ml - ll[i] * dl) * itl - (mu_ - lu[i] * du) * itu;
+                    } else if (k == N) {
+                        r[i] = 0.0;
+                    }
+                }
             }
             if (k == 0) proj0(r + NU);
+#pragma unroll
             for (int i = 0; i < NZ; ++i) {
                 bad |= (r[i] != r[i]);
                 vg = fmax(vg, fabs(r[i]));
-                s(k, L::RR + i) = r[i] + bar[i];
+                skw[(L::HH + i) * W] = hh[i];
+                skw[(L::RR + i) * W] = r[i] + bar[i];
             }
-            if (k < N)
-                for (int i = 0; i < NX; ++i) {
-                    double a = s(k, L::BD + i) - s(k + 1, L::DZ + NU + i);
-                    for (int j = 0; j < NZ; ++j) a += s(k, L::BA + i * NZ + j) * s(k, L::DZ + j);
-                    s(k, L::RB + i) = a;
-                    bad |= (a != a);
-                    vb = fmax(vb, fabs(a));
-                }
         }
         double x0[NX], e[NX];
         for (int i = 0; i < NX; ++i) x0[i] = s(0, L::Z + NU + i) + s(0, L::DZ + NU + i);
@@ -353,110 +408,176 @@ struct LaneSolver {
 
     // ---------------------------------------------------------------- Riccati: backward sweep
     // mode 0 factorise + predictor rhs, 1 corrector, 2 centering only, 3 border basis solve for the
-    // fixed terminal component bidx[bj] (unit terminal gradient, all other right-hand sides zero)
-    VB_HD bool backward(int mode, double sm, double *dx0, int bj = 0) {
+    // fixed terminal component bidx[bj] (unit terminal gradient, all other right-hand sides zero).
+    //
+    // Register plan of the factor step (n = 3: 54 + 21 + 6 + 6 + 6 doubles live at the peak): the stage's
+    // [B A] block and the symmetric P+ stay in registers, T_j = P+ c_j is formed one column at a time, the
+    // entries M[a][j] = c_a . T_j go straight to the per-thread shared-memory scratch `sm` (45 + 9 doubles),
+    // from which the nu x nu Cholesky and the Schur complement read them back.  No per-thread arrays in
+    // local memory on this path.
+    VB_HD static constexpr int TRI(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+    static constexpr int SM_M = 0, SM_V = NZ * (NZ + 1) / 2, SM_B = SM_V + NZ, SM_TOTAL = SM_B + NZ;
+    VB_HD double &scr(int idx) const { return sm[idx * SMS]; }
+
+    VB_HD bool backward(int mode, double sm_, double *dx0, int bj = 0) {
         const bool factor = mode == 0;
-        double P[NX][NX], pv[NX];
+        double P[NX * (NX + 1) / 2], pv[NX];
+#pragma unroll
         for (int i = 0; i < NX; ++i) {
             bool fx = termfix && ((fixedN >> i) & 1);
-            double hh = s(N, L::HH + NU + i), rr = rhs_of(N, NU + i, mode, sm);
+            double hh = s(N, L::HH + NU + i), rr = rhs_of(N, NU + i, mode, sm_);
             if (mode == 3) rr = (i == bidx[bj]) ? 1.0 : 0.0;
             g(L::HHN + i) = fx ? 0.0 : hh;
             g(L::RN + i) = fx ? 0.0 : rr;
             pv[i] = fx ? 0.0 : rr;
-            for (int j = 0; j < NX; ++j) P[i][j] = (j == i && !fx) ? hh : 0.0;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) P[TRI(i, j)] = (j == i && !fx) ? hh : 0.0;
         }
         bool ok = true;
 #pragma unroll 1
         for (int k = N - 1; k >= 0; --k) {
             const bool last = (k == N - 1) && termfix;
-            double BA[NX][NZ], m[NZ];
+            prefetch_l2(k - 2, L::BA, factor ? L::Q1 : L::P);
+            const double *sk = &s(k, 0);  // stage base: every field is sk[field * W]
+            double *skw = &s(k, 0);
+            double c[NX][NZ];
+#pragma unroll
             for (int i = 0; i < NX; ++i)
-                for (int j = 0; j < NZ; ++j) BA[i][j] = s(k, L::BA + i * NZ + j);
-            double M[NZ][NZ];
+#pragma unroll
+                for (int j = 0; j < NZ; ++j) c[i][j] = sk[(L::BA + i * NZ + j) * W];
+            // right-hand sides of the stage, loaded before any store of this iteration
+            double rhsv[NZ];
+#pragma unroll
+            for (int j = 0; j < NZ; ++j) rhsv[j] = rhs_of(k, j, mode, sm_);
             if (factor) {
-                double T[NX][NZ], tb[NX];  // P+ [B A], P+ beta
+                double tb[NX], hhv[NZ], rb[NX];
+#pragma unroll
+                for (int j = 0; j < NZ; ++j) hhv[j] = sk[(L::HH + j) * W];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) rb[i] = sk[(L::RB + i) * W];
+#pragma unroll
                 for (int i = 0; i < NX; ++i) {
                     double a = 0.0;
-                    for (int mm = 0; mm < NX; ++mm) a += P[i][mm] * s(k, L::RB + mm);
+#pragma unroll
+                    for (int mm = 0; mm < NX; ++mm) a += P[TRI(i, mm)] * rb[mm];
                     tb[i] = a;
-                    for (int j = 0; j < NZ; ++j) {
+                }
+#pragma unroll
+                for (int j = 0; j < NZ; ++j) {
+                    double T[NX];
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
                         double t = 0.0;
-                        for (int mm = 0; mm < NX; ++mm) t += P[i][mm] * BA[mm][j];
-                        T[i][j] = t;
+#pragma unroll
+                        for (int mm = 0; mm < NX; ++mm) t += P[TRI(i, mm)] * c[mm][j];
+                        T[i] = t;
                     }
-                }
-                for (int a_ = 0; a_ < NZ; ++a_) {
-                    for (int b_ = 0; b_ <= a_; ++b_) {
-                        double t = (a_ == b_) ? s(k, L::HH + a_) : 0.0;
-                        for (int mm = 0; mm < NX; ++mm) t += BA[mm][a_] * T[mm][b_];
-                        M[a_][b_] = t, M[b_][a_] = t;
+#pragma unroll
+                    for (int a_ = 0; a_ <= j; ++a_) {
+                        double t = (a_ == j) ? hhv[j] : 0.0;
+#pragma unroll
+                        for (int mm = 0; mm < NX; ++mm) t += c[mm][a_] * T[mm];
+                        scr(SM_M + TRI(j, a_)) = t;
                     }
-                    double mb = 0.0;
-                    for (int i = 0; i < NX; ++i) mb += BA[i][a_] * tb[i];
-                    s(k, L::MB + a_) = mb;
-                    m[a_] = mb;
+                    double mb = 0.0, mp = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) mb += c[i][j] * tb[i], mp += c[i][j] * pv[i];
+                    scr(SM_B + j) = mb;
+                    scr(SM_V + j) = mb + mp + rhsv[j];
                 }
+#pragma unroll
+                for (int j = 0; j < NZ; ++j) skw[(L::MB + j) * W] = scr(SM_B + j);
             } else {
-                for (int a_ = 0; a_ < NZ; ++a_) m[a_] = mode == 3 ? 0.0 : s(k, L::MB + a_);
+                double mbv[NZ];
+#pragma unroll
+                for (int j = 0; j < NZ; ++j) mbv[j] = mode == 3 ? 0.0 : sk[(L::MB + j) * W];
+#pragma unroll
+                for (int j = 0; j < NZ; ++j) {
+                    double t = mbv[j] + rhsv[j];
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) t += c[i][j] * pv[i];
+                    scr(SM_V + j) = t;
+                }
                 if (last)
+#pragma unroll
                     for (int a_ = 0; a_ < NZ; ++a_)
-                        for (int b_ = 0; b_ < NZ; ++b_) M[a_][b_] = g(L::MF + a_ * NZ + b_);
-            }
-            for (int a_ = 0; a_ < NZ; ++a_) {
-                double t = m[a_] + rhs_of(k, a_, mode, sm);
-                for (int i = 0; i < NX; ++i) t += BA[i][a_] * pv[i];
-                m[a_] = t;
+#pragma unroll
+                        for (int b_ = 0; b_ <= a_; ++b_) scr(SM_M + TRI(a_, b_)) = g(L::MF + a_ * NZ + b_);
             }
             if (!last) {
-                double Lu[NU][NU], di[NU], y[NU], Lxu[NX][NU];
+                double Lu[NU][NU], di[NU], y[NU];
                 if (factor) {
+#pragma unroll
                     for (int j = 0; j < NU; ++j) {
-                        double d = M[j][j];
-                        for (int c = 0; c < j; ++c) d -= Lu[j][c] * Lu[j][c];
+                        double d = scr(SM_M + TRI(j, j));
+#pragma unroll
+                        for (int cc = 0; cc < j; ++cc) d -= Lu[j][cc] * Lu[j][cc];
                         di[j] = d > 0.0 ? VB_RSQRT(d) : 0.0;
+#pragma unroll
                         for (int i = j + 1; i < NU; ++i) {
-                            double a = M[i][j];
-                            for (int c = 0; c < j; ++c) a -= Lu[i][c] * Lu[j][c];
+                            double a = scr(SM_M + TRI(i, j));
+#pragma unroll
+                            for (int cc = 0; cc < j; ++cc) a -= Lu[i][cc] * Lu[j][cc];
                             Lu[i][j] = a * di[j];
                         }
                     }
-                    for (int i = 0; i < NX; ++i)
-                        for (int c = 0; c < NU; ++c) {
-                            double a = M[NU + i][c];
-                            for (int c2 = 0; c2 < c; ++c2) a -= Lxu[i][c2] * Lu[c][c2];
-                            Lxu[i][c] = a * di[c];
-                            s(k, L::LXU + i * NU + c) = Lxu[i][c];
-                        }
+#pragma unroll
                     for (int i = 0; i < NU; ++i)
-                        for (int c = 0; c <= i; ++c) s(k, L::LUU + i * NU + c) = (c == i) ? di[i] : Lu[i][c];
-                    for (int i = 0; i < NX; ++i)
-                        for (int j = 0; j <= i; ++j) {
-                            double a = M[NU + i][NU + j];
-                            for (int c = 0; c < NU; ++c) a -= Lxu[i][c] * Lxu[j][c];
-                            P[i][j] = a, P[j][i] = a;
-                        }
-                    for (int i = 0; i < NX; ++i)
-                        for (int j = 0; j < NX; ++j) s(k, L::P + i * NX + j) = P[i][j];
+#pragma unroll
+                        for (int cc = 0; cc <= i; ++cc) skw[(L::LUU + i * NU + cc) * W] = (cc == i) ? di[i] : Lu[i][cc];
                 } else {
+#pragma unroll
                     for (int i = 0; i < NU; ++i) {
-                        di[i] = s(k, L::LUU + i * NU + i);
-                        for (int c = 0; c < i; ++c) Lu[i][c] = s(k, L::LUU + i * NU + c);
+                        di[i] = sk[(L::LUU + i * NU + i) * W];
+#pragma unroll
+                        for (int cc = 0; cc < i; ++cc) Lu[i][cc] = sk[(L::LUU + i * NU + cc) * W];
                     }
-                    for (int i = 0; i < NX; ++i)
-                        for (int c = 0; c < NU; ++c) Lxu[i][c] = s(k, L::LXU + i * NU + c);
                 }
-                for (int c = 0; c < NU; ++c) {
-                    double a = m[c];
-                    for (int c2 = 0; c2 < c; ++c2) a -= Lu[c][c2] * y[c2];
-                    y[c] = a * di[c];
-                    s(k, L::YV + c) = y[c];
+#pragma unroll
+                for (int cc = 0; cc < NU; ++cc) {
+                    double a = scr(SM_V + cc);
+#pragma unroll
+                    for (int c2 = 0; c2 < cc; ++c2) a -= Lu[cc][c2] * y[c2];
+                    y[cc] = a * di[cc];
+                    skw[(L::YV + cc) * W] = y[cc];
                 }
+                double Lxu[NX][NU];
+#pragma unroll
                 for (int i = 0; i < NX; ++i) {
-                    double p = m[NU + i];
-                    for (int c = 0; c < NU; ++c) p -= Lxu[i][c] * y[c];
-                    pv[i] = p;
-                    s(k, L::PV + i) = p;
+#pragma unroll
+                    for (int cc = 0; cc < NU; ++cc) {
+                        double a;
+                        if (factor) {
+                            a = scr(SM_M + TRI(NU + i, cc));
+#pragma unroll
+                            for (int c2 = 0; c2 < cc; ++c2) a -= Lxu[i][c2] * Lu[cc][c2];
+                            a *= di[cc];
+                            skw[(L::LXU + i * NU + cc) * W] = a;
+                        } else {
+                            a = sk[(L::LXU + i * NU + cc) * W];
+                        }
+                        Lxu[i][cc] = a;
+                    }
+                    double pn = scr(SM_V + NU + i);
+#pragma unroll
+                    for (int cc = 0; cc < NU; ++cc) pn -= Lxu[i][cc] * y[cc];
+                    pv[i] = pn;
+                    skw[(L::PV + i) * W] = pn;
+                }
+                if (factor) {
+#pragma unroll
+                    for (int i = 0; i < NX; ++i)
+#pragma unroll
+                        for (int j = 0; j <= i; ++j) {
+                            double a = scr(SM_M + TRI(NU + i, NU + j));
+#pragma unroll
+                            for (int cc = 0; cc < NU; ++cc) a -= Lxu[i][cc] * Lxu[j][cc];
+                            P[TRI(i, j)] = a;
+                        }
+#pragma unroll
+                    for (int i = 0; i < NX; ++i)
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) skw[(L::P + i * NX + j) * W] = P[TRI(i, j)];
                 }
             } else {
                 // terminal velocity equalities through the last control: du = K dx + k0
@@ -464,55 +585,55 @@ struct LaneSolver {
                 if (factor) {
                     double G[NU][NU];
                     for (int a = 0; a < NU; ++a)
-                        for (int b = 0; b < NU; ++b) G[a][b] = BA[NQ + a][b];
+                        for (int b2 = 0; b2 < NU; ++b2) G[a][b2] = c[NQ + a][b2];
                     ok = inverse_small(G, Gi) && ok;
                     for (int a = 0; a < NU; ++a)
                         for (int j = 0; j < NX; ++j) {
                             double v = 0.0;
-                            for (int b = 0; b < NU; ++b) v -= Gi[a][b] * BA[NQ + b][NU + j];
+                            for (int b2 = 0; b2 < NU; ++b2) v -= Gi[a][b2] * c[NQ + b2][NU + j];
                             K[a][j] = v;
                             s(k, L::LXU + j * NU + a) = v;
                         }
                     for (int a = 0; a < NU; ++a)
-                        for (int b = 0; b < NU; ++b) s(k, L::LUU + a * NU + b) = Gi[a][b];
+                        for (int b2 = 0; b2 < NU; ++b2) s(k, L::LUU + a * NU + b2) = Gi[a][b2];
                     for (int a_ = 0; a_ < NZ; ++a_)
-                        for (int b_ = 0; b_ < NZ; ++b_) g(L::MF + a_ * NZ + b_) = M[a_][b_];
+                        for (int b_ = 0; b_ < NZ; ++b_) g(L::MF + a_ * NZ + b_) = scr(SM_M + TRI(a_, b_));
                 } else {
                     for (int a = 0; a < NU; ++a) {
-                        for (int b = 0; b < NU; ++b) Gi[a][b] = s(k, L::LUU + a * NU + b);
+                        for (int b2 = 0; b2 < NU; ++b2) Gi[a][b2] = s(k, L::LUU + a * NU + b2);
                         for (int j = 0; j < NX; ++j) K[a][j] = s(k, L::LXU + j * NU + a);
                     }
                 }
                 for (int a = 0; a < NU; ++a) {
                     double v = 0.0;
-                    for (int b = 0; b < NU; ++b) v -= Gi[a][b] * (g(L::EN + NQ + b) + s(k, L::RB + NQ + b));
+                    for (int b2 = 0; b2 < NU; ++b2) v -= Gi[a][b2] * (g(L::EN + NQ + b2) + s(k, L::RB + NQ + b2));
                     k0[a] = v;
                     g(L::K0 + a) = v;
                 }
                 for (int i = 0; i < NZ; ++i) {
-                    double v = m[i];
-                    for (int a = 0; a < NU; ++a) v += M[i][a] * k0[a];
+                    double v = scr(SM_V + i);
+                    for (int a = 0; a < NU; ++a) v += scr(SM_M + TRI(i, a)) * k0[a];
                     tmp[i] = v;
-                    g(L::ML + i) = m[i];
+                    g(L::ML + i) = scr(SM_V + i);
                 }
                 if (factor) {
                     for (int i = 0; i < NX; ++i)
                         for (int j = 0; j <= i; ++j) {
-                            double a = M[NU + i][NU + j];
-                            for (int c = 0; c < NU; ++c) {
-                                a += K[c][i] * M[c][NU + j] + M[NU + i][c] * K[c][j];
-                                for (int c2 = 0; c2 < NU; ++c2) a += K[c][i] * M[c][c2] * K[c2][j];
+                            double a = scr(SM_M + TRI(NU + i, NU + j));
+                            for (int cc = 0; cc < NU; ++cc) {
+                                a += K[cc][i] * scr(SM_M + TRI(cc, NU + j)) + scr(SM_M + TRI(NU + i, cc)) * K[cc][j];
+                                for (int c2 = 0; c2 < NU; ++c2) a += K[cc][i] * scr(SM_M + TRI(cc, c2)) * K[c2][j];
                             }
-                            P[i][j] = a, P[j][i] = a;
+                            P[TRI(i, j)] = a;
                         }
                     for (int i = 0; i < NX; ++i)
-                        for (int j = 0; j < NX; ++j) s(k, L::P + i * NX + j) = P[i][j];
+                        for (int j = 0; j < NX; ++j) s(k, L::P + i * NX + j) = P[TRI(i, j)];
                 }
                 for (int j = 0; j < NX; ++j) {
-                    double p = tmp[NU + j];
-                    for (int a = 0; a < NU; ++a) p += K[a][j] * tmp[a];
-                    pv[j] = p;
-                    s(k, L::PV + j) = p;
+                    double pn = tmp[NU + j];
+                    for (int a = 0; a < NU; ++a) pn += K[a][j] * tmp[a];
+                    pv[j] = pn;
+                    s(k, L::PV + j) = pn;
                 }
             }
         }
@@ -521,12 +642,12 @@ struct LaneSolver {
             double T[NX][NX], Lz[NX][NX], dzi[NX];
             for (int i = 0; i < NX; ++i) {
                 double a = 0.0;
-                for (int j = 0; j < NX; ++j) a += P[i][j] * g(L::E0 + j);
+                for (int j = 0; j < NX; ++j) a += P[TRI(i, j)] * g(L::E0 + j);
                 g(L::PE + i) = a;
-                for (int c = 0; c < NX; ++c) {
+                for (int cc = 0; cc < NX; ++cc) {
                     double t = 0.0;
-                    for (int j = 0; j < NX; ++j) t += P[i][j] * g(L::Z0 + j * NX + c);
-                    T[i][c] = t;
+                    for (int j = 0; j < NX; ++j) t += P[TRI(i, j)] * g(L::Z0 + j * NX + cc);
+                    T[i][cc] = t;
                 }
             }
             for (int a_ = 0; a_ < NX; ++a_)
@@ -537,17 +658,17 @@ struct LaneSolver {
                 }
             for (int j = 0; j < NX; ++j) {
                 double d = Lz[j][j];
-                for (int c = 0; c < j; ++c) d -= Lz[j][c] * Lz[j][c];
+                for (int cc = 0; cc < j; ++cc) d -= Lz[j][cc] * Lz[j][cc];
                 dzi[j] = d > 0.0 ? VB_RSQRT(d) : 0.0;
                 for (int i = j + 1; i < NX; ++i) {
                     double a = Lz[i][j];
-                    for (int c = 0; c < j; ++c) a -= Lz[i][c] * Lz[j][c];
+                    for (int cc = 0; cc < j; ++cc) a -= Lz[i][cc] * Lz[j][cc];
                     Lz[i][j] = a * dzi[j];
                 }
             }
             for (int i = 0; i < NX; ++i) {
                 g(L::DZI + i) = dzi[i];
-                for (int c = 0; c < i; ++c) g(L::LZ + i * NX + c) = Lz[i][c];
+                for (int cc = 0; cc < i; ++cc) g(L::LZ + i * NX + cc) = Lz[i][cc];
             }
         }
         {
@@ -566,7 +687,7 @@ struct LaneSolver {
             }
             for (int i = 0; i < NX; ++i) {
                 double a = -e0s * g(L::E0 + i);
-                for (int c = 0; c < NX; ++c) a += g(L::Z0 + i * NX + c) * dy[c];
+                for (int cc = 0; cc < NX; ++cc) a += g(L::Z0 + i * NX + cc) * dy[cc];
                 dx0[i] = a;
             }
         }
@@ -602,37 +723,92 @@ struct LaneSolver {
     // corrector gradient pieces Q1, Q2; modes 1/2 store DT, DLAM.
     // slack / multiplier steps of the bound constraints of stage k for the primal step dz: ratio test and
     // the sums of mu(alpha); mode 0 stores the second-order products and Q1, Q2, modes 1/2 store DT, DLAM
-    VB_HD void con_stage(int k, const double *dz, int mode, double sm, double &al, double &s0, double &s1,
+    // Memory discipline of the streaming loops: every access goes through `base`, so the compiler cannot move a
+    // load above an earlier store.  Each block therefore LOADS everything it needs first (independent loads, one
+    // exposed round trip), computes in registers, and stores last.
+    static constexpr int CBS = (NZ % 3 == 0) ? 3 : 2;  // components per block (code size vs loads in flight)
+    VB_HD void con_block(int k, int I0, const double *dzb, int mode, double sm, double &al, double &s0, double &s1,
                          double &s2) {
-            for (int i = 0; i < NZ; ++i) {
-                double q1 = 0.0, q2 = 0.0;
-                if (active(k, i)) {
-                    double z = s(k, L::Z + i), v = s(k, L::DZ + i);
+        constexpr int NI = CBS;
+        const double *sk = &s(k, 0);
+        double *skw = &s(k, 0);
+        const int sc = sclass(k);
+        double z[NI], v[NI], lam[2][NI], t[2][NI], pr[2][NI], rr[NI], bl[NI], bu[NI];
 #pragma unroll
-                    for (int sd = 0; sd < 2; ++sd) {
-                        double lam = s(k, L::LAMQ + sd * NZ + i), t = s(k, L::TQ + sd * NZ + i);
-                        double rd = sd ? v - (ub(k, i) - z) + t : (lb(k, i) - z) - v + t;
-                        double rm = lam * t;
-                        if (mode == 1) rm += s(k, L::PROD + sd * NZ + i) - sm;
-                        if (mode == 2) rm -= sm;
-                        double dtt = (sd ? -dz[i] : dz[i]) - rd;
-                        double it = 1.0 / t;
-                        double dl = -(rm + lam * dtt) * it;
-                        if (dtt < 0.0 && t + al * dtt < 0.0) al = fmin(al, -t / dtt);
-                        if (dl < 0.0 && lam + al * dl < 0.0) al = fmin(al, -lam / dl);
-                        s0 += lam * t, s1 += lam * dtt + t * dl, s2 += dtt * dl;
-                        if (mode == 0) {
-                            double pr = dtt * dl;
-                            s(k, L::PROD + sd * NZ + i) = pr;
-                            q1 += sd ? -pr * it : pr * it;
-                            q2 += sd ? -it : it;
-                        } else {
-                            s(k, L::DT + sd * NZ + i) = dtt, s(k, L::DLAM + sd * NZ + i) = dl;
-                        }
+        for (int a = 0; a < NI; ++a) {
+            const int i = I0 + a;
+            z[a] = sk[(L::Z + i) * W], v[a] = sk[(L::DZ + i) * W];
+            bl[a] = g(L::LB + sc * NZ + i), bu[a] = g(L::UB + sc * NZ + i);
+            rr[a] = mode == 0 ? sk[(L::RR + i) * W] : 0.0;
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                lam[sd][a] = sk[(L::LAMQ + sd * NZ + i) * W], t[sd][a] = sk[(L::TQ + sd * NZ + i) * W];
+                pr[sd][a] = mode == 1 ? sk[(L::PROD + sd * NZ + i) * W] : 0.0;
+            }
+        }
+        double o1[2][NI], o2[2][NI], q1[NI], q2[NI];
+#pragma unroll
+        for (int a = 0; a < NI; ++a) {
+            const int i = I0 + a;
+            q1[a] = 0.0, q2[a] = 0.0;
+            const bool act = active(k, i);
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                const double lm = act ? lam[sd][a] : 1.0, tt = act ? t[sd][a] : 1.0;
+                const double rd = sd ? v[a] - (bu[a] - z[a]) + tt : (bl[a] - z[a]) - v[a] + tt;
+                double rm = lm * tt;
+                if (mode == 1) rm += pr[sd][a] - sm;
+                if (mode == 2) rm -= sm;
+                const double dtt = (sd ? -dzb[a] : dzb[a]) - rd;
+                const double it = 1.0 / tt;
+                const double dl = -(rm + lm * dtt) * it;
+                if (act) {
+                    if (dtt < 0.0 && tt + al * dtt < 0.0) al = fmin(al, -tt / dtt);
+                    if (dl < 0.0 && lm + al * dl < 0.0) al = fmin(al, -lm / dl);
+                    s0 += lm * tt, s1 += lm * dtt + tt * dl, s2 += dtt * dl;
+                    const double p_ = dtt * dl;
+                    q1[a] += sd ? -p_ * it : p_ * it;
+                    q2[a] += sd ? -it : it;
+                    o1[sd][a] = mode == 0 ? p_ : dtt, o2[sd][a] = dl;
+                } else {
+                    o1[sd][a] = 0.0, o2[sd][a] = 0.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < NI; ++a) {
+            const int i = I0 + a;
+            if (active(k, i)) {
+#pragma unroll
+                for (int sd = 0; sd < 2; ++sd) {
+                    if (mode == 0) {
+                        skw[(L::PROD + sd * NZ + i) * W] = o1[sd][a];
+                    } else {
+                        skw[(L::DT + sd * NZ + i) * W] = o1[sd][a], skw[(L::DLAM + sd * NZ + i) * W] = o2[sd][a];
                     }
                 }
-                if (mode == 0) s(k, L::Q1 + i) = s(k, L::RR + i) + q1, s(k, L::Q2 + i) = q2;
             }
+            if (mode == 0) skw[(L::Q1 + i) * W] = rr[a] + q1[a], skw[(L::Q2 + i) * W] = q2[a];
+        }
+    }
+    // slack / multiplier steps of the bound constraints of stage k for the primal step dz: ratio test and
+    // the sums of mu(alpha); mode 0 stores the second-order products and Q1, Q2, modes 1/2 store DT, DLAM
+    VB_HD void con_stage(int k, const double *dz, int mode, double sm, double &al, double &s0, double &s1,
+                         double &s2) {
+#pragma unroll 1
+        for (int b0 = 0; b0 < NZ / CBS; ++b0) {
+            double dzb[CBS];
+#pragma unroll
+            for (int a = 0; a < CBS; ++a) {
+                // dz lives in registers: pick the block's entries with selects instead of dynamic indexing
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < NZ; ++i)
+                    if (i == b0 * CBS + a) v = dz[i];
+                dzb[a] = v;
+            }
+            con_block(k, b0 * CBS, dzb, mode, sm, al, s0, s1, s2);
+        }
     }
     VB_HD double con_pass(int mode, double sm, double &S0, double &S1, double &S2) {
         double al = 1.0, s0 = 0, s1 = 0, s2 = 0;
@@ -689,50 +865,103 @@ struct LaneSolver {
         const size_t fDV = mode == 3 ? L::DVB + (size_t)bj * NZ : L::DV;
         const size_t fDPI = mode == 3 ? L::DPIB + (size_t)bj * NX : L::DPI;
         double dx[NX], al = 1.0, s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
         for (int i = 0; i < NX; ++i) dx[i] = dx0[i];
 #pragma unroll 1
         for (int k = 0; k <= N; ++k) {
             const bool last = (k == N - 1) && termfix;
+            prefetch_l2(k + 2, L::Z, L::Z + NZ);
+            prefetch_l2(k + 2, L::BA, L::BA + NX * NZ + NX);
+            prefetch_l2(k + 2, L::LUU, L::DV);
+            if (mode == 0) prefetch_l2(k + 2, L::RR, L::Q1);
+            if (mode == 1) prefetch_l2(k + 2, L::PROD, L::DLAM);
+            const double *sk = &s(k, 0);
+            double *skw = &s(k, 0);
             double dz[NZ];
+#pragma unroll
             for (int i = 0; i < NX; ++i) dz[NU + i] = dx[i];
-            for (int c = 0; c < NU; ++c) dz[c] = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < NU; ++cc) dz[cc] = 0.0;
             if (k < N) {
+                // phase 1: the control step from the factors
+                double lxu[NX][NU], luu[NU][NU], yv[NU];
+#pragma unroll
+                for (int j = 0; j < NX; ++j)
+#pragma unroll
+                    for (int cc = 0; cc < NU; ++cc) lxu[j][cc] = sk[(L::LXU + j * NU + cc) * W];
+#pragma unroll
+                for (int i = 0; i < NU; ++i) {
+                    yv[i] = last ? g(L::K0 + i) : sk[(L::YV + i) * W];
+#pragma unroll
+                    for (int cc = 0; cc <= i; ++cc) luu[i][cc] = sk[(L::LUU + i * NU + cc) * W];
+                }
                 if (!last) {
                     double t[NU];
-                    for (int c = 0; c < NU; ++c) {
-                        double a = s(k, L::YV + c);
-                        for (int j = 0; j < NX; ++j) a += s(k, L::LXU + j * NU + c) * dx[j];
-                        t[c] = a;
+#pragma unroll
+                    for (int cc = 0; cc < NU; ++cc) {
+                        double a = yv[cc];
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) a += lxu[j][cc] * dx[j];
+                        t[cc] = a;
                     }
-                    for (int c = NU - 1; c >= 0; --c) {
-                        double a = -t[c];
-                        for (int c2 = c + 1; c2 < NU; ++c2) a -= s(k, L::LUU + c2 * NU + c) * dz[c2];
-                        dz[c] = a * s(k, L::LUU + c * NU + c);
+#pragma unroll
+                    for (int cc = NU - 1; cc >= 0; --cc) {
+                        double a = -t[cc];
+#pragma unroll
+                        for (int c2 = cc + 1; c2 < NU; ++c2) a -= luu[c2][cc] * dz[c2];
+                        dz[cc] = a * luu[cc][cc];
                     }
                 } else {
+#pragma unroll
                     for (int a_ = 0; a_ < NU; ++a_) {
-                        double a = g(L::K0 + a_);
-                        for (int j = 0; j < NX; ++j) a += s(k, L::LXU + j * NU + a_) * dx[j];
+                        double a = yv[a_];
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) a += lxu[j][a_] * dx[j];
                         dz[a_] = a;
                     }
                 }
             }
-            for (int i = 0; i < NZ; ++i) s(k, fDV + i) = dz[i];
+#pragma unroll
+            for (int i = 0; i < NZ; ++i) skw[(fDV + i) * W] = dz[i];
             if (!raw) con_stage(k, dz, mode, sm, al, s0, s1, s2);
             if (k < N) {
+                // phase 2: the next state
                 double dxn[NX];
-                for (int i = 0; i < NX; ++i) {
-                    double a = mode == 3 ? 0.0 : s(k, L::RB + i);
-                    for (int j = 0; j < NZ; ++j) a += s(k, L::BA + i * NZ + j) * dz[j];
-                    dxn[i] = a;
-                }
-                // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
-                if (k + 1 < N) {
+                {
+                    double c[NX][NZ], rb[NX];
+#pragma unroll
                     for (int i = 0; i < NX; ++i) {
-                        double a = s(k + 1, L::PV + i);
-                        for (int j = 0; j < NX; ++j) a += s(k + 1, L::P + i * NX + j) * dxn[j];
-                        s(k, fDPI + i) = a;
+                        rb[i] = mode == 3 ? 0.0 : sk[(L::RB + i) * W];
+#pragma unroll
+                        for (int j = 0; j < NZ; ++j) c[i][j] = sk[(L::BA + i * NZ + j) * W];
                     }
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
+                        double a = rb[i];
+#pragma unroll
+                        for (int j = 0; j < NZ; ++j) a += c[i][j] * dz[j];
+                        dxn[i] = a;
+                    }
+                }
+                // phase 3: dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
+                if (k + 1 < N) {
+                    const double *sn = &s(k + 1, 0);
+                    double Pn[NX][NX], pn[NX], dpi[NX];
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
+                        pn[i] = sn[(L::PV + i) * W];
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) Pn[i][j] = sn[(L::P + i * NX + j) * W];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
+                        double a = pn[i];
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) a += Pn[i][j] * dxn[j];
+                        dpi[i] = a;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) skw[(fDPI + i) * W] = dpi[i];
                 } else {
                     double nuv[NU];
                     if (last) {
@@ -742,18 +971,20 @@ struct LaneSolver {
                             for (int j = 0; j < NZ; ++j) a += g(L::MF + a_ * NZ + j) * dz[j];
                             tu[a_] = a;
                         }
-                        for (int b = 0; b < NU; ++b) {
+                        for (int b2 = 0; b2 < NU; ++b2) {
                             double a = 0.0;
-                            for (int a_ = 0; a_ < NU; ++a_) a -= s(k, L::LUU + a_ * NU + b) * tu[a_];
-                            nuv[b] = a;
+                            for (int a_ = 0; a_ < NU; ++a_) a -= s(k, L::LUU + a_ * NU + b2) * tu[a_];
+                            nuv[b2] = a;
                         }
                     }
+#pragma unroll
                     for (int i = 0; i < NX; ++i) {
                         double a = g(L::HHN + i) * dxn[i] + g(L::RN + i);
                         if (last && i >= NQ) a = nuv[i - NQ];
-                        s(k, fDPI + i) = a;
+                        skw[(fDPI + i) * W] = a;
                     }
                 }
+#pragma unroll
                 for (int i = 0; i < NX; ++i) dx[i] = dxn[i];
             }
         }
@@ -780,9 +1011,9 @@ struct LaneSolver {
                 double S0, S1, S2, dx0[NX];
                 ok = backward(ph, sm, dx0) && ok;
                 if (!ok) break;
-                if (nb == 0) {
+                if (!DTS || nb == 0) {
                     alpha = forward(ph, sm, dx0, S0, S1, S2);
-                } else {
+                } else if constexpr (DTS != 0) {
                     forward(ph, sm, dx0, S0, S1, S2, true);
                     if (ph == 0)
                         for (int j = 0; j < nb; ++j) {
@@ -810,15 +1041,34 @@ struct LaneSolver {
             if (as < 1.0) as = as * ((1.0 - as) * 0.99 + as * 0.9999);
 #pragma unroll 1
             for (int k = 0; k <= N; ++k) {
-                for (int i = 0; i < NZ; ++i) s(k, L::DZ + i) += as * s(k, L::DV + i);
-                if (k < N)
-                    for (int i = 0; i < NX; ++i) s(k, L::PIQ + i) += as * s(k, L::DPI + i);
-                for (int c = 0; c < NC; ++c) {
-                    int i = c >= NZ ? c - NZ : c;
-                    if (active(k, i)) {
-                        s(k, L::LAMQ + c) = fmax(s(k, L::LAMQ + c) + as * s(k, L::DLAM + c), o.qp_lam_min);
-                        s(k, L::TQ + c) = fmax(s(k, L::TQ + c) + as * s(k, L::DT + c), o.qp_t_min);
-                    }
+                prefetch_l2(k + 2, L::DZ, L::PROD);
+                prefetch_l2(k + 2, L::DLAM, L::WDYN);
+                const double *sk = &s(k, 0);
+                double *skw = &s(k, 0);
+                {
+                    double a0[NZ], a1[NZ], b0[NX], b1[NX];
+#pragma unroll
+                    for (int i = 0; i < NZ; ++i) a0[i] = sk[(L::DZ + i) * W], a1[i] = sk[(L::DV + i) * W];
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) b0[i] = sk[(L::PIQ + i) * W], b1[i] = sk[(L::DPI + i) * W];
+#pragma unroll
+                    for (int i = 0; i < NZ; ++i) skw[(L::DZ + i) * W] = a0[i] + as * a1[i];
+                    if (k < N)
+#pragma unroll
+                        for (int i = 0; i < NX; ++i) skw[(L::PIQ + i) * W] = b0[i] + as * b1[i];
+                }
+                {
+                    double a0[NC], a1[NC];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) a0[c] = sk[(L::LAMQ + c) * W], a1[c] = sk[(L::DLAM + c) * W];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+                        if (active(k, c >= NZ ? c - NZ : c)) skw[(L::LAMQ + c) * W] = fmax(a0[c] + as * a1[c], o.qp_lam_min);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) a0[c] = sk[(L::TQ + c) * W], a1[c] = sk[(L::DT + c) * W];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+                        if (active(k, c >= NZ ? c - NZ : c)) skw[(L::TQ + c) * W] = fmax(a0[c] + as * a1[c], o.qp_t_min);
                 }
             }
         }

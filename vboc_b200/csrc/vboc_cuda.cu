@@ -88,11 +88,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) solve_kernel(const B
 // at the top of the loop, so the warp stays full until the queue is empty.
 constexpr int LANE_THREADS = 128;
 template <int NQ, int FAM, int DTS>
-__global__ void __launch_bounds__(LANE_THREADS, 2) solve_lane_kernel(const Batch B) {
+__global__ void __launch_bounds__(LANE_THREADS, 2) solve_lane_kernel(const Batch B, double *work) {
+    // `work` is a direct pointer parameter (not a member of B) so that the compiler knows it is global memory
+    // and emits LDG/STG instead of generic loads / stores
     const int lane = threadIdx.x & 31;
     const size_t wslot = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    double *base = B.work + wslot * LaneLayout<NQ, DTS>::TOTAL * 32;
-    LaneSolver<NQ, FAM, 32, DTS> sol(base, lane, B.opts);
+    double *base = work + wslot * LaneLayout<NQ, DTS>::TOTAL * 32;
+    // per-thread scratch [element][thread] (conflict free): the symmetric stage Hessian and its gradient
+    extern __shared__ double lane_scratch[];  // SM_TOTAL * LANE_THREADS doubles (dynamic: > 48 KB for n = 3)
+    double *scratch = lane_scratch + threadIdx.x;
+    // address-space facts for the optimiser: typed loads/stores (LDG/STG, LDS/STS) instead of generic ones,
+    // and no aliasing between the workspace and the scratch
+    LaneSolver<NQ, FAM, 32, DTS> sol(base, scratch, lane, B.opts);
     LaneState ls;
     ls.have = 0, ls.it = 0;
     Prob pb;
@@ -180,7 +187,9 @@ struct vboc_solver {
 template <int NQ, int FAM>
 static cudaError_t launch(vboc_solver *s, const Batch &B) {
     if (s->lane_kernel) {
-        solve_lane_kernel<NQ, FAM, 0><<<s->grid, LANE_THREADS, 0, s->stream>>>(B);
+        const int smem = LaneSolver<NQ, FAM, 32, 0>::SM_TOTAL * LANE_THREADS * (int)sizeof(double);
+        cudaFuncSetAttribute(solve_lane_kernel<NQ, FAM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        solve_lane_kernel<NQ, FAM, 0><<<s->grid, LANE_THREADS, smem, s->stream>>>(B, B.work);
         return cudaGetLastError();
     }
     if (s->ctas_per_sm >= 6)
@@ -478,7 +487,8 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
     cudaError_t e = cudaErrorInvalidValue;
     if (s->free_dt) {
         B.work = s->dwork_free_dt;
-        solve_lane_kernel<1, VBOC_FAMILY_VBOC, 1><<<s->grid_free_dt, LANE_THREADS, 0, s->stream>>>(B);
+        const int smem = LaneSolver<1, VBOC_FAMILY_VBOC, 32, 1>::SM_TOTAL * LANE_THREADS * (int)sizeof(double);
+        solve_lane_kernel<1, VBOC_FAMILY_VBOC, 1><<<s->grid_free_dt, LANE_THREADS, smem, s->stream>>>(B, B.work);
         e = cudaGetLastError();
     } else {
 #define GO(NQ, FAM) \

@@ -21,6 +21,8 @@
  *                                (VBOC/triplependulum_vboc.py:399-402)
  *   vboc_upload / vboc_solve_resident / vboc_download
  *                                the same three steps split so that inputs may stay resident in HBM
+ *   vboc_stream_*                the same solves as a ticket queue (see below): the drivers' per-problem loops
+ *                                VBOC/triplependulum_vboc.py:107-136, 232-289, triplependulum_testdata.py:77-125
  *   vboc_mlp_create / _forward   model_dir(...) / sigmoid(model(...)) + entropy: my_nn.py:4-34,
  *                                VBOC/triplependulum_vboc.py:604-620, AL/triplependulum_al.py:253-264
  *   vboc_sim_step                SYMtriplependulumINIT.acados_integrator set/solve/get
@@ -124,6 +126,34 @@ int vboc_download(vboc_solver *s, double *x, double *u, vboc_stats *stats);
 /* Device time of the last vboc_solve_resident kernel in milliseconds (CUDA events on the solver's
  * stream); negative if none. */
 double vboc_last_kernel_ms(vboc_solver *s);
+
+/*
+ * Streaming engine.  Replaces `Pool.map(data_generation, ...)` / `Pool.map(testing, ...)`
+ * (VBOC/triplependulum_vboc.py:399-402, triplependulum_testdata.py:141-142) when every problem is a CHAIN of
+ * dependent OCP_solve calls of very different lengths (extension loop VBOC/triplependulum_vboc.py:107-136,
+ * sub-OCP chains :232-289): problems are submitted whenever a worker has one ready and are collected one by
+ * one as they finish, so no solve ever waits for another worker's solve.
+ *   vboc_stream_submit    same arrays as vboc_solve_batch with `count` rows; writes one ticket per problem.
+ *                         count must not exceed vboc_stream_free_slots().  Returns right after the launch.
+ *   vboc_stream_poll      non-blocking: up to `max` tickets whose solve has finished; returns how many.
+ *   vboc_stream_fetch     copies the result of a finished ticket (rows 0..N of x, 0..N-1 of u) and frees it.
+ *   vboc_stream_sim_step  vboc_sim_step on the engine's own stream (does not wait for solves in flight).
+ * A free dt state (1-DOF VBOC driver) is not served here (VBOC_ERR_UNSUPPORTED): use vboc_solve_batch.
+ * One handle per host thread.
+ */
+typedef struct vboc_stream vboc_stream;
+int vboc_stream_create(int n_dof, int family, int capacity, int N_max, int device, vboc_stream **out);
+void vboc_stream_destroy(vboc_stream *s);
+int vboc_stream_set_opts(vboc_stream *s, const vboc_opts *o);
+int vboc_stream_free_slots(vboc_stream *s);
+int vboc_stream_pending(vboc_stream *s);
+int vboc_stream_submit(vboc_stream *s, int mode, int count, const int *N, const double *x_guess,
+                       const double *u_guess, const double *p, const double *lbx0, const double *ubx0,
+                       const double *lbx, const double *ubx, const double *lbxN, const double *ubxN,
+                       const double *lbu, const double *ubu, const double *C0, double Tf, int *tickets);
+int vboc_stream_poll(vboc_stream *s, int max, int *tickets);
+int vboc_stream_fetch(vboc_stream *s, int ticket, double *x, double *u, vboc_stats *stats);
+int vboc_stream_sim_step(vboc_stream *s, int count, const double *x, const double *u, double T, double *x_next);
 
 /* One classical RK4 step of the unscaled 2n-state model: x_next = Phi_T(x, u).  HOST arrays
  * x [batch][2n], u [batch][n], x_next [batch][2n]. */

@@ -84,3 +84,61 @@ def test_pendulum_data_generation(backend):
         assert abs(x[0] - lim) < 5e-3, (q, v, x)
         checked += 1
     assert checked >= 3
+
+
+class FakeStream:
+    """The ticket-queue protocol of `engine.StreamSolver` served by the oracle: finished tickets are handed
+    out late and out of order, at most a few per poll, with a tiny slot pool -- the event loop must cope."""
+
+    def __init__(self, oracle, n, slots=3):
+        self.oracle, self.n, self.slots = oracle, n, slots
+        self.results, self.order, self.next_ticket, self.polls = {}, [], 0, 0
+        self.rng = np.random.default_rng(0)
+
+    @property
+    def free_slots(self):
+        return self.slots - len(self.results)
+
+    def submit(self, bp, mode=0):
+        B = len(bp["N"])
+        assert 1 <= B <= self.free_slots
+        out = self.oracle.solve_batch(self.n, 0, mode, bp)
+        tk = []
+        for b in range(B):
+            t = self.next_ticket
+            self.next_ticket += 1
+            N = int(bp["N"][b])
+            self.results[t] = dict(status=int(out["status"][b]), cost=float(out["cost"][b]),
+                                   x=out["x"][b, :N + 1].copy(), u=out["u"][b, :N].copy())
+            self.order.append(t)
+            tk.append(t)
+        return np.array(tk, dtype=np.int32)
+
+    def poll(self):
+        self.polls += 1
+        if self.polls % 2 or not self.order:
+            return []
+        self.rng.shuffle(self.order)
+        k = int(self.rng.integers(1, 3))
+        out, self.order = self.order[:k], self.order[k:]
+        return out
+
+    def fetch(self, t):
+        return self.results.pop(t)
+
+    def sim_step(self, X, U, T):
+        return np.stack([self.oracle.rk4(self.n, 1, x, u, T) for x, u in zip(X, U)])
+
+
+def test_stream_event_loop_equals_rounds(oracle, backend):
+    """`run_workers_stream` (tickets, out-of-order completion, slot back-pressure) returns exactly what the
+    round-synchronous `run_workers` returns for the same workers."""
+    n = 2
+    st_r, st_s = {}, {}
+    a = drivers.data_generation_batch(n, 5, seed=21, backend=backend(n), stats=st_r)
+    b = drivers.data_generation_stream(n, 5, seed=21, ssol=FakeStream(oracle, n), stats=st_s)
+    assert np.array_equal(a, b)
+    assert st_r["solves"] == st_s["solves"] and st_r["converged"] == st_s["converged"]
+    c = drivers.testing_batch(n, 4, seed=2, backend=backend(n))
+    d = drivers.testing_stream(n, 4, seed=2, ssol=FakeStream(oracle, n, slots=2))
+    assert np.array_equal(c, d)

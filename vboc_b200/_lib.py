@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvboc_b200.so")
+# VBOC_LIB: kernel-tuning experiments load a differently compiled build of the same library (tools/build_variant.sh)
+LIB_PATH = os.environ.get("VBOC_LIB") or os.path.join(_HERE, "libvboc_b200.so")
 
 FAMILY_VBOC, FAMILY_AL = 0, 1
 MODE_SQP, MODE_RTI = 0, 1
@@ -18,6 +19,8 @@ EXPORTS = (
     "vboc_default_opts", "vboc_create", "vboc_destroy", "vboc_set_opts", "vboc_set_stream",
     "vboc_solve_batch", "vboc_upload", "vboc_solve_resident", "vboc_solve_resident_async", "vboc_sync",
     "vboc_download", "vboc_last_kernel_ms",
+    "vboc_stream_create", "vboc_stream_destroy", "vboc_stream_set_opts", "vboc_stream_free_slots",
+    "vboc_stream_pending", "vboc_stream_submit", "vboc_stream_poll", "vboc_stream_fetch", "vboc_stream_sim_step",
     "vboc_sim_step", "vboc_mlp_create", "vboc_mlp_destroy", "vboc_mlp_forward", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
 )
 
@@ -79,6 +82,16 @@ def lib():
         L.vboc_last_kernel_ms.argtypes = [vp]
         L.vboc_last_kernel_ms.restype = C.c_double
         L.vboc_sim_step.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, dp]
+        L.vboc_stream_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.vboc_stream_destroy.argtypes = [vp]
+        L.vboc_stream_destroy.restype = None
+        L.vboc_stream_set_opts.argtypes = [vp, C.POINTER(Opts)]
+        L.vboc_stream_free_slots.argtypes = [vp]
+        L.vboc_stream_pending.argtypes = [vp]
+        L.vboc_stream_submit.argtypes = [vp, C.c_int, C.c_int, ip] + [dp] * 12 + [C.c_double, ip]
+        L.vboc_stream_poll.argtypes = [vp, C.c_int, ip]
+        L.vboc_stream_fetch.argtypes = [vp, C.c_int, dp, dp, C.POINTER(Stats)]
+        L.vboc_stream_sim_step.argtypes = [vp, C.c_int, dp, dp, C.c_double, dp]
         fp = C.POINTER(C.c_float)
         L.vboc_mlp_create.argtypes = [C.c_int] * 5 + [fp] * 6 + [C.POINTER(vp)]
         L.vboc_mlp_destroy.argtypes = [vp]

@@ -50,13 +50,46 @@ struct Batch {
     unsigned int *counter;
     int mode;
     vboc_opts opts;
+    // streaming launches (vboc_stream_*): the i-th problem of the launch lives in slot index[i] of the
+    // arrays above; done[slot] is raised (system scope) when its results are written; the CTA takes its
+    // workspace from a per-SM pool (ws_mask[sm]: one bit per workspace of that SM) because any number of
+    // launches may be resident at once.
+    const int *index;
+    int *done;
+    unsigned int *ws_mask;
+    int ws_per_sm;
 };
 
-template <int NQ, int FAM, int MINB>
+template <int NQ, int FAM, int MINB, bool STREAM = false>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) solve_kernel(const Batch B) {
     __shared__ Smem<NQ> smem[WARPS_PER_CTA];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * WARPS_PER_CTA + warp;
+    int slot = blockIdx.x * WARPS_PER_CTA + warp;
+    unsigned int *ws_word = nullptr;
+    unsigned int ws_bit = 0;
+    if constexpr (STREAM) {
+        // Workspaces belong to RESIDENT CTAs, not to launches: at most MINB CTAs of this kernel fit on an SM,
+        // so a pool of ws_per_sm >= MINB workspaces per SM serves every launch that is in flight.
+        __shared__ int cta_ws;
+        if (threadIdx.x == 0) {
+            unsigned int sm;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            ws_word = B.ws_mask + sm;
+            const unsigned int all = (1u << B.ws_per_sm) - 1u;
+            for (;;) {
+                unsigned int cur = *(volatile unsigned int *)ws_word, fr = ~cur & all;
+                if (fr) {
+                    ws_bit = fr & (0u - fr);
+                    if (atomicCAS(ws_word, cur, cur | ws_bit) == cur) break;
+                } else {
+                    __nanosleep(500);  // a CTA that migrated here after a preemption holds a bit: wait for a release
+                }
+            }
+            cta_ws = (int)sm * B.ws_per_sm + (__ffs(ws_bit) - 1);
+        }
+        __syncthreads();
+        slot = cta_ws * WARPS_PER_CTA + warp;
+    }
     Work<NQ> w;
     w.carve(B.work + (size_t)slot * B.work_doubles, B.Nmax);
     WarpSolver<NQ, FAM> sol(smem[warp], w, B.opts);
@@ -66,6 +99,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) solve_kernel(const B
         if (lane == 0) b = atomicAdd(B.counter, 1u);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= (unsigned)B.batch) break;
+        if constexpr (STREAM) b = (unsigned)B.index[b];
         Prob pb;
         pb.N = B.N[b], pb.nxr = B.nxr, pb.h = B.h[b];
         pb.p = B.p ? B.p + (size_t)b * (NQ + 1) : nullptr;
@@ -76,10 +110,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) solve_kernel(const B
         pb.lbxN = B.lbxN + (size_t)b * B.nxr, pb.ubxN = B.ubxN + (size_t)b * B.nxr;
         pb.lbu = B.lbu + (size_t)b * nu, pb.ubu = B.ubu + (size_t)b * nu;
         pb.dir = B.dir ? B.dir + (size_t)b * NQ : nullptr;
+        if constexpr (STREAM) pb.dir = (B.dir && B.dir[(size_t)b * NQ] == B.dir[(size_t)b * NQ]) ? pb.dir : nullptr;
         pb.x = B.x + (size_t)b * (B.Nmax + 1) * B.nxr, pb.u = B.u + (size_t)b * B.Nmax * nu;
         pb.st = B.st + b;
         sol.solve(pb, B.mode);
         __syncwarp();
+        if constexpr (STREAM) {
+            // results (mapped host memory) before the flag, at system scope: the host polls done[]
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) *(volatile int *)(B.done + b) = 1;
+        }
+    }
+    if constexpr (STREAM) {
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAnd(ws_word, ~ws_bit);
     }
 }
 
@@ -159,6 +204,13 @@ __global__ void dfma_peak_kernel(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// number of SM identifiers (%smid < %nsmid; may exceed the SM count of the device)
+__global__ void nsmid_kernel(unsigned int *out) {
+    unsigned int v;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
+    *out = v;
+}
+
 }  // namespace
 
 struct vboc_solver {
@@ -198,6 +250,50 @@ static cudaError_t launch(vboc_solver *s, const Batch &B) {
         solve_kernel<NQ, FAM, 5><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
     else
         solve_kernel<NQ, FAM, 4><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Streaming engine: problems enter and leave one at a time (tickets), launches never wait for each other.
+// The drivers' per-problem state machines (data_generation / testing: chains of dependent solves whose
+// lengths differ 100x between problems) keep the GPU full this way; with whole-batch calls every round
+// waits for its slowest solve.
+//
+//  * problem slots (inputs, results, done flags) live in MAPPED PINNED host memory: the kernel reads a
+//    problem's ~9 KB once and writes its ~8 KB result over the host link, the host polls done[slot];
+//  * every submit is one launch of solve_kernel<.., STREAM> on a non-blocking stream of its own;
+//  * workspaces are bound to resident CTAs (per-SM pool), so any number of launches can be in flight.
+struct vboc_stream {
+    int n, family, cap, Nmax, device, nxr, nu, num_sms, nsmid;
+    vboc_opts opts;
+    // mapped pinned slot arrays
+    int *N, *done;
+    double *xg, *ug, *p, *lbx0, *ubx0, *lbx, *ubx, *lbxN, *ubxN, *lbu, *ubu, *dir, *h, *x, *u;
+    vboc_stats *st;
+    // device
+    double *dwork;
+    size_t work_doubles;
+    unsigned int *ws_mask, *dcounters;
+    int ws_per_sm;
+    // launch records
+    static constexpr int NREC = 96;
+    struct Rec {
+        cudaStream_t stream;
+        cudaEvent_t ev;
+        int *index;  // mapped pinned, cap entries
+        bool busy;
+    } rec[NREC];
+    std::vector<int> free_slots, inflight;
+    // batched RK4 steps on their own stream
+    cudaStream_t sim_stream;
+    double *sx, *su, *sxn;  // mapped pinned, sim_cap rows
+    int sim_cap;
+    long long launches, solved;
+};
+
+template <int NQ, int FAM>
+static cudaError_t launch_stream(int grid, cudaStream_t st, const Batch &B) {
+    solve_kernel<NQ, FAM, 5, true><<<grid, WARPS_PER_CTA * 32, 0, st>>>(B);
     return cudaGetLastError();
 }
 
@@ -353,6 +449,66 @@ static int d2h(vboc_solver *s, void *dst, const void *src, size_t bytes) {
     return 0;
 }
 
+// Validation and host-side preparation of one problem (what the shim's OCP_solve would otherwise do stage by
+// stage through ocp_solver.set / constraints_set): the RK4 step h, the unit direction d of the stage-0
+// projector, and the refusals listed in include/vboc_b200.h.  *pinned = false reports a free dt state
+// (VBOC family; the caller decides whether that is supported), h is then 1.
+static int prepare_problem(int n, int nxr, int Nmax, int family, int Nb, const double *l0, const double *u0,
+                           const double *l1, const double *u1, const double *lN, const double *uN,
+                           const double *xg, const double *C, double Tf, double *h, double *dir, bool *pinned_out) {
+    if (Nb < 1 || Nb > Nmax) return fail(VBOC_ERR_ARG, "vboc_upload: horizon out of range");
+    *pinned_out = true;
+    if (family == VBOC_FAMILY_VBOC) {
+        // the dt state must be pinned (VBOC/triplependulum_vboc.py:98-103)
+        double dt = l0[2 * n];
+        bool pinned = u0[2 * n] == dt && l1[2 * n] == dt && u1[2 * n] == dt && lN[2 * n] == dt && uN[2 * n] == dt;
+        for (int k = 0; k <= Nb && pinned; ++k) pinned = xg[(size_t)k * nxr + 2 * n] == dt;
+        if (!pinned) {
+            *pinned_out = false;
+            *h = 1.0;
+            return 0;
+        }
+        if (!(dt > 0.0)) return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: dt <= 0");
+        *h = dt;
+    } else {
+        *h = Tf / Nb;
+    }
+    int nf = 0, nfv = 0;
+    for (int i = 0; i < 2 * n; ++i)
+        if (lN[i] == uN[i]) {
+            ++nf;
+            nfv += i >= n;
+        }
+    if (!(nf == 0 || (nf == n && nfv == n)))
+        return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: terminal equalities must be on none or exactly all velocities");
+    if (C) {
+        // only C0 = [0 | I - d d' | 0] (VBOC/triplependulum_class_vboc.py:174-178)
+        double Md[3][3], d[3];
+        int jm = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) Md[i][j] = (i == j) - C[i * nxr + n + j];
+        for (int i = 1; i < n; ++i)
+            if (Md[i][i] > Md[jm][jm]) jm = i;
+        if (!(Md[jm][jm] > 0.0)) return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: C0 is not a projector I - d d'");
+        double dj = sqrt(Md[jm][jm]), nrm = 0.0;
+        for (int i = 0; i < n; ++i) d[i] = Md[i][jm] / dj, nrm += d[i] * d[i];
+        nrm = sqrt(nrm);
+        for (int i = 0; i < n; ++i) d[i] /= nrm;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < nxr; ++j) {
+                double want = (j >= n && j < 2 * n) ? (i == j - n) - d[i] * d[j - n] : 0.0;
+                if (fabs(C[i * nxr + j] - want) > 1e-9)
+                    return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: C0 is not of the form [0 | I - d d' | 0]");
+            }
+        for (int i = 0; i < n; ++i)
+            if (l0[n + i] == u0[n + i])
+                return fail(VBOC_ERR_UNSUPPORTED,
+                            "vboc_upload: fixed initial velocity together with a direction constraint");
+        for (int i = 0; i < n; ++i) dir[i] = d[i];
+    }
+    return 0;
+}
+
 int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
                 const double *u_guess, const double *p, const double *lbx0, const double *ubx0,
                 const double *lbx, const double *ubx, const double *lbxN, const double *ubxN,
@@ -370,70 +526,23 @@ int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
     bool free_dt = false;
     if (C0) dir.resize((size_t)batch * n);
     for (int b = 0; b < batch; ++b) {
-        if (N[b] < 1 || N[b] > Nmax) return fail(VBOC_ERR_ARG, "vboc_upload: horizon out of range");
-        const double *l0 = lbx0 + (size_t)b * nxr, *u0 = ubx0 + (size_t)b * nxr;
-        const double *l1 = lbx + (size_t)b * nxr, *u1 = ubx + (size_t)b * nxr;
-        const double *lN = lbxN + (size_t)b * nxr, *uN = ubxN + (size_t)b * nxr;
-        if (s->family == VBOC_FAMILY_VBOC) {
-            // the dt state must be pinned (VBOC/triplependulum_vboc.py:98-103)
-            double dt = l0[2 * n];
-            bool pinned = u0[2 * n] == dt && l1[2 * n] == dt && u1[2 * n] == dt && lN[2 * n] == dt &&
-                          uN[2 * n] == dt;
-            const double *xg = x_guess + (size_t)b * (Nmax + 1) * nxr;
-            for (int k = 0; k <= N[b] && pinned; ++k) pinned = xg[(size_t)k * nxr + 2 * n] == dt;
-            if (!pinned) {
-                // free dt (VBOC/pendulum_vboc.py:69-70): 1-DOF only, whole batch
-                if (n != 1 || (b > 0 && !free_dt))
-                    return fail(VBOC_ERR_UNSUPPORTED,
-                                "vboc_upload: the dt state must be pinned to one positive value at every "
-                                "stage and in the guess (a free dt is supported for the 1-DOF model only, "
-                                "and not mixed with pinned problems in one batch)");
-                free_dt = true;
-                h[b] = 1.0;
-                continue;
-            }
-            if (free_dt || !(dt > 0.0))
-                return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: pinned and free dt mixed in one batch, or dt <= 0");
-            h[b] = dt;
-        } else {
-            h[b] = Tf / N[b];
-        }
-        int nf = 0, nfv = 0;
-        for (int i = 0; i < 2 * n; ++i)
-            if (lN[i] == uN[i]) {
-                ++nf;
-                nfv += i >= n;
-            }
-        if (!(nf == 0 || (nf == n && nfv == n)))
-            return fail(VBOC_ERR_UNSUPPORTED,
-                        "vboc_upload: terminal equalities must be on none or exactly all velocities");
-        if (C0) {
-            // only C0 = [0 | I - d d' | 0] (VBOC/triplependulum_class_vboc.py:174-178)
-            const double *C = C0 + (size_t)b * n * nxr;
-            double Md[3][3], d[3];
-            int jm = 0;
-            for (int i = 0; i < n; ++i)
-                for (int j = 0; j < n; ++j) Md[i][j] = (i == j) - C[i * nxr + n + j];
-            for (int i = 1; i < n; ++i)
-                if (Md[i][i] > Md[jm][jm]) jm = i;
-            if (!(Md[jm][jm] > 0.0))
-                return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: C0 is not a projector I - d d'");
-            double dj = sqrt(Md[jm][jm]), nrm = 0.0;
-            for (int i = 0; i < n; ++i) d[i] = Md[i][jm] / dj, nrm += d[i] * d[i];
-            nrm = sqrt(nrm);
-            for (int i = 0; i < n; ++i) d[i] /= nrm;
-            for (int i = 0; i < n; ++i)
-                for (int j = 0; j < nxr; ++j) {
-                    double want = (j >= n && j < 2 * n) ? (i == j - n) - d[i] * d[j - n] : 0.0;
-                    if (fabs(C[i * nxr + j] - want) > 1e-9)
-                        return fail(VBOC_ERR_UNSUPPORTED,
-                                    "vboc_upload: C0 is not of the form [0 | I - d d' | 0]");
-                }
-            for (int i = 0; i < n; ++i)
-                if (l0[n + i] == u0[n + i])
-                    return fail(VBOC_ERR_UNSUPPORTED,
-                                "vboc_upload: fixed initial velocity together with a direction constraint");
-            for (int i = 0; i < n; ++i) dir[(size_t)b * n + i] = d[i];
+        bool pinned = true;
+        int rc = prepare_problem(n, nxr, Nmax, s->family, N[b], lbx0 + (size_t)b * nxr, ubx0 + (size_t)b * nxr,
+                                 lbx + (size_t)b * nxr, ubx + (size_t)b * nxr, lbxN + (size_t)b * nxr,
+                                 ubxN + (size_t)b * nxr, x_guess + (size_t)b * (Nmax + 1) * nxr,
+                                 C0 ? C0 + (size_t)b * n * nxr : nullptr, Tf, &h[b],
+                                 C0 ? &dir[(size_t)b * n] : nullptr, &pinned);
+        if (rc) return rc;
+        if (!pinned) {
+            // free dt (VBOC/pendulum_vboc.py:69-70): 1-DOF only, whole batch
+            if (n != 1 || (b > 0 && !free_dt))
+                return fail(VBOC_ERR_UNSUPPORTED,
+                            "vboc_upload: the dt state must be pinned to one positive value at every "
+                            "stage and in the guess (a free dt is supported for the 1-DOF model only, "
+                            "and not mixed with pinned problems in one batch)");
+            free_dt = true;
+        } else if (free_dt) {
+            return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: pinned and free dt mixed in one batch");
         }
     }
     size_t B = batch;
@@ -692,6 +801,239 @@ int vboc_sim_step(int n_dof, int device, int batch, const double *x, const doubl
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpy(x_next, dxn, B * nx * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(dx), cudaFree(du), cudaFree(dxn);
+    return 0;
+}
+
+int vboc_stream_create(int n_dof, int family, int capacity, int N_max, int device, vboc_stream **out) {
+    if (!out || n_dof < 1 || n_dof > 3 || (family != VBOC_FAMILY_VBOC && family != VBOC_FAMILY_AL) || capacity < 1 ||
+        N_max < 1 || N_max > (int)Work<3>::SMAX - 1)
+        return fail(VBOC_ERR_ARG, "vboc_stream_create: bad argument");
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(VBOC_ERR_CUDA, "vboc_stream_create: no such CUDA device");
+    CUDA_OK(cudaSetDevice(device));
+    vboc_stream *s = new vboc_stream();
+    s->n = n_dof, s->family = family, s->cap = capacity, s->Nmax = N_max, s->device = device;
+    s->nxr = 2 * n_dof + (family == VBOC_FAMILY_VBOC), s->nu = n_dof;
+    s->launches = s->solved = 0;
+    vboc_default_opts(family, &s->opts);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    s->num_sms = prop.multiProcessorCount;
+    size_t C = (size_t)capacity, nxr = s->nxr, nu = s->nu;
+#define HOST_ALLOC(ptr, count) \
+    CUDA_OK(cudaHostAlloc((void **)&s->ptr, (size_t)(count) * sizeof(*s->ptr), cudaHostAllocMapped | cudaHostAllocPortable))
+    HOST_ALLOC(N, C);
+    HOST_ALLOC(done, C);
+    HOST_ALLOC(xg, C * (N_max + 1) * nxr);
+    HOST_ALLOC(ug, C * N_max * nu);
+    HOST_ALLOC(p, C * (n_dof + 1));
+    HOST_ALLOC(lbx0, C * nxr);
+    HOST_ALLOC(ubx0, C * nxr);
+    HOST_ALLOC(lbx, C * nxr);
+    HOST_ALLOC(ubx, C * nxr);
+    HOST_ALLOC(lbxN, C * nxr);
+    HOST_ALLOC(ubxN, C * nxr);
+    HOST_ALLOC(lbu, C * nu);
+    HOST_ALLOC(ubu, C * nu);
+    HOST_ALLOC(dir, C * n_dof);
+    HOST_ALLOC(h, C);
+    HOST_ALLOC(x, C * (N_max + 1) * nxr);
+    HOST_ALLOC(u, C * N_max * nu);
+    HOST_ALLOC(st, C);
+    s->sim_cap = capacity;
+    HOST_ALLOC(sx, C * 2 * n_dof);
+    HOST_ALLOC(su, C * n_dof);
+    HOST_ALLOC(sxn, C * 2 * n_dof);
+    for (int r = 0; r < vboc_stream::NREC; ++r) {
+        HOST_ALLOC(rec[r].index, C);
+        CUDA_OK(cudaStreamCreateWithFlags(&s->rec[r].stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&s->rec[r].ev, cudaEventDisableTiming));
+        s->rec[r].busy = false;
+    }
+#undef HOST_ALLOC
+    memset(s->done, 0, C * sizeof(int));
+    CUDA_OK(cudaStreamCreateWithFlags(&s->sim_stream, cudaStreamNonBlocking));
+    // per-SM workspace pool: 5 CTAs of solve_kernel<.., 5, STREAM> are resident per SM at most; one spare
+    unsigned int *dn = nullptr, nsmid = 0;
+    CUDA_OK(cudaMalloc((void **)&dn, sizeof(unsigned int)));
+    nsmid_kernel<<<1, 1>>>(dn);
+    CUDA_OK(cudaMemcpy(&nsmid, dn, sizeof(nsmid), cudaMemcpyDeviceToHost));
+    cudaFree(dn);
+    s->nsmid = (int)nsmid > s->num_sms ? (int)nsmid : s->num_sms;
+    s->ws_per_sm = 6;
+    s->work_doubles = work_doubles_for(n_dof, N_max);
+    CUDA_OK(cudaMalloc((void **)&s->dwork,
+                       (size_t)s->nsmid * s->ws_per_sm * WARPS_PER_CTA * s->work_doubles * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&s->ws_mask, (size_t)s->nsmid * sizeof(unsigned int)));
+    CUDA_OK(cudaMemset(s->ws_mask, 0, (size_t)s->nsmid * sizeof(unsigned int)));
+    CUDA_OK(cudaMalloc((void **)&s->dcounters, vboc_stream::NREC * sizeof(unsigned int)));
+    s->free_slots.reserve(C);
+    for (int i = capacity - 1; i >= 0; --i) s->free_slots.push_back(i);
+    *out = s;
+    return 0;
+}
+
+void vboc_stream_destroy(vboc_stream *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    void *hp[] = {s->N,    s->done,  s->xg,  s->ug,  s->p,   s->lbx0, s->ubx0, s->lbx, s->ubx, s->lbxN, s->ubxN,
+                  s->lbu,  s->ubu,   s->dir, s->h,   s->x,   s->u,    s->st,   s->sx,  s->su,  s->sxn};
+    for (void *q : hp)
+        if (q) cudaFreeHost(q);
+    for (int r = 0; r < vboc_stream::NREC; ++r) {
+        if (s->rec[r].index) cudaFreeHost(s->rec[r].index);
+        if (s->rec[r].stream) cudaStreamDestroy(s->rec[r].stream);
+        if (s->rec[r].ev) cudaEventDestroy(s->rec[r].ev);
+    }
+    if (s->sim_stream) cudaStreamDestroy(s->sim_stream);
+    cudaFree(s->dwork), cudaFree(s->ws_mask), cudaFree(s->dcounters);
+    delete s;
+}
+
+int vboc_stream_set_opts(vboc_stream *s, const vboc_opts *o) {
+    if (!s || !o) return fail(VBOC_ERR_ARG, "vboc_stream_set_opts: null argument");
+    s->opts = *o;
+    return 0;
+}
+
+int vboc_stream_free_slots(vboc_stream *s) { return s ? (int)s->free_slots.size() : 0; }
+int vboc_stream_pending(vboc_stream *s) { return s ? (int)s->inflight.size() : 0; }
+
+int vboc_stream_submit(vboc_stream *s, int mode, int count, const int *N, const double *x_guess,
+                       const double *u_guess, const double *p, const double *lbx0, const double *ubx0,
+                       const double *lbx, const double *ubx, const double *lbxN, const double *ubxN,
+                       const double *lbu, const double *ubu, const double *C0, double Tf, int *tickets) {
+    if (!s || !tickets) return fail(VBOC_ERR_ARG, "vboc_stream_submit: null argument");
+    if (mode != VBOC_MODE_SQP && mode != VBOC_MODE_RTI) return fail(VBOC_ERR_ARG, "vboc_stream_submit: bad mode");
+    if (count < 1 || count > (int)s->free_slots.size())
+        return fail(VBOC_ERR_ARG, "vboc_stream_submit: count exceeds the free slots (vboc_stream_free_slots)");
+    if (!N || !x_guess || !u_guess || !lbx0 || !ubx0 || !lbx || !ubx || !lbxN || !ubxN || !lbu || !ubu)
+        return fail(VBOC_ERR_ARG, "vboc_stream_submit: null array");
+    if (s->family == VBOC_FAMILY_VBOC && !p) return fail(VBOC_ERR_ARG, "vboc_stream_submit: p required");
+    CUDA_OK(cudaSetDevice(s->device));
+    const int n = s->n, nxr = s->nxr, nu = s->nu, Nmax = s->Nmax;
+    // a free launch record (its previous kernel has finished)
+    int r = -1;
+    for (int spin = 0; r < 0; ++spin) {
+        for (int i = 0; i < vboc_stream::NREC && r < 0; ++i) {
+            if (s->rec[i].busy && cudaEventQuery(s->rec[i].ev) == cudaSuccess) s->rec[i].busy = false;
+            if (!s->rec[i].busy) r = i;
+        }
+        cudaGetLastError();  // cudaErrorNotReady of the queries is not an error
+    }
+    // validate everything before touching a slot
+    std::vector<double> h(count), dir((size_t)count * n);
+    for (int b = 0; b < count; ++b) {
+        bool pinned = true;
+        int rc = prepare_problem(n, nxr, Nmax, s->family, N[b], lbx0 + (size_t)b * nxr, ubx0 + (size_t)b * nxr,
+                                 lbx + (size_t)b * nxr, ubx + (size_t)b * nxr, lbxN + (size_t)b * nxr,
+                                 ubxN + (size_t)b * nxr, x_guess + (size_t)b * (Nmax + 1) * nxr,
+                                 C0 ? C0 + (size_t)b * n * nxr : nullptr, Tf, &h[b], &dir[(size_t)b * n], &pinned);
+        if (rc) return rc;
+        if (!pinned)
+            return fail(VBOC_ERR_UNSUPPORTED, "vboc_stream_submit: a free dt state is served by vboc_solve_batch only");
+        if (!C0) dir[(size_t)b * n] = NAN;  // no direction constraint for this problem
+    }
+    vboc_stream::Rec &R = s->rec[r];
+    for (int b = 0; b < count; ++b) {
+        const int t = s->free_slots.back();
+        s->free_slots.pop_back();
+        tickets[b] = t, R.index[b] = t;
+        s->N[t] = N[b], s->h[t] = h[b], s->done[t] = 0;
+        const size_t xs = (size_t)(Nmax + 1) * nxr, us = (size_t)Nmax * nu;
+        memcpy(s->xg + t * xs, x_guess + b * xs, (size_t)(N[b] + 1) * nxr * sizeof(double));
+        memcpy(s->ug + t * us, u_guess + b * us, (size_t)N[b] * nu * sizeof(double));
+        if (p) memcpy(s->p + (size_t)t * (n + 1), p + (size_t)b * (n + 1), (n + 1) * sizeof(double));
+#define ROW(dst, src, w) memcpy(s->dst + (size_t)t * (w), src + (size_t)b * (w), (w) * sizeof(double))
+        ROW(lbx0, lbx0, nxr), ROW(ubx0, ubx0, nxr), ROW(lbx, lbx, nxr), ROW(ubx, ubx, nxr);
+        ROW(lbxN, lbxN, nxr), ROW(ubxN, ubxN, nxr), ROW(lbu, lbu, nu), ROW(ubu, ubu, nu);
+#undef ROW
+        memcpy(s->dir + (size_t)t * n, &dir[(size_t)b * n], n * sizeof(double));
+        s->inflight.push_back(t);
+    }
+    Batch B;
+    B.batch = count, B.Nmax = Nmax, B.nxr = nxr;
+    B.N = s->N, B.xg = s->xg, B.ug = s->ug, B.p = p ? s->p : nullptr;
+    B.lbx0 = s->lbx0, B.ubx0 = s->ubx0, B.lbx = s->lbx, B.ubx = s->ubx, B.lbxN = s->lbxN, B.ubxN = s->ubxN;
+    B.lbu = s->lbu, B.ubu = s->ubu, B.dir = s->dir, B.h = s->h, B.x = s->x, B.u = s->u, B.st = s->st;
+    B.work = s->dwork, B.work_doubles = s->work_doubles, B.counter = s->dcounters + r;
+    B.mode = mode, B.opts = s->opts;
+    B.index = R.index, B.done = s->done, B.ws_mask = s->ws_mask, B.ws_per_sm = s->ws_per_sm;
+    CUDA_OK(cudaMemsetAsync(s->dcounters + r, 0, sizeof(unsigned int), R.stream));
+    int grid = (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA, maxg = s->num_sms * 5;
+    if (grid > maxg) grid = maxg;
+    cudaError_t e = cudaErrorInvalidValue;
+#define GO(NQ, FAM) \
+    if (n == NQ && s->family == FAM) e = launch_stream<NQ, FAM>(grid, R.stream, B);
+    GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
+#undef GO
+    if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("solve_kernel (stream) launch: ") + cudaGetErrorString(e));
+    CUDA_OK(cudaEventRecord(R.ev, R.stream));
+    R.busy = true;
+    ++s->launches;
+    return 0;
+}
+
+int vboc_stream_poll(vboc_stream *s, int max, int *tickets) {
+    if (!s || !tickets || max < 0) return fail(VBOC_ERR_ARG, "vboc_stream_poll: bad argument");
+    int nout = 0;
+    size_t keep = 0;
+    for (size_t i = 0; i < s->inflight.size(); ++i) {
+        const int t = s->inflight[i];
+        if (nout < max && __atomic_load_n(&s->done[t], __ATOMIC_ACQUIRE) == 1) {
+            s->done[t] = 2;  // finished, waiting for vboc_stream_fetch
+            tickets[nout++] = t;
+        } else {
+            s->inflight[keep++] = t;
+        }
+    }
+    s->inflight.resize(keep);
+    if (nout == 0 && keep) {
+        // surface a failed launch / a faulted kernel instead of polling forever
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("vboc_stream_poll: ") + cudaGetErrorString(e));
+        for (int i = 0; i < vboc_stream::NREC; ++i)
+            if (s->rec[i].busy) {
+                e = cudaEventQuery(s->rec[i].ev);
+                if (e == cudaSuccess) s->rec[i].busy = false;
+                else if (e != cudaErrorNotReady)
+                    return fail(VBOC_ERR_CUDA, std::string("vboc_stream_poll: ") + cudaGetErrorString(e));
+            }
+        cudaGetLastError();
+    }
+    return nout;
+}
+
+int vboc_stream_fetch(vboc_stream *s, int ticket, double *x, double *u, vboc_stats *stats) {
+    if (!s || ticket < 0 || ticket >= s->cap || s->done[ticket] != 2)
+        return fail(VBOC_ERR_ARG, "vboc_stream_fetch: not a finished ticket");
+    const int t = ticket, Nb = s->N[t];
+    if (x) memcpy(x, s->x + (size_t)t * (s->Nmax + 1) * s->nxr, (size_t)(Nb + 1) * s->nxr * sizeof(double));
+    if (u) memcpy(u, s->u + (size_t)t * s->Nmax * s->nu, (size_t)Nb * s->nu * sizeof(double));
+    if (stats) *stats = s->st[t];
+    s->done[t] = 0;
+    s->free_slots.push_back(t);
+    ++s->solved;
+    return 0;
+}
+
+int vboc_stream_sim_step(vboc_stream *s, int count, const double *x, const double *u, double T, double *x_next) {
+    if (!s || count < 1 || count > s->sim_cap || !x || !u || !x_next)
+        return fail(VBOC_ERR_ARG, "vboc_stream_sim_step: bad argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    const int n = s->n;
+    memcpy(s->sx, x, (size_t)count * 2 * n * sizeof(double));
+    memcpy(s->su, u, (size_t)count * n * sizeof(double));
+    // 32-thread CTAs: they fit beside the resident solve CTAs (registers), so a step never waits for a solve
+    const int th = 32, bl = (count + th - 1) / th;
+    if (n == 1) sim_kernel<1><<<bl, th, 0, s->sim_stream>>>(count, s->sx, s->su, T, s->sxn);
+    if (n == 2) sim_kernel<2><<<bl, th, 0, s->sim_stream>>>(count, s->sx, s->su, T, s->sxn);
+    if (n == 3) sim_kernel<3><<<bl, th, 0, s->sim_stream>>>(count, s->sx, s->su, T, s->sxn);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s->sim_stream));
+    memcpy(x_next, s->sxn, (size_t)count * 2 * n * sizeof(double));
     return 0;
 }
 

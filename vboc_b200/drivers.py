@@ -120,6 +120,76 @@ def run_workers(n, workers, solver, sim_step, stats=None):
     return results
 
 
+def run_workers_stream(n, workers, ssol, stats=None, max_launch=1024, idle_sleep=5e-5):
+    """`run_workers` over a `engine.StreamSolver`: an event loop instead of rounds.  A worker's next solve is
+    submitted as soon as the worker has it ready and the worker is resumed as soon as ITS solve is back
+    (tickets); RK4 requests of all workers that are ready at the same time go out as one batched call.
+    Same workers, same answers as `run_workers` -- only the waiting changes."""
+    import time
+    results = [None] * len(workers)
+    ready = []   # (worker id, request) not yet served
+    owner = {}   # ticket -> (worker id, N)
+    live = 0
+
+    t_start = time.perf_counter()
+    t_done = np.zeros(len(workers))
+    t_solve = []
+
+    def advance(i, ans, first=False):
+        nonlocal live
+        try:
+            ready.append((i, next(workers[i]) if first else workers[i].send(ans)))
+        except StopIteration as e:
+            results[i] = e.value
+            t_done[i] = time.perf_counter() - t_start
+            live -= 1
+
+    live = len(workers)
+    for i in range(len(workers)):
+        advance(i, None, first=True)
+    nsolve = nconv = nsim = loops = 0
+    while live:
+        loops += 1
+        sims = [(i, r) for i, r in ready if isinstance(r, SimReq)]
+        sols = [(i, r) for i, r in ready if isinstance(r, SolveReq)]
+        ready.clear()
+        # solves first: they run while the host serves the RK4 steps
+        if sols:
+            k = min(len(sols), ssol.free_slots, max_launch)
+            if k:
+                tk = ssol.submit(_pack(n, [r for _, r in sols[:k]]), MODE_SQP)
+                for t, (i, r) in zip(tk.tolist(), sols[:k]):
+                    owner[t] = (i, r.N)
+            ready.extend(sols[k:])  # no free slot yet: next turn
+        if sims:
+            T = sims[0][1].T
+            Xn = ssol.sim_step(np.stack([r.x for _, r in sims]), np.stack([r.u for _, r in sims]), T)
+            nsim += len(sims)
+            for b, (i, _) in enumerate(sims):
+                advance(i, Xn[b])
+        done = ssol.poll()
+        for t in done:
+            i, N = owner.pop(t)
+            out = ssol.fetch(t)
+            nsolve += 1
+            nconv += out["status"] == 0
+            t_solve.append(time.perf_counter() - t_start)
+            advance(i, SolveAns(int(out["status"]), float(out["cost"]), out["x"], out["u"]))
+        if not done and not sims and not (sols and ssol.free_slots):
+            time.sleep(idle_sleep)
+    if stats is not None:
+        stats["solves"] = stats.get("solves", 0) + nsolve
+        stats["converged"] = stats.get("converged", 0) + int(nconv)
+        stats["sim_steps"] = nsim
+        stats["loops"] = loops
+        # when the workers finished: the last percent is a few problems whose solves hit the iteration limit
+        if t_solve:  # throughput while the GPU is still full: until 90 % of the solves are back
+            t90 = float(np.percentile(t_solve, 90))
+            stats["solves_per_s_first_90pct"] = round(0.9 * len(t_solve) / max(t90, 1e-9), 1)
+        stats["t_done_p50_p90_p99_max"] = [round(float(v), 2) for v in np.percentile(t_done, [50, 90, 99, 100])]
+    return results
+
+
 # ------------------------------------------------------------------------------------------------
 def _limits(n, mdl, dt_sym):
     q_min, q_max, v_max, tau = mdl.thetamin, mdl.thetamax, mdl.dthetamax, mdl.umax
@@ -397,6 +467,35 @@ def data_generation_batch(n, num_prob, seed, device=0, backend=None, stats=None)
     (VBOC/triplependulum_vboc.py:399-405) -> X_save (rows [q, v])."""
     solver, sim = backend or _gpu_backend(n, num_prob, device)
     res = run_workers(n, [data_generation_worker(n, _rng(seed, i)) for i in range(num_prob)], solver, sim, stats)
+    rows = [np.asarray(r) for r in res if r is not None and len(r)]
+    if stats is not None:
+        stats["problems"] = num_prob
+        stats["problems_ok"] = len(rows)
+    return np.concatenate(rows).reshape(-1, 2 * n) if rows else np.empty((0, 2 * n))
+
+
+def _stream_backend(n, capacity, device):
+    from . import engine
+    return engine.StreamSolver(n, "vboc", capacity, N_CAP, device=device)
+
+
+def testing_stream(n, num_prob, seed, device=0, ssol=None, stats=None):
+    """`testing_batch` through the streaming engine (no round barrier)."""
+    own = ssol is None
+    ssol = ssol or _stream_backend(n, num_prob, device)
+    res = run_workers_stream(n, [testing_worker(n, _rng(seed, i)) for i in range(num_prob)], ssol, stats)
+    if own:
+        ssol.close()
+    return np.array([r for r in res if r is not None]).reshape(-1, 2 * n)
+
+
+def data_generation_stream(n, num_prob, seed, device=0, ssol=None, stats=None):
+    """`data_generation_batch` through the streaming engine (no round barrier): same workers, same rows."""
+    own = ssol is None
+    ssol = ssol or _stream_backend(n, num_prob, device)
+    res = run_workers_stream(n, [data_generation_worker(n, _rng(seed, i)) for i in range(num_prob)], ssol, stats)
+    if own:
+        ssol.close()
     rows = [np.asarray(r) for r in res if r is not None and len(r)]
     if stats is not None:
         stats["problems"] = num_prob

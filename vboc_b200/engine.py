@@ -128,6 +128,97 @@ class BatchSolver:
         return _lib.lib().vboc_last_kernel_ms(self._h)
 
 
+class StreamSolver:
+    """Ticket queue over the same kernels (`vboc_stream_*`): `submit` launches and returns at once, `poll`
+    returns the tickets whose solve has finished, `fetch` hands out one result and frees its slot.  This is
+    what serves the drivers' per-problem loops (`drivers.run_workers_stream`): every worker resubmits as soon
+    as ITS solve is back, instead of every round waiting for the slowest solve of the round."""
+
+    def __init__(self, n, family, capacity, N_max, device=0, opts=None):
+        self.n, self.family = int(n), _FAM.get(family, family)
+        self.cap, self.N_max, self.device = int(capacity), int(N_max), int(device)
+        self.nx = 2 * self.n + (self.family == FAMILY_VBOC)
+        self.nu = self.n
+        self._h = C.c_void_p()
+        check(_lib.lib().vboc_stream_create(self.n, self.family, self.cap, self.N_max, self.device, C.byref(self._h)))
+        self.opts = opts or default_opts(self.family)
+        check(_lib.lib().vboc_stream_set_opts(self._h, C.byref(self.opts)))
+        self._tick = np.empty(self.cap, dtype=np.int32)
+        self._N = {}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().vboc_stream_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def set_opts(self, opts):
+        self.opts = opts
+        check(_lib.lib().vboc_stream_set_opts(self._h, C.byref(opts)))
+
+    @property
+    def free_slots(self):
+        return _lib.lib().vboc_stream_free_slots(self._h)
+
+    @property
+    def pending(self):
+        return _lib.lib().vboc_stream_pending(self._h)
+
+    def submit(self, bp, mode=MODE_SQP):
+        """bp as for `BatchSolver.solve` (x_guess / u_guess with N_max + 1 / N_max rows); returns the tickets."""
+        Nv = np.ascontiguousarray(bp["N"], dtype=np.int32)
+        B = Nv.shape[0]
+        xg, ug = _c(bp["x_guess"]), _c(bp["u_guess"])
+        assert xg.shape == (B, self.N_max + 1, self.nx) and ug.shape == (B, self.N_max, self.nu)
+        arrs = [xg, ug] + [_c(bp.get(k)) for k in
+                           ("p", "lbx0", "ubx0", "lbx", "ubx", "lbxN", "ubxN", "lbu", "ubu", "C0")]
+        tk = np.empty(B, dtype=np.int32)
+        check(_lib.lib().vboc_stream_submit(self._h, int(mode), B, Nv.ctypes.data_as(C.POINTER(C.c_int)),
+                                            *[_dp(a) for a in arrs], float(bp.get("Tf", 1.0)),
+                                            tk.ctypes.data_as(C.POINTER(C.c_int))))
+        for t, Nb in zip(tk.tolist(), Nv.tolist()):
+            self._N[t] = Nb
+        return tk
+
+    def poll(self):
+        k = _lib.lib().vboc_stream_poll(self._h, self.cap, self._tick.ctypes.data_as(C.POINTER(C.c_int)))
+        if k < 0:
+            check(k)
+        return self._tick[:k].tolist()
+
+    def fetch(self, ticket):
+        """Result of a finished ticket: dict(status, cost, x (N+1, nx), u (N, nu), sqp_iter, qp_iter, ...)."""
+        Nb = self._N.pop(int(ticket))
+        x = np.empty((Nb + 1, self.nx))
+        u = np.empty((Nb, self.nu))
+        st = np.empty(1, dtype=_STATS_DTYPE)
+        check(_lib.lib().vboc_stream_fetch(self._h, int(ticket), _dp(x), _dp(u), st.ctypes.data_as(C.POINTER(Stats))))
+        out = dict(x=x, u=u)
+        for f in _STAT_FIELDS:
+            out[f] = st[f][0].item()
+        return out
+
+    def sim_step(self, x, u, T):
+        x, u = _c(np.atleast_2d(x)), _c(np.atleast_2d(u))
+        xn = np.empty_like(x)
+        check(_lib.lib().vboc_stream_sim_step(self._h, x.shape[0], _dp(x), _dp(u), float(T), _dp(xn)))
+        return xn
+
+    def solve(self, bp, mode=MODE_SQP):
+        """Convenience (tests): submit a batch and wait for all of it; results in submission order."""
+        import time
+        tk = self.submit(bp, mode).tolist()
+        got = {}
+        while len(got) < len(tk):
+            done = self.poll()
+            for t in done:
+                got[t] = self.fetch(t)
+            if not done:
+                time.sleep(1e-4)
+        return [got[t] for t in tk]
+
+
 def sim_step(n, x, u, T, device=0):
     """Batched RK4 step of the unscaled model (the reference's `sim.acados_integrator`)."""
     x, u = _c(np.atleast_2d(x)), _c(np.atleast_2d(u))

@@ -16,6 +16,12 @@ of the boundary states afterwards, as the drivers do before the NN fit).
 `roofline`: FP64.  achieved = algorithmic flops of the launch (per stage 7348 / 3395 /
            856 flops per linearisation / IPM iteration / merit evaluation, times the per-problem
            counters the kernel exports) / kernel time; peak = DFMA peak measured live on the device.
+           `traffic` = DRAM bytes per launch: the ncu-measured bytes per IPM iteration of this kernel
+           (profiles/r1_traffic.json, one `ncu --set full` capture) times the IPM iterations of the launch;
+           `hbm` restates the same launch against the measured copy bandwidth (MEASURED_PEAKS.json).
+`pipeline`: (N = 1) the full `data_generation` of `--pipeline` problems -- extension loop, retries, sub-OCP
+           chains, twin simulation (VBOC/triplependulum_vboc.py:19-370) -- through the streaming engine
+           (`vboc_stream_*`): SURVEY 8(d)(ii).
 `cpu_baseline`: the oracle port (kind "port": acados is not installable here) on the host cores, on a
            bounded sample of the same workload.
 """
@@ -129,6 +135,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32768, help="problems per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="problems of the CPU baseline sample")
+    ap.add_argument("--pipeline", type=int, default=1024,
+                    help="problems of the data_generation pipeline leg (N = 1 only; 0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -234,10 +242,45 @@ def main():
         conv, conv_e, flops_all = tot.tolist()
     else:
         flops_all = flops
+    for sv in sols:  # free the batch workspaces before the pipeline leg
+        sv.close()
+    pipeline = None
+    if world == 1 and args.pipeline > 0:
+        from vboc_b200 import drivers
+        pst = {}
+        tp0 = time.perf_counter()
+        rows = drivers.data_generation_stream(N_DOF, args.pipeline, seed=77, device=local, stats=pst)
+        tp = time.perf_counter() - tp0
+        pipeline = {"workload": "triplependulum_vboc data_generation (extensions, retries, sub-OCP chains, twin simulation) "
+                                "through the streaming engine",
+                    "problems": args.pipeline, "rows": int(rows.shape[0]), "solves": pst.get("solves", 0),
+                    "converged": pst.get("converged", 0), "sim_steps": pst.get("sim_steps", 0), "wall_s": tp,
+                    "converged_solves_per_s": pst.get("converged", 0) / tp,
+                    "solves_per_s_first_90pct": pst.get("solves_per_s_first_90pct"),
+                    "t_done_p50_p90_p99_max_s": pst.get("t_done_p50_p90_p99_max")}
     if rank == 0:
         cores = os.cpu_count() or 1
         c_conv, c_dt = cpu_sample(args.cpu_sample, 4242, cores) if world == 1 else (0, 1.0)
         achieved_tf = flops / t_dev_local / 1e12  # rank 0's launches
+        traffic = hbm = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            ipm_iters = float(sum(int(o["qp_iter"].sum()) for o in outs))
+            total_bytes = tj["dram_bytes_per_ipm_iteration"] * ipm_iters
+            traffic = total_bytes / args.steps
+            peak_gbs = None
+            try:
+                peak_gbs = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            except Exception:
+                pass
+            ach = total_bytes / t_dev_local / 1e9
+            hbm = {"achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs if peak_gbs else None,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)" if peak_gbs else "unavailable",
+                   "bytes_per_ipm_iteration": tj["dram_bytes_per_ipm_iteration"],
+                   "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one bounded launch "
+                             "(profiles/r1_traffic.json) scaled by this launch's IPM iterations"}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": conv / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
@@ -250,17 +293,17 @@ def main():
             "e2e": {"value": conv_e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "peak_source": "DFMA micro-benchmark run live by bench.py (MEASURED_PEAKS.json has no FP64 entry)",
-                         "flops_per_launch": flops / args.steps},
+                         "flops_per_launch": flops / args.steps, "hbm": hbm},
             "clocks": clocks,
         }
+        if pipeline is not None:
+            line["pipeline"] = pipeline
         if world == 1:
             line["cpu_baseline"] = {"value": c_conv / c_dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} problems of the same sampler, oracle port, OpenMP over problems"}
         print(json.dumps(line))
-    for sv in sols:
-        sv.close()
     if world > 1:
         dist.destroy_process_group()
 

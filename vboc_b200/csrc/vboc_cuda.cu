@@ -236,8 +236,17 @@ struct vboc_solver {
     size_t stage_bytes;
 };
 
+// VB_TUNE_BUILD: kernel-tuning builds (tools/build_variant.sh) compile only the benchmark's instantiation
+// (3-DOF VBOC, 5 CTAs / SM) -- seconds instead of minutes; everything else is refused at run time.
+#ifdef VB_TUNE_BUILD
+#define VB_ALL_SYSTEMS(GO) GO(3, 0)
+#else
+#define VB_ALL_SYSTEMS(GO) GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
+#endif
+
 template <int NQ, int FAM>
 static cudaError_t launch(vboc_solver *s, const Batch &B) {
+#ifndef VB_TUNE_BUILD
     if (s->lane_kernel) {
         const int smem = LaneSolver<NQ, FAM, 32, 0>::SM_TOTAL * LANE_THREADS * (int)sizeof(double);
         cudaFuncSetAttribute(solve_lane_kernel<NQ, FAM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -246,10 +255,11 @@ static cudaError_t launch(vboc_solver *s, const Batch &B) {
     }
     if (s->ctas_per_sm >= 6)
         solve_kernel<NQ, FAM, 6><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
-    else if (s->ctas_per_sm == 5)
-        solve_kernel<NQ, FAM, 5><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
-    else
+    else if (s->ctas_per_sm == 4)
         solve_kernel<NQ, FAM, 4><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+    else
+#endif
+        solve_kernel<NQ, FAM, 5><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
     return cudaGetLastError();
 }
 
@@ -595,14 +605,16 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
     CUDA_OK(cudaEventRecord(s->ev0, s->stream));
     cudaError_t e = cudaErrorInvalidValue;
     if (s->free_dt) {
+#ifndef VB_TUNE_BUILD
         B.work = s->dwork_free_dt;
         const int smem = LaneSolver<1, VBOC_FAMILY_VBOC, 32, 1>::SM_TOTAL * LANE_THREADS * (int)sizeof(double);
         solve_lane_kernel<1, VBOC_FAMILY_VBOC, 1><<<s->grid_free_dt, LANE_THREADS, smem, s->stream>>>(B, B.work);
         e = cudaGetLastError();
+#endif
     } else {
 #define GO(NQ, FAM) \
     if (s->n == NQ && s->family == FAM) e = launch<NQ, FAM>(s, B);
-        GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
+        VB_ALL_SYSTEMS(GO)
 #undef GO
     }
     if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("solve_kernel launch: ") + cudaGetErrorString(e));
@@ -967,7 +979,7 @@ int vboc_stream_submit(vboc_stream *s, int mode, int count, const int *N, const 
     cudaError_t e = cudaErrorInvalidValue;
 #define GO(NQ, FAM) \
     if (n == NQ && s->family == FAM) e = launch_stream<NQ, FAM>(grid, R.stream, B);
-    GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
+    VB_ALL_SYSTEMS(GO)
 #undef GO
     if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("solve_kernel (stream) launch: ") + cudaGetErrorString(e));
     CUDA_OK(cudaEventRecord(R.ev, R.stream));

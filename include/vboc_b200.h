@@ -178,6 +178,8 @@ int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu,
 void vboc_mlp_destroy(vboc_mlp *m);
 int vboc_mlp_forward(vboc_mlp *m, int batch, const float *x, int mode, double mean, double stdv,
                      double safety_margin, float *out, float *aux, int *label);
+/* Device time of the last vboc_mlp_forward kernel in milliseconds (CUDA events around the launch). */
+double vboc_mlp_last_kernel_ms(vboc_mlp *m);
 
 /* Measured FP64 FMA peak of the device in TFLOP/s (dependent-free DFMA chains on every SM): the
  * roofline denominator bench.py reports against (MEASURED_PEAKS.json has no FP64 entry). */

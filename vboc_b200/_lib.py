@@ -21,7 +21,7 @@ EXPORTS = (
     "vboc_download", "vboc_last_kernel_ms",
     "vboc_stream_create", "vboc_stream_destroy", "vboc_stream_set_opts", "vboc_stream_free_slots",
     "vboc_stream_pending", "vboc_stream_submit", "vboc_stream_poll", "vboc_stream_fetch", "vboc_stream_sim_step",
-    "vboc_sim_step", "vboc_mlp_create", "vboc_mlp_destroy", "vboc_mlp_forward", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
+    "vboc_sim_step", "vboc_mlp_create", "vboc_mlp_destroy", "vboc_mlp_forward", "vboc_mlp_last_kernel_ms", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
 )
 
 
@@ -97,6 +97,8 @@ def lib():
         L.vboc_mlp_destroy.argtypes = [vp]
         L.vboc_mlp_destroy.restype = None
         L.vboc_mlp_forward.argtypes = [vp, C.c_int, fp, C.c_int, C.c_double, C.c_double, C.c_double, fp, fp, ip]
+        L.vboc_mlp_last_kernel_ms.argtypes = [vp]
+        L.vboc_mlp_last_kernel_ms.restype = C.c_double
         L.vboc_fp64_peak.argtypes = [C.c_int, dp]
         L.vboc_last_error.restype = C.c_char_p
         L.vboc_version.restype = C.c_char_p

@@ -93,6 +93,18 @@ VB_HD double dotv(const double *a, const double *b, double init = 0.0) {
     return a0 + a1;
 #endif
 }
+#ifndef VB_CON_ROLLED
+#define VB_CON_ROLLED 1  // the two sides of a bound as a rolled loop: half the body, +3 % (instruction fetch bound)
+#endif
+#ifndef VB_PF_RES
+#define VB_PF_RES 0  // measured: the residual pass is no faster with it, the constraint and update passes are
+#endif
+#ifndef VB_PF_CON
+#define VB_PF_CON 1
+#endif
+#ifndef VB_PF_UPD
+#define VB_PF_UPD 1
+#endif
 #ifndef VB_PF_DIST
 #define VB_PF_DIST 64  // software prefetch distance of the flat passes: two lane-strided iterations ahead
 #endif
@@ -401,14 +413,16 @@ struct WarpSolver {
         END_LANES
         proj0(s.va);
         eq0_violation(s.vb, s.vc);
+        FOR_LANES
+        if (lane < NX) {
+            const double va = s.va[lane];
+            L(bad) |= (va != va);
+            L(a_s) = fmax(L(a_s), fabs(va));
+            L(a_i) = fmax(L(a_i), fabs(s.vc[lane]));
+        }
+        END_LANES
         rs = WARP_MAX(a_s), re = WARP_MAX(a_e), ri = WARP_MAX(a_i), rc = WARP_MAX(a_c);
         bool nan = WARP_ANY(bad);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-            nan |= (s.va[i] != s.va[i]);
-            rs = fmax(rs, fabs(s.va[i]));
-            ri = fmax(ri, fabs(s.vc[i]));
-        }
         UNIFORM_SYNC();
         return !nan;
     }
@@ -475,7 +489,7 @@ struct WarpSolver {
             int k = idx / NZ, i = idx - k * NZ;
             {
                 const int nidx = idx + VB_PF_DIST, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
-                if (nidx < (N + 1) * NZ) {
+                if (VB_PF_RES && nidx < (N + 1) * NZ) {
                     VB_PREFETCH(w.DZ + nidx), VB_PREFETCH(w.Z + nidx);
                     VB_PREFETCH(rec(nk) + R::BAT + (nidx - nk * NZ) * NX), VB_PREFETCH(w.PIQ + nk * NX);
                     VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
@@ -505,7 +519,7 @@ struct WarpSolver {
                 vd = fmax(vd, fmax(fabs(dl), fabs(du)));
                 vm = fmax(vm, fmax(fabs(ml), fabs(mu_)));
                 mu += ml + mu_;
-                double itl = 1.0 / tl, itu = 1.0 / tu;
+                double itl = VB_RCP(tl), itu = VB_RCP(tu);
                 hh += ll * itl + lu * itu;
                 bar = (ml - ll * dl) * itl - (mu_ - lu * du) * itu;
             } else {
@@ -543,15 +557,18 @@ struct WarpSolver {
         END_LANES
         proj0(s.va);
         eq0_violation(s.vb, s.e0);
+        // the stage-0 pieces join the lane-wise maxima before the reductions (a max is order independent)
+        FOR_LANES
+        if (lane < NX) {
+            const double va = s.va[lane];
+            L(bad) |= (va != va);
+            L(a_g) = fmax(L(a_g), fabs(va));
+            L(a_b) = fmax(L(a_b), fmax(fabs(s.e0[lane]), fabs(s.eN[lane])));
+        }
+        END_LANES
         ng = WARP_MAX(a_g), nb_ = WARP_MAX(a_b), nd = WARP_MAX(a_d), nm = WARP_MAX(a_m);
         double mu = WARP_SUM(a_mu);
         nan = WARP_ANY(bad);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-            nan |= (s.va[i] != s.va[i]);
-            ng = fmax(ng, fabs(s.va[i]));
-            nb_ = fmax(nb_, fmax(fabs(s.e0[i]), fabs(s.eN[i])));
-        }
         FOR_LANES
         if (lane < NX) {
             double rv = s.va[lane], rraw = w.RG[NU + lane];
@@ -1031,7 +1048,7 @@ struct WarpSolver {
             double q1 = 0.0, q2 = 0.0;
             {
                 const int nidx = idx + VB_PF_DIST, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
-                if (nidx < (N + 1) * NZ) {
+                if (VB_PF_CON && nidx < (N + 1) * NZ) {
                     VB_PREFETCH(w.DV + nidx);
                     VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
                     VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.TQ + nc + NZ);
@@ -1043,18 +1060,22 @@ struct WarpSolver {
             }
             if (active(k, i)) {
                 double dvv = w.DV[idx];
+#if VB_CON_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
                 for (int sd = 0; sd < 2; ++sd) {
                     int c = k * NC + sd * NZ + i;
                     double lam = w.LAMQ[c], t = w.TQ[c], rm = w.RMB[c];
                     if (mode == 1) rm += w.RM[c] - sm;
                     if (mode == 2) rm -= sm;
                     double dtt = (sd ? -dvv : dvv) - w.RD[c];
-                    double it = 1.0 / t;
+                    double it = VB_RCP(t);
                     double dl = -(rm + lam * dtt) * it;
                     // ratio test; the division only when this constraint tightens the step
-                    if (dtt < 0.0 && t + al * dtt < 0.0) al = fmin(al, -t / dtt);
-                    if (dl < 0.0 && lam + al * dl < 0.0) al = fmin(al, -lam / dl);
+                    if (dtt < 0.0 && t + al * dtt < 0.0) al = fmin(al, VB_RATIO(t, -dtt));
+                    if (dl < 0.0 && lam + al * dl < 0.0) al = fmin(al, VB_RATIO(lam, -dl));
                     s0 += lam * t, s1 += lam * dtt + t * dl, s2 += dtt * dl;
                     if (mode == 0) {
                         double pr = dtt * dl;
@@ -1119,13 +1140,13 @@ struct WarpSolver {
             // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
             FOR_LANES
             for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
-                if (idx + VB_PF_DIST < (N + 1) * NZ) VB_PREFETCH(w.DZ + idx + VB_PF_DIST), VB_PREFETCH(w.DV + idx + VB_PF_DIST);
+                if (VB_PF_UPD && idx + VB_PF_DIST < (N + 1) * NZ) VB_PREFETCH(w.DZ + idx + VB_PF_DIST), VB_PREFETCH(w.DV + idx + VB_PF_DIST);
                 w.DZ[idx] += as * w.DV[idx];
             }
             for (int idx = lane; idx < N * NX; idx += 32) {
                 int k = idx / NX, mI = idx - k * NX;
                 const double *dxn = w.DV + (size_t)(k + 1) * NZ + NU;
-                if (idx + VB_PF_DIST < N * NX) {
+                if (VB_PF_UPD && idx + VB_PF_DIST < N * NX) {
                     const int nk = (idx + VB_PF_DIST) / NX, nm = idx + VB_PF_DIST - nk * NX;
                     VB_PREFETCH(w.PP + (size_t)(nk + 1) * Work<NQ>::PPS + nm * NX);
                     VB_PREFETCH(w.PP + (size_t)(nk + 1) * Work<NQ>::PPS + NX * NX + nm);
@@ -1146,7 +1167,7 @@ struct WarpSolver {
             }
             for (int idx = lane; idx < (N + 1) * NC; idx += 32) {
                 int k = idx / NC, c = idx - k * NC, i = c >= NZ ? c - NZ : c;
-                if (idx + VB_PF_DIST < (N + 1) * NC) {
+                if (VB_PF_UPD && idx + VB_PF_DIST < (N + 1) * NC) {
                     VB_PREFETCH(w.LAMQ + idx + VB_PF_DIST), VB_PREFETCH(w.DLAM + idx + VB_PF_DIST);
                     VB_PREFETCH(w.TQ + idx + VB_PF_DIST), VB_PREFETCH(w.DT + idx + VB_PF_DIST);
                 }

@@ -36,7 +36,15 @@ int fail(int code, const std::string &msg) {
             return fail(VBOC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
     } while (0)
 
-constexpr int WARPS_PER_CTA = 4;
+#ifndef VB_WARPS_PER_CTA
+#define VB_WARPS_PER_CTA 4
+#endif
+constexpr int WARPS_PER_CTA = VB_WARPS_PER_CTA;  // tuning builds may change the CTA shape
+#ifdef VB_TUNE_MINB
+#define VB_LB_MINB(m) VB_TUNE_MINB
+#else
+#define VB_LB_MINB(m) m
+#endif
 
 // device-resident problem batch, reference-shaped
 struct Batch {
@@ -61,7 +69,7 @@ struct Batch {
 };
 
 template <int NQ, int FAM, int MINB, bool STREAM = false>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) solve_kernel(const Batch B) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, VB_LB_MINB(MINB)) solve_kernel(const Batch B) {
     __shared__ Smem<NQ> smem[WARPS_PER_CTA];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int slot = blockIdx.x * WARPS_PER_CTA + warp;
@@ -358,6 +366,9 @@ int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device
     // or 6 (80, spills); VBOC_CTAS_PER_SM overrides for tuning
     int ctas_per_sm = 5;
     if (const char *e = getenv("VBOC_CTAS_PER_SM")) ctas_per_sm = atoi(e) >= 6 ? 6 : (atoi(e) == 5 ? 5 : 4);
+#ifdef VB_TUNE_CTAS
+    ctas_per_sm = VB_TUNE_CTAS;
+#endif
     s->ctas_per_sm = ctas_per_sm;
     int max_grid = prop.multiProcessorCount * ctas_per_sm;
     int need = (batch_capacity + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -670,6 +681,7 @@ struct vboc_mlp {
     float *W1, *b1, *W2T, *b2, *W3, *b3;  // CUDA-core kernel (W2 transposed)
     int Hp;                               // hidden size padded to a multiple of 32 (tensor-core kernel)
     float *W1p, *b1p, *W2p, *b2p, *W3p;   // zero padded
+    double last_ms;                       // device time of the last forward kernel (CUDA events)
 };
 
 int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu, const float *W1,
@@ -744,6 +756,10 @@ int vboc_mlp_forward(vboc_mlp *m, int batch, const float *x, int mode, double me
     // tensor cores (tcgen05, 3xTF32) for hidden sizes the 512-column TMEM holds; VBOC_MLP_CUDA_CORES=1 selects
     // the plain FP32 kernel (kept as the cross-check of the tensor-core path)
     const char *force = getenv("VBOC_MLP_CUDA_CORES");
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0));
     if (m->Hp <= 512 && !(force && atoi(force))) {
         P.W1 = m->W1p, P.b1 = m->b1p, P.W2T = m->W2p, P.b2 = m->b2p, P.W3 = m->W3p;
         TcLayout lay(m->Hp);
@@ -759,13 +775,22 @@ int vboc_mlp_forward(vboc_mlp *m, int batch, const float *x, int mode, double me
         mlp_forward_kernel<<<grid, MLP_THREADS, smem>>>(P);
     }
     CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(e1));
     CUDA_OK(cudaDeviceSynchronize());
+    {
+        float ms = -1.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        m->last_ms = ms;
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+    }
     CUDA_OK(cudaMemcpy(out, dout, B * m->n_out * sizeof(float), cudaMemcpyDeviceToHost));
     if (aux) CUDA_OK(cudaMemcpy(aux, daux, B * sizeof(float), cudaMemcpyDeviceToHost));
     if (label) CUDA_OK(cudaMemcpy(label, dlab, B * sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(dx), cudaFree(dout), cudaFree(daux), cudaFree(dlab);
     return 0;
 }
+
+double vboc_mlp_last_kernel_ms(vboc_mlp *m) { return m ? m->last_ms : -1.0; }
 
 int vboc_fp64_peak(int device, double *tflops) {
     if (!tflops) return fail(VBOC_ERR_ARG, "vboc_fp64_peak: null argument");

@@ -53,6 +53,11 @@ class MLP:
                                           lab.ctypes.data_as(C.POINTER(C.c_int)) if want_label else None))
         return out, aux, lab
 
+    @property
+    def last_kernel_ms(self):
+        """Device time of the last forward kernel (CUDA events around the launch, no copies)."""
+        return _lib.lib().vboc_mlp_last_kernel_ms(self._h)
+
     def forward(self, X):
         """net(X) for already normalised inputs."""
         return self._run(X, 0)[0]

@@ -71,21 +71,22 @@ VB_HD void accel(const T *q, const T *v, const T *u, T *a) {
         a[0] = (1.0 / (Pend1::d * Pend1::d * Pend1::m)) * num;
     } else {
         constexpr double ll = PendN::l * PendN::l;
-        T M[NQ][NQ], r[NQ], v2[NQ];
+        T M[NQ][NQ], r[NQ], v2[NQ], sq[NQ], cq[NQ];
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
-            T si, ci;
-            sincos_t(q[i], si, ci);
+            sincos_t(q[i], sq[i], cq[i]);
             v2[i] = v[i] * v[i];
-            r[i] = u[i] - (PendN::m * (NQ - i) * PendN::g * PendN::l) * si;
+            r[i] = u[i] - (PendN::m * (NQ - i) * PendN::g * PendN::l) * sq[i];
             M[i][i] = constant<T>(PendN::m * (NQ - i) * ll);
         }
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
 #pragma unroll
             for (int j = i + 1; j < NQ; ++j) {
-                T s, c;
-                sincos_t(q[i] - q[j], s, c);
+                // sin / cos of the angle difference from the addition theorems: n sincos evaluations per
+                // model call instead of n (n + 1) / 2 (each is ~80 instructions of kernel code)
+                T s = sq[i] * cq[j] - cq[i] * sq[j];
+                T c = cq[i] * cq[j] + sq[i] * sq[j];
                 const double cf = PendN::m * (NQ - j) * ll;  // mu_ij = sum_{k >= j} m_k for j > i
                 M[i][j] = cf * c;
                 M[j][i] = M[i][j];

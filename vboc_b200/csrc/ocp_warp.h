@@ -53,6 +53,25 @@ struct Dim {
 template <int NQ>
 struct Rec {
     using D = Dim<NQ>;
+#if VB_REC_WINDOWS
+    // Field order: each sweep reads one contiguous window of the record, so its TMA copy moves only that window.
+    static constexpr int HH = 0;                       // effective Hessian diagonal  hd + lam/t (both sides)
+    static constexpr int RR = HH + D::NZ;              // predictor gradient
+    static constexpr int RB = RR + D::NZ;              // dynamics residual of the QP iterate (even offset)
+    static constexpr int BAT = RB + D::NX;             // [B A]' (nz x nx): column j of [B A] contiguous (even offset)
+    static constexpr int LUU = BAT + D::NZ * D::NX;    // nu x nu Cholesky factor, inverse diagonal
+    static constexpr int LXU = LUU + D::NU * D::NU;    // nx x nu
+    static constexpr int YV = LXU + D::NX * D::NU;     // Luu^-1 m_u
+    static constexpr int MB = YV + D::NU;              // [B A]' P+ beta (kept for the re-solves)
+    static constexpr int Q1 = MB + D::NZ;              // corrector gradient = Q1 - sigma*mu*Q2
+    static constexpr int Q2 = Q1 + D::NZ;
+    static constexpr int END = Q2 + D::NZ;
+    // windows (doubles, even bounds = 16-byte aligned): factorisation, forward sweep, re-solve
+    static constexpr int W_FAC0 = 0, W_FAC1 = LUU;
+    static constexpr int W_FWD0 = RB, W_FWD1 = MB;
+    static constexpr int W_SOL0 = RR & ~1, W_SOL1 = (END + 1) & ~1;
+    static_assert(RB % 2 == 0 && BAT % 2 == 0 && LUU % 2 == 0 && MB % 2 == 0, "16-byte aligned windows");
+#else
     static constexpr int BAT = 0;                      // [B A]' (nz x nx): column j of [B A] contiguous
     static constexpr int RB = BAT + D::NZ * D::NX;     // dynamics residual of the QP iterate
     static constexpr int HH = RB + D::NX;              // effective Hessian diagonal  hd + lam/t (both sides)
@@ -64,6 +83,8 @@ struct Rec {
     static constexpr int LXU = LUU + D::NU * D::NU;    // nx x nu
     static constexpr int YV = LXU + D::NX * D::NU;     // Luu^-1 m_u
     static constexpr int END = YV + D::NU;
+    static constexpr int W_FAC0 = 0, W_FAC1 = (END + 1) & ~1, W_FWD0 = 0, W_FWD1 = W_FAC1, W_SOL0 = 0, W_SOL1 = W_FAC1;
+#endif
     static constexpr int SIZE = (END + 1) & ~1;        // doubles; bytes are a multiple of 16
     static constexpr int BYTES = SIZE * 8;
 };
@@ -104,6 +125,15 @@ VB_HD double dotv(const double *a, const double *b, double init = 0.0) {
 #endif
 #ifndef VB_PF_UPD
 #define VB_PF_UPD 1
+#endif
+#ifndef VB_STORE_RMB
+#define VB_STORE_RMB 0  // lam*t of the constraint pass: recomputed (two loads and two stores fewer per element, +1.7 %)
+#endif
+#ifndef VB_REC_WINDOWS
+#define VB_REC_WINDOWS 1  // each sweep's TMA copy moves only the fields it reads (-12 % DRAM bytes, +2 %)
+#endif
+#ifndef VB_RG_ALL
+#define VB_RG_ALL 0  // the stationarity residual is stored for stage 0 only (the only one read back)
 #endif
 #ifndef VB_PF_DIST
 #define VB_PF_DIST 64  // software prefetch distance of the flat passes: two lane-strided iterations ahead
@@ -171,6 +201,7 @@ struct alignas(16) Smem {
     double c0[D::NX], cN[D::NX], w[NQ];
     double h, wtdt;
     int N, fixed0, fixedN, termfix, nact;
+    unsigned char tri[64];  // (row << 4 | column) of the entries of the lower triangle of M, row-major
     // Riccati staging
     alignas(16) double P[D::NX][D::NX];
     alignas(16) double PBAT[D::NZ][D::NX];
@@ -293,6 +324,12 @@ struct WarpSolver {
             s.nact = (N + 1) * NZ - NU - nf0 - nfN;
             for (int i = 0; i < NQ; ++i) s.w[i] = (FAM == VBOC_FAMILY_VBOC) ? pb.p[i] : 0.0;
         }
+        static_assert(TRI <= 64 && NZ <= 16, "triangle index table");
+        for (int idx = lane; idx < TRI; idx += 32) {
+            int a_ = 0;
+            while ((a_ + 1) * (a_ + 2) / 2 <= idx) ++a_;
+            s.tri[idx] = (unsigned char)((a_ << 4) | (idx - a_ * (a_ + 1) / 2));
+        }
         for (int idx = lane; idx < 3 * NZ; idx += 32) {
             int sc = idx / NZ, i = idx - sc * NZ;
             const double *l = sc == 0 ? pb.lbx0 : (sc == 1 ? pb.lbx : pb.lbxN);
@@ -305,7 +342,9 @@ struct WarpSolver {
             w.Z[idx] = i < NU ? (k < N ? pb.ug[k * NU + i] : 0.0) : pb.xg[(size_t)k * pb.nxr + i - NU];
         }
         // acados reset(): zero multipliers
+#pragma unroll 1
         for (int idx = lane; idx < N * NX; idx += 32) w.PI[idx] = 0.0;
+#pragma unroll 1
         for (int idx = lane; idx < (N + 1) * NC; idx += 32) w.LAM[idx] = 0.0;
         END_LANES
     }
@@ -395,12 +434,13 @@ struct WarpSolver {
                     vi = fmax(vi, fabs(z - s.cN[i - NU]));
                 }
             }
-            w.RG[idx] = r;  // scratch: the stage-0 state part is projected below
+            if (VB_RG_ALL || k == 0) w.RG[idx] = r;  // scratch: the stage-0 state part is projected below
             if (!(k == 0 && i >= NU)) {
                 nb |= (r != r);
                 vs = fmax(vs, fabs(r));
             }
         }
+#pragma unroll 1
         for (int idx = lane; idx < N * NX; idx += 32) {
             double v = w.BD[idx];
             nb |= (v != v);
@@ -459,6 +499,7 @@ struct WarpSolver {
             w.LAMQ[k * NC + i] = ll, w.LAMQ[k * NC + NZ + i] = lu;
             w.TQ[k * NC + i] = tl, w.TQ[k * NC + NZ + i] = tu;
         }
+#pragma unroll 1
         for (int idx = lane; idx < N * NX; idx += 32) w.PIQ[idx] = 0.0;
         END_LANES
         FOR_LANES
@@ -514,7 +555,8 @@ struct WarpSolver {
                 r += lu - ll;
                 double dl = (s.lb[sc][i] - z) - v + tl, du = v - (s.ub[sc][i] - z) + tu;
                 double ml = ll * tl, mu_ = lu * tu;
-                w.RD[c] = dl, w.RD[c + NZ] = du, w.RMB[c] = ml, w.RMB[c + NZ] = mu_;
+                w.RD[c] = dl, w.RD[c + NZ] = du;
+                if (VB_STORE_RMB) w.RMB[c] = ml, w.RMB[c + NZ] = mu_;
                 nb |= (dl != dl) | (du != du) | (ml != ml) | (mu_ != mu_);
                 vd = fmax(vd, fmax(fabs(dl), fabs(du)));
                 vm = fmax(vm, fmax(fabs(ml), fabs(mu_)));
@@ -523,10 +565,11 @@ struct WarpSolver {
                 hh += ll * itl + lu * itu;
                 bar = (ml - ll * dl) * itl - (mu_ - lu * du) * itu;
             } else {
-                w.RD[c] = 0.0, w.RD[c + NZ] = 0.0, w.RMB[c] = 0.0, w.RMB[c + NZ] = 0.0;
+                w.RD[c] = 0.0, w.RD[c + NZ] = 0.0;
+                if (VB_STORE_RMB) w.RMB[c] = 0.0, w.RMB[c + NZ] = 0.0;
                 if (k == N) r = 0.0;
             }
-            w.RG[idx] = r;
+            if (VB_RG_ALL || k == 0) w.RG[idx] = r;  // only the stage-0 state part is read back (projection)
             rk[R::HH + i] = hh;
             rk[R::RR + i] = r + bar;
             if (!(k == 0 && i >= NU)) {
@@ -610,11 +653,14 @@ struct WarpSolver {
             }
             END_LANES
         }
+        // only the window of the record this sweep reads travels through the ring
+        const int w0 = factor ? R::W_FAC0 : R::W_SOL0;
+        const unsigned wbytes = (factor ? R::W_FAC1 - R::W_FAC0 : R::W_SOL1 - R::W_SOL0) * 8u;
         for (int j = 0; j < RING_DEPTH && j < N; ++j)
-            RING_FETCH(ring, j, s.ring[j], rec(N - 1 - j), R::BYTES);
+            RING_FETCH(ring, j, s.ring[j] + w0, rec(N - 1 - j) + w0, wbytes);
         bool ok = true;
-        for (int it = 0; it < N; ++it) {
-            const int k = N - 1 - it, slot = it % RING_DEPTH;
+        for (int it = 0, slot = 0; it < N; ++it, slot = slot + 1 == RING_DEPTH ? 0 : slot + 1) {
+            const int k = N - 1 - it;
             const bool last = (it == 0) && s.termfix;
             RING_WAIT(ring, slot);
             const double *r = s.ring[slot];
@@ -635,9 +681,8 @@ struct WarpSolver {
             FOR_LANES
             if (factor) {
                 for (int idx = lane; idx < TRI; idx += 32) {
-                    // row of the idx-th entry of the row-major lower triangle: floor((sqrt(8 idx + 1) - 1) / 2),
-                    // exact in FP32 for idx < 2^20
-                    int a_ = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f), b_ = idx - a_ * (a_ + 1) / 2;
+                    // (row, column) of the idx-th entry of the row-major lower triangle, from the table
+                    const int ab = s.tri[idx], a_ = ab >> 4, b_ = ab & 15;
                     double a = dotv<NX>(r + R::BAT + a_ * NX, &s.PBAT[b_][0], (a_ == b_) ? r[R::HH + a_] : 0.0);
                     s.M[a_][b_] = a, s.M[b_][a_] = a;
                 }
@@ -691,8 +736,10 @@ struct WarpSolver {
                 }
                 FOR_LANES
                 if (factor) {
-                    for (int idx = lane; idx < NX * NX; idx += 32) {
-                        int i = idx / NX, j = idx - i * NX;
+                    // P is symmetric: the nx (nx + 1) / 2 entries of its lower triangle fit one round of lanes,
+                    // each entry is stored twice (the mirrored value is bit-identical: M is stored symmetric)
+                    for (int idx = lane; idx < NX * (NX + 1) / 2; idx += 32) {
+                        const int ab = s.tri[idx], i = ab >> 4, j = ab & 15;
                         double li[NU], lj[NU];
 #pragma unroll
                         for (int c = 0; c < NU; ++c) {
@@ -704,8 +751,8 @@ struct WarpSolver {
                         double a = s.M[NU + i][NU + j];
 #pragma unroll
                         for (int c = 0; c < NU; ++c) a -= li[c] * lj[c];
-                        s.P[i][j] = a;
-                        pp[idx] = a;
+                        s.P[i][j] = a, s.P[j][i] = a;
+                        pp[i * NX + j] = a, pp[j * NX + i] = a;
                         if (j == 0) {
 #pragma unroll
                             for (int c = 0; c < NU; ++c) gk[R::LXU + i * NU + c] = li[c];
@@ -837,7 +884,7 @@ struct WarpSolver {
                 }
                 END_LANES
             }
-            if (it + RING_DEPTH < N) RING_FETCH(ring, slot, s.ring[slot], rec(k - RING_DEPTH), R::BYTES);
+            if (it + RING_DEPTH < N) RING_FETCH(ring, slot, s.ring[slot] + w0, rec(k - RING_DEPTH) + w0, wbytes);
         }
         // stage 0:  dx0 = -e0 + Z0 dy,  (Z0'P0 Z0) dy = -Z0'(p0 - P0 e0)
         if (factor) {
@@ -950,9 +997,11 @@ struct WarpSolver {
     // lane region per stage: every lane forms du redundantly in registers, lanes < nx form dx+.
     VB_DEV void forward() {
         const int N = s.N;
-        for (int j = 0; j < RING_DEPTH && j < N; ++j) RING_FETCH(ring, j, s.ring[j], rec(j), R::BYTES);
-        for (int k = 0; k < N; ++k) {
-            const int slot = k % RING_DEPTH, cur = k & 1;
+        constexpr int w0 = R::W_FWD0;
+        constexpr unsigned wbytes = (R::W_FWD1 - R::W_FWD0) * 8u;
+        for (int j = 0; j < RING_DEPTH && j < N; ++j) RING_FETCH(ring, j, s.ring[j] + w0, rec(j) + w0, wbytes);
+        for (int k = 0, slot = 0; k < N; ++k, slot = slot + 1 == RING_DEPTH ? 0 : slot + 1) {
+            const int cur = k & 1;
             const bool last = (k == N - 1) && s.termfix;
             RING_WAIT(ring, slot);
             const double *r = s.ring[slot];
@@ -1023,7 +1072,7 @@ struct WarpSolver {
                 }
                 END_LANES
             }
-            if (k + RING_DEPTH < N) RING_FETCH(ring, slot, s.ring[slot], rec(k + RING_DEPTH), R::BYTES);
+            if (k + RING_DEPTH < N) RING_FETCH(ring, slot, s.ring[slot] + w0, rec(k + RING_DEPTH) + w0, wbytes);
         }
         FOR_LANES
         if (lane < NZ) w.DV[N * NZ + lane] = lane < NU ? 0.0 : s.dx[N & 1][lane - NU];
@@ -1052,7 +1101,7 @@ struct WarpSolver {
                     VB_PREFETCH(w.DV + nidx);
                     VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
                     VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.TQ + nc + NZ);
-                    VB_PREFETCH(w.RMB + nc), VB_PREFETCH(w.RMB + nc + NZ);
+                    if (VB_STORE_RMB) VB_PREFETCH(w.RMB + nc), VB_PREFETCH(w.RMB + nc + NZ);
                     VB_PREFETCH(w.RD + nc), VB_PREFETCH(w.RD + nc + NZ);
                     if (mode == 1) VB_PREFETCH(w.RM + nc), VB_PREFETCH(w.RM + nc + NZ);
                     if (mode == 0) VB_PREFETCH(rec(nk) + R::RR + (nidx - nk * NZ));
@@ -1067,7 +1116,7 @@ struct WarpSolver {
 #endif
                 for (int sd = 0; sd < 2; ++sd) {
                     int c = k * NC + sd * NZ + i;
-                    double lam = w.LAMQ[c], t = w.TQ[c], rm = w.RMB[c];
+                    double lam = w.LAMQ[c], t = w.TQ[c], rm = VB_STORE_RMB ? w.RMB[c] : lam * t;
                     if (mode == 1) rm += w.RM[c] - sm;
                     if (mode == 2) rm -= sm;
                     double dtt = (sd ? -dvv : dvv) - w.RD[c];

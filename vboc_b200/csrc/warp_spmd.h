@@ -51,9 +51,10 @@
 #endif
 // software prefetch of the next lane-strided iteration (the flat passes are latency bound)
 __device__ __forceinline__ void vb_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#define VB_PREFETCH(p) vb_prefetch(p)
+
 __device__ __forceinline__ void vb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #define VB_PREFETCH_L2(p) vb_prefetch_l2(p)
+#define VB_PREFETCH(p) vb_prefetch(p)
 
 // out of line on purpose: ~20 call sites share one copy (instruction-cache footprint)
 __device__ __noinline__ double vb_warp_max(double v) {
@@ -82,13 +83,14 @@ __device__ __forceinline__ int vb_warp_or(int v) { return __reduce_or_sync(0xfff
 // mbarrier phase.  `ph` is the warp-uniform bitmask of the slots' current phase parities.
 struct VbRing {
     unsigned long long *bar;  // shared: one mbarrier per slot
+    unsigned bar0;            // its shared-window address (computed once)
     unsigned ph;
 };
 __device__ __forceinline__ unsigned vb_smem_addr(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
 }
 __device__ __forceinline__ void vb_ring_init(VbRing &r, unsigned long long *bars, int depth) {
-    r.bar = bars, r.ph = 0u;
+    r.bar = bars, r.ph = 0u, r.bar0 = vb_smem_addr(bars);
     if ((threadIdx.x & 31u) == 0) {
         for (int i = 0; i < depth; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(vb_smem_addr(bars + i)));
@@ -99,7 +101,7 @@ __device__ __forceinline__ void vb_ring_init(VbRing &r, unsigned long long *bars
 __device__ __forceinline__ void vb_ring_fetch(VbRing &r, int slot, void *dst, const void *src, unsigned bytes,
                                               bool leader) {
     if (leader) {
-        unsigned b = vb_smem_addr(r.bar + slot);
+        unsigned b = r.bar0 + 8u * (unsigned)slot;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
         asm volatile(
             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -109,7 +111,7 @@ __device__ __forceinline__ void vb_ring_fetch(VbRing &r, int slot, void *dst, co
     }
 }
 __device__ __forceinline__ void vb_ring_wait(VbRing &r, int slot) {
-    unsigned b = vb_smem_addr(r.bar + slot), parity = (r.ph >> slot) & 1u;
+    unsigned b = r.bar0 + 8u * (unsigned)slot, parity = (r.ph >> slot) & 1u;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"

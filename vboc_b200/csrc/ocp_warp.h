@@ -515,7 +515,10 @@ struct WarpSolver {
     // RG (stationarity), RB (dynamics, into the stage records), RD (bounds), RMB (lam*t), and the
     // Newton-system data of the predictor: HH = hd + lam/t, RR = RG + (lam*t - lam*rd)/t (signed).
     // Returns mu, norms by reference.
-    VB_DEV double qp_residuals(double &ng, double &nb_, double &nd, double &nm, bool &nan) {
+    // upd: first apply the step of the previous IPM iteration to DZ, LAMQ, TQ (z += as dz, lam/t = max(. + as d., min))
+    // -- the update rides on the loads this pass does anyway instead of two more passes over the arrays.
+    VB_DEV double qp_residuals(double &ng, double &nb_, double &nd, double &nm, bool &nan, bool upd = false,
+                               double as = 0.0) {
         const int N = s.N;
         LV(double, a_g);
         LV(double, a_b);
@@ -524,7 +527,7 @@ struct WarpSolver {
         LV(double, a_mu);
         LV(int, bad);
         FOR_LANES
-        double vg = 0, vb = 0, vd = 0, vm = 0, mu = 0;
+        double vg = 0, vd = 0, vm = 0, mu = 0;
         int nb = 0;
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
@@ -535,9 +538,17 @@ struct WarpSolver {
                     VB_PREFETCH(rec(nk) + R::BAT + (nidx - nk * NZ) * NX), VB_PREFETCH(w.PIQ + nk * NX);
                     VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
                     VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.TQ + nc + NZ);
+                    if (upd) {
+                        VB_PREFETCH(w.DV + nidx), VB_PREFETCH(w.DLAM + nc), VB_PREFETCH(w.DLAM + nc + NZ);
+                        VB_PREFETCH(w.DT + nc), VB_PREFETCH(w.DT + nc + NZ);
+                    }
                 }
             }
             double v = w.DZ[idx];
+            if (upd) {
+                v += as * w.DV[idx];
+                w.DZ[idx] = v;
+            }
             double hh = cost_h(k, i) + o.qp_reg_prim, bar = 0.0;
             double r = (hh - o.qp_reg_prim) * v + cost_g(k, i, w.Z[idx]);
             double *rk = rec(k);
@@ -552,6 +563,11 @@ struct WarpSolver {
                 int sc = sclass(k);
                 double z = w.Z[idx];
                 double ll = w.LAMQ[c], lu = w.LAMQ[c + NZ], tl = w.TQ[c], tu = w.TQ[c + NZ];
+                if (upd) {
+                    ll = fmax(ll + as * w.DLAM[c], o.qp_lam_min), lu = fmax(lu + as * w.DLAM[c + NZ], o.qp_lam_min);
+                    tl = fmax(tl + as * w.DT[c], o.qp_t_min), tu = fmax(tu + as * w.DT[c + NZ], o.qp_t_min);
+                    w.LAMQ[c] = ll, w.LAMQ[c + NZ] = lu, w.TQ[c] = tl, w.TQ[c + NZ] = tu;
+                }
                 r += lu - ll;
                 double dl = (s.lb[sc][i] - z) - v + tl, du = v - (s.ub[sc][i] - z) + tu;
                 double ml = ll * tl, mu_ = lu * tu;
@@ -577,6 +593,11 @@ struct WarpSolver {
                 vg = fmax(vg, fabs(r));
             }
         }
+        L(a_g) = vg, L(a_d) = vd, L(a_m) = vm, L(a_mu) = mu, L(bad) = nb;
+        END_LANES  // the loop below reads DZ entries that other lanes may just have updated
+        FOR_LANES
+        double vb = 0;
+        int nb = 0;
         for (int idx = lane; idx < N * NX; idx += 32) {
             int k = idx / NX, i = idx - k * NX;
             double a = w.BD[idx] - w.DZ[(k + 1) * NZ + NU + i];
@@ -587,7 +608,7 @@ struct WarpSolver {
             nb |= (a != a);
             vb = fmax(vb, fabs(a));
         }
-        L(a_g) = vg, L(a_b) = vb, L(a_d) = vd, L(a_m) = vm, L(a_mu) = mu, L(bad) = nb;
+        L(a_b) = vb, L(bad) |= nb;
         END_LANES
         FOR_LANES
         if (lane < NX) {
@@ -1155,8 +1176,10 @@ struct WarpSolver {
         bool nan = false, ok = true;
         const double nc = 2.0 * s.nact;
         int kk = 0;
+        bool upd = false;
+        double as_prev = 0.0;
         for (;; ++kk) {
-            mu = qp_residuals(rg, rb, rd, rm, nan);
+            mu = qp_residuals(rg, rb, rd, rm, nan, upd, as_prev);
             if (!(kk < o.qp_iter_max && alpha > o.qp_alpha_min && !nan &&
                   (rg > o.qp_tol_stat || rb > o.qp_tol_eq || rd > o.qp_tol_ineq || rm > o.qp_tol_comp)))
                 break;
@@ -1185,13 +1208,10 @@ struct WarpSolver {
             if (!ok) break;
             double as = alpha;
             if (as < 1.0) as = as * ((1.0 - as) * 0.99 + as * 0.9999);
-            // update; the multiplier step of the dynamics is recovered here from the value functions:
-            // dpi_k = P_{k+1} dx_{k+1} + p_{k+1}
+            // update: only the multipliers of the dynamics are stepped here, dpi_k = P_{k+1} dx_{k+1} + p_{k+1} from the
+            // value functions; z, lam, t are stepped inside the next residual pass (qp_residuals(.., upd, as))
+            upd = true, as_prev = as;
             FOR_LANES
-            for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
-                if (VB_PF_UPD && idx + VB_PF_DIST < (N + 1) * NZ) VB_PREFETCH(w.DZ + idx + VB_PF_DIST), VB_PREFETCH(w.DV + idx + VB_PF_DIST);
-                w.DZ[idx] += as * w.DV[idx];
-            }
             for (int idx = lane; idx < N * NX; idx += 32) {
                 int k = idx / NX, mI = idx - k * NX;
                 const double *dxn = w.DV + (size_t)(k + 1) * NZ + NU;
@@ -1213,17 +1233,6 @@ struct WarpSolver {
                     a = s.hhN[mI] * dxn[mI] + s.rN[mI];
                 }
                 w.PIQ[idx] += as * a;
-            }
-            for (int idx = lane; idx < (N + 1) * NC; idx += 32) {
-                int k = idx / NC, c = idx - k * NC, i = c >= NZ ? c - NZ : c;
-                if (VB_PF_UPD && idx + VB_PF_DIST < (N + 1) * NC) {
-                    VB_PREFETCH(w.LAMQ + idx + VB_PF_DIST), VB_PREFETCH(w.DLAM + idx + VB_PF_DIST);
-                    VB_PREFETCH(w.TQ + idx + VB_PF_DIST), VB_PREFETCH(w.DT + idx + VB_PF_DIST);
-                }
-                if (active(k, i)) {
-                    w.LAMQ[idx] = fmax(w.LAMQ[idx] + as * w.DLAM[idx], o.qp_lam_min);
-                    w.TQ[idx] = fmax(w.TQ[idx] + as * w.DT[idx], o.qp_t_min);
-                }
             }
             END_LANES
         }

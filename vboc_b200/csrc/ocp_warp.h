@@ -135,6 +135,12 @@ VB_HD double dotv(const double *a, const double *b, double init = 0.0) {
 #ifndef VB_RG_ALL
 #define VB_RG_ALL 0  // the stationarity residual is stored for stage 0 only (the only one read back)
 #endif
+#ifndef VB_VEC_RES
+#define VB_VEC_RES 1  // 128-bit loads of the [B A] column and pi in the residual pass (+0.9 %)
+#endif
+#ifndef VB_PAIR_LAYOUT
+#define VB_PAIR_LAYOUT 1  // lower / upper entries of a bound adjacent: one 128-bit load per array in the flat passes (+1.8 %)
+#endif
 #ifndef VB_PF_DIST
 #define VB_PF_DIST 64  // software prefetch distance of the flat passes: two lane-strided iterations ahead
 #endif
@@ -168,7 +174,7 @@ struct Work {
     // The workspace is carved with the compile-time stride SMAX so that every array is the slot base
     // plus a constant (no pointer table in registers, immediate offsets in the load/store
     // instructions); N_max <= SMAX - 1 is checked by vboc_create.
-    static constexpr size_t SMAX = 129;
+    static constexpr size_t SMAX = 130;  // even: every array then starts on a 16-byte boundary (128-bit loads)
     static constexpr size_t O_SR = 0;
     static constexpr size_t O_Z = O_SR + SMAX * R::SIZE, O_PI = O_Z + SMAX * D::NZ, O_LAM = O_PI + SMAX * D::NX;
     static constexpr size_t O_BD = O_LAM + SMAX * D::NC, O_DZ = O_BD + SMAX * D::NX, O_PIQ = O_DZ + SMAX * D::NZ;
@@ -178,6 +184,8 @@ struct Work {
     static constexpr size_t O_PP = O_RMB + SMAX * D::NC, O_WDYN = O_PP + SMAX * PPS, O_WB = O_WDYN + SMAX * D::NX;
     static constexpr size_t O_ZT = O_WB + SMAX * D::NC, O_MF = O_ZT + SMAX * D::NZ;
     static constexpr size_t TOTAL = (O_MF + D::MFS + 1) & ~(size_t)1;
+    static_assert(O_PIQ % 2 == 0 && O_LAMQ % 2 == 0 && O_TQ % 2 == 0 && O_DLAM % 2 == 0 && O_DT % 2 == 0 && O_RD % 2 == 0 &&
+                      O_RM % 2 == 0, "16-byte aligned arrays");
     static VB_HD size_t doubles(int) { return TOTAL; }
     VB_HD void carve(double *b, int) {
         SR = b + O_SR;
@@ -231,6 +239,15 @@ struct WarpSolver {
         RING_INIT(ring, s.bar, RING_DEPTH);
     }
 
+    // index of the (k, i, side) bound constraint in the constraint arrays (LAM, LAMQ, TQ, DLAM, DT, RD, RM, RMB, WB).
+    // VB_PAIR_LAYOUT: the lower / upper entries of a component are adjacent, so both come with one 128-bit load.
+    static VB_DEV int CI(int k, int i, int sd) {
+#if VB_PAIR_LAYOUT
+        return (k * NZ + i) * 2 + sd;
+#else
+        return k * NC + sd * NZ + i;
+#endif
+    }
     // ---------------------------------------------------------------- problem structure helpers
     VB_DEV int sclass(int k) const { return k == 0 ? 0 : (k == s.N ? 2 : 1); }
     VB_DEV bool active(int k, int i) const {
@@ -424,7 +441,7 @@ struct WarpSolver {
                 if (k > 0 && i >= NU) r -= w.PI[(k - 1) * NX + i - NU];
                 if (active(k, i)) {
                     int sc = sclass(k);
-                    double ll = w.LAM[k * NC + i], lu = w.LAM[k * NC + NZ + i];
+                    double ll = w.LAM[CI(k, i, 0)], lu = w.LAM[CI(k, i, 1)];
                     double fl = s.lb[sc][i] - z, fu = z - s.ub[sc][i];
                     r += lu - ll;
                     vi = fmax(vi, fmax(fl, fu));
@@ -496,8 +513,8 @@ struct WarpSolver {
                 v = s.cN[i - NU] - z;
             }
             w.DZ[idx] = v;
-            w.LAMQ[k * NC + i] = ll, w.LAMQ[k * NC + NZ + i] = lu;
-            w.TQ[k * NC + i] = tl, w.TQ[k * NC + NZ + i] = tu;
+            w.LAMQ[CI(k, i, 0)] = ll, w.LAMQ[CI(k, i, 1)] = lu;
+            w.TQ[CI(k, i, 0)] = tl, w.TQ[CI(k, i, 1)] = tu;
         }
 #pragma unroll 1
         for (int idx = lane; idx < N * NX; idx += 32) w.PIQ[idx] = 0.0;
@@ -532,15 +549,17 @@ struct WarpSolver {
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             {
-                const int nidx = idx + VB_PF_DIST, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
+                const int nidx = idx + VB_PF_DIST, nk = nidx / NZ, nc = CI(nk, nidx - nk * NZ, 0);
+                constexpr int NZ_ = VB_PAIR_LAYOUT ? 1 : NZ;  // distance of the upper entry
+                (void)NZ_;
                 if (VB_PF_RES && nidx < (N + 1) * NZ) {
                     VB_PREFETCH(w.DZ + nidx), VB_PREFETCH(w.Z + nidx);
                     VB_PREFETCH(rec(nk) + R::BAT + (nidx - nk * NZ) * NX), VB_PREFETCH(w.PIQ + nk * NX);
-                    VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
-                    VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.TQ + nc + NZ);
+                    VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ_);
+                    VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.TQ + nc + NZ_);
                     if (upd) {
-                        VB_PREFETCH(w.DV + nidx), VB_PREFETCH(w.DLAM + nc), VB_PREFETCH(w.DLAM + nc + NZ);
-                        VB_PREFETCH(w.DT + nc), VB_PREFETCH(w.DT + nc + NZ);
+                        VB_PREFETCH(w.DV + nidx), VB_PREFETCH(w.DLAM + nc), VB_PREFETCH(w.DLAM + nc + NZ_);
+                        VB_PREFETCH(w.DT + nc), VB_PREFETCH(w.DT + nc + NZ_);
                     }
                 }
             }
@@ -554,25 +573,49 @@ struct WarpSolver {
             double *rk = rec(k);
             if (k < N) {
                 const double *col = rk + R::BAT + i * NX, *pi = w.PIQ + k * NX;
+#if VB_VEC_RES && defined(__CUDA_ARCH__)
+                // column i of [B A] and pi_k are 16-byte aligned runs of nx doubles: 128-bit loads
+                static_assert(Work<NQ>::O_PIQ % 2 == 0 && R::BAT % 2 == 0 && R::SIZE % 2 == 0 && NX % 2 == 0, "alignment");
+                const double2 *c2 = reinterpret_cast<const double2 *>(col), *p2 = reinterpret_cast<const double2 *>(pi);
+#pragma unroll
+                for (int m = 0; m < NX / 2; ++m) {
+                    const double2 cv = c2[m], pv = p2[m];
+                    r += cv.x * pv.x;
+                    r += cv.y * pv.y;
+                }
+#else
 #pragma unroll
                 for (int m = 0; m < NX; ++m) r += col[m] * pi[m];
+#endif
             }
             if (k > 0 && i >= NU) r -= w.PIQ[(k - 1) * NX + i - NU];
-            int c = k * NC + i;
+            const int c = CI(k, i, 0), cu = CI(k, i, 1);
             if (active(k, i)) {
                 int sc = sclass(k);
                 double z = w.Z[idx];
-                double ll = w.LAMQ[c], lu = w.LAMQ[c + NZ], tl = w.TQ[c], tu = w.TQ[c + NZ];
+#if VB_PAIR_LAYOUT && defined(__CUDA_ARCH__)
+                const double2 l2 = *reinterpret_cast<const double2 *>(w.LAMQ + c), t2 = *reinterpret_cast<const double2 *>(w.TQ + c);
+                double ll = l2.x, lu = l2.y, tl = t2.x, tu = t2.y;
                 if (upd) {
-                    ll = fmax(ll + as * w.DLAM[c], o.qp_lam_min), lu = fmax(lu + as * w.DLAM[c + NZ], o.qp_lam_min);
-                    tl = fmax(tl + as * w.DT[c], o.qp_t_min), tu = fmax(tu + as * w.DT[c + NZ], o.qp_t_min);
-                    w.LAMQ[c] = ll, w.LAMQ[c + NZ] = lu, w.TQ[c] = tl, w.TQ[c + NZ] = tu;
+                    const double2 dl2 = *reinterpret_cast<const double2 *>(w.DLAM + c), dt2 = *reinterpret_cast<const double2 *>(w.DT + c);
+                    ll = fmax(ll + as * dl2.x, o.qp_lam_min), lu = fmax(lu + as * dl2.y, o.qp_lam_min);
+                    tl = fmax(tl + as * dt2.x, o.qp_t_min), tu = fmax(tu + as * dt2.y, o.qp_t_min);
+                    *reinterpret_cast<double2 *>(w.LAMQ + c) = make_double2(ll, lu);
+                    *reinterpret_cast<double2 *>(w.TQ + c) = make_double2(tl, tu);
                 }
+#else
+                double ll = w.LAMQ[c], lu = w.LAMQ[cu], tl = w.TQ[c], tu = w.TQ[cu];
+                if (upd) {
+                    ll = fmax(ll + as * w.DLAM[c], o.qp_lam_min), lu = fmax(lu + as * w.DLAM[cu], o.qp_lam_min);
+                    tl = fmax(tl + as * w.DT[c], o.qp_t_min), tu = fmax(tu + as * w.DT[cu], o.qp_t_min);
+                    w.LAMQ[c] = ll, w.LAMQ[cu] = lu, w.TQ[c] = tl, w.TQ[cu] = tu;
+                }
+#endif
                 r += lu - ll;
                 double dl = (s.lb[sc][i] - z) - v + tl, du = v - (s.ub[sc][i] - z) + tu;
                 double ml = ll * tl, mu_ = lu * tu;
-                w.RD[c] = dl, w.RD[c + NZ] = du;
-                if (VB_STORE_RMB) w.RMB[c] = ml, w.RMB[c + NZ] = mu_;
+                w.RD[c] = dl, w.RD[cu] = du;
+                if (VB_STORE_RMB) w.RMB[c] = ml, w.RMB[cu] = mu_;
                 nb |= (dl != dl) | (du != du) | (ml != ml) | (mu_ != mu_);
                 vd = fmax(vd, fmax(fabs(dl), fabs(du)));
                 vm = fmax(vm, fmax(fabs(ml), fabs(mu_)));
@@ -581,8 +624,8 @@ struct WarpSolver {
                 hh += ll * itl + lu * itu;
                 bar = (ml - ll * dl) * itl - (mu_ - lu * du) * itu;
             } else {
-                w.RD[c] = 0.0, w.RD[c + NZ] = 0.0;
-                if (VB_STORE_RMB) w.RMB[c] = 0.0, w.RMB[c + NZ] = 0.0;
+                w.RD[c] = 0.0, w.RD[cu] = 0.0;
+                if (VB_STORE_RMB) w.RMB[c] = 0.0, w.RMB[cu] = 0.0;
                 if (k == N) r = 0.0;
             }
             if (VB_RG_ALL || k == 0) w.RG[idx] = r;  // only the stage-0 state part is read back (projection)
@@ -1117,30 +1160,51 @@ struct WarpSolver {
             double *rk = rec(k);
             double q1 = 0.0, q2 = 0.0;
             {
-                const int nidx = idx + VB_PF_DIST, nk = nidx / NZ, nc = nk * NC + (nidx - nk * NZ);
+                const int nidx = idx + VB_PF_DIST, nk = nidx / NZ, nc = CI(nk, nidx - nk * NZ, 0);
                 if (VB_PF_CON && nidx < (N + 1) * NZ) {
                     VB_PREFETCH(w.DV + nidx);
+#if VB_PAIR_LAYOUT
+                    VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.RD + nc);  // pairs share a sector
+                    if (mode == 1) VB_PREFETCH(w.RM + nc);
+#else
                     VB_PREFETCH(w.LAMQ + nc), VB_PREFETCH(w.LAMQ + nc + NZ);
                     VB_PREFETCH(w.TQ + nc), VB_PREFETCH(w.TQ + nc + NZ);
                     if (VB_STORE_RMB) VB_PREFETCH(w.RMB + nc), VB_PREFETCH(w.RMB + nc + NZ);
                     VB_PREFETCH(w.RD + nc), VB_PREFETCH(w.RD + nc + NZ);
                     if (mode == 1) VB_PREFETCH(w.RM + nc), VB_PREFETCH(w.RM + nc + NZ);
+#endif
                     if (mode == 0) VB_PREFETCH(rec(nk) + R::RR + (nidx - nk * NZ));
                 }
             }
             if (active(k, i)) {
                 double dvv = w.DV[idx];
+#if VB_PAIR_LAYOUT && defined(__CUDA_ARCH__)
+                // both sides of the component with one 128-bit load per array
+                const int c0 = CI(k, i, 0);
+                const double2 l2 = *reinterpret_cast<const double2 *>(w.LAMQ + c0);
+                const double2 t2 = *reinterpret_cast<const double2 *>(w.TQ + c0);
+                const double2 rd2 = *reinterpret_cast<const double2 *>(w.RD + c0);
+                double2 rm2 = make_double2(0.0, 0.0);
+                if (mode == 1) rm2 = *reinterpret_cast<const double2 *>(w.RM + c0);
+#endif
 #if VB_CON_ROLLED
 #pragma unroll 1
 #else
 #pragma unroll
 #endif
                 for (int sd = 0; sd < 2; ++sd) {
-                    int c = k * NC + sd * NZ + i;
+                    const int c = CI(k, i, sd);
+#if VB_PAIR_LAYOUT && defined(__CUDA_ARCH__)
+                    double lam = sd ? l2.y : l2.x, t = sd ? t2.y : t2.x, rm = lam * t;
+                    if (mode == 1) rm += (sd ? rm2.y : rm2.x) - sm;
+                    if (mode == 2) rm -= sm;
+                    double dtt = (sd ? -dvv : dvv) - (sd ? rd2.y : rd2.x);
+#else
                     double lam = w.LAMQ[c], t = w.TQ[c], rm = VB_STORE_RMB ? w.RMB[c] : lam * t;
                     if (mode == 1) rm += w.RM[c] - sm;
                     if (mode == 2) rm -= sm;
                     double dtt = (sd ? -dvv : dvv) - w.RD[c];
+#endif
                     double it = VB_RCP(t);
                     double dl = -(rm + lam * dtt) * it;
                     // ratio test; the division only when this constraint tightens the step
@@ -1245,7 +1309,7 @@ struct WarpSolver {
             const double *col = rec(0) + R::BAT + (NU + i) * NX;
 #pragma unroll
             for (int m = 0; m < NX; ++m) a += col[m] * w.PIQ[m];
-            if (active(0, NU + i)) a += w.LAMQ[NZ + NU + i] - w.LAMQ[NU + i];
+            if (active(0, NU + i)) a += w.LAMQ[CI(0, NU + i, 1)] - w.LAMQ[CI(0, NU + i, 0)];
             s.va[i] = s.vb[i] = a;
             s.nuNq[i] = ((s.fixedN >> i) & 1)
                             ? w.PIQ[(N - 1) * NX + i] - cost_g(N, NU + i, w.Z[N * NZ + NU + i]) -
@@ -1302,8 +1366,8 @@ struct WarpSolver {
             if (active(k, i)) {
                 int sc = sclass(k);
                 double z = Zs[idx], fl = s.lb[sc][i] - z, fu = z - s.ub[sc][i];
-                if (fl > 0) a += w.WB[k * NC + i] * fl;
-                if (fu > 0) a += w.WB[k * NC + NZ + i] * fu;
+                if (fl > 0) a += w.WB[CI(k, i, 0)] * fl;
+                if (fu > 0) a += w.WB[CI(k, i, 1)] * fu;
             }
         }
         L(acc) = a;

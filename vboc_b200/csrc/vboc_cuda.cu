@@ -39,6 +39,9 @@ int fail(int code, const std::string &msg) {
 #ifndef VB_WARPS_PER_CTA
 #define VB_WARPS_PER_CTA 4
 #endif
+// largest horizon: both workspaces (warp and lane kernels) hold N_max + 1 stages
+constexpr int VBOC_N_MAX = 128;
+static_assert(VBOC_N_MAX + 1 <= (int)Work<3>::SMAX && VBOC_N_MAX + 1 <= (int)LaneLayout<3>::SMAX, "workspace stages");
 constexpr int WARPS_PER_CTA = VB_WARPS_PER_CTA;  // tuning builds may change the CTA shape
 #ifdef VB_TUNE_MINB
 #define VB_LB_MINB(m) VB_TUNE_MINB
@@ -348,7 +351,7 @@ static size_t work_doubles_for(int n, int Nmax) {
 
 int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device, vboc_solver **out) {
     if (!out || n_dof < 1 || n_dof > 3 || (family != VBOC_FAMILY_VBOC && family != VBOC_FAMILY_AL) ||
-        batch_capacity < 1 || N_max < 1 || N_max > (int)Work<3>::SMAX - 1)
+        batch_capacity < 1 || N_max < 1 || N_max > VBOC_N_MAX)
         return fail(VBOC_ERR_ARG, "vboc_create: bad argument");
     int ndev = 0;
     CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -843,7 +846,7 @@ int vboc_sim_step(int n_dof, int device, int batch, const double *x, const doubl
 
 int vboc_stream_create(int n_dof, int family, int capacity, int N_max, int device, vboc_stream **out) {
     if (!out || n_dof < 1 || n_dof > 3 || (family != VBOC_FAMILY_VBOC && family != VBOC_FAMILY_AL) || capacity < 1 ||
-        N_max < 1 || N_max > (int)Work<3>::SMAX - 1)
+        N_max < 1 || N_max > VBOC_N_MAX)
         return fail(VBOC_ERR_ARG, "vboc_stream_create: bad argument");
     int ndev = 0;
     CUDA_OK(cudaGetDeviceCount(&ndev));

@@ -44,6 +44,8 @@ def test_no_cpu_fallback():
     from vboc_b200._lib import VbocError
     with pytest.raises(VbocError):
         engine.BatchSolver(3, "vboc", 4, 100)
+    with pytest.raises(VbocError):  # the streaming engine has no host path either
+        engine.StreamSolver(3, "vboc", 4, 100)
 
 
 def test_product_never_imports_the_oracle():

@@ -1,0 +1,105 @@
+"""The active-learning loop of the AL drivers (AL/triplependulum_al.py:100-360, doublependulum_al.py, pendulum_al.py)
+around the batched engine: SURVEY 8(f)2.
+
+Per round the reference (i) scores the whole unlabeled pool with the classifier's entropy and takes the B most
+uncertain states (:241-281), (ii) labels them with `testing_guess` -- one SQP_RTI solve each, started from the
+trajectory the guess network predicts (:45-62, AL/triplependulum_class_al.py:171-201) -- under `Pool(30)`, (iii)
+slides the training windows (`X_iter = X_iter[qi:] + new`, `X_traj = X_traj[qt:] + new`, :284-293) and (iv) retrains
+both networks (:300-360).  Here (i) is the fused MLP + entropy kernel with a (global) top-B, (ii) one batched RTI
+call; (iii) is this module; (iv) stays PyTorch (`fit_minibatch`, the reference's Adam loop).  Nothing here imports
+the oracle: `label_fn` defaults to `drivers.al_label_batch` (GPU)."""
+import numpy as np
+
+from . import drivers
+
+
+def fit_minibatch(model, optimizer, criterion, X, Y, mean, std, n_minibatch=512, loss_stop=0.1, it_max=1000,
+                  beta=0.95, seed=0, normalize_targets=False):
+    """The reference's training loop (AL/triplependulum_al.py:147-170 classifier, :176-201 guess network): random
+    minibatches, Adam steps until the exponentially averaged loss drops below `loss_stop` or `it_max` steps."""
+    import torch
+    rng = np.random.default_rng(seed)
+    dev = next(model.parameters()).device
+    Xt = (torch.as_tensor(np.asarray(X), dtype=torch.float32, device=dev) - mean) / std
+    Yt = torch.as_tensor(np.asarray(Y), dtype=torch.float32, device=dev)
+    if normalize_targets:
+        Yt = (Yt - mean) / std
+    val, it = 1.0, 0
+    while val > loss_stop and it <= it_max and len(Xt):
+        ind = torch.as_tensor(rng.choice(len(Xt), size=min(n_minibatch, len(Xt)), replace=False), device=dev)
+        optimizer.zero_grad(set_to_none=True)
+        loss = criterion(model(Xt[ind]), Yt[ind])
+        loss.backward()
+        optimizer.step()
+        val = beta * val + (1 - beta) * float(loss.item())
+        it += 1
+    return val, it
+
+
+def predict_guess(model_guess, X, mean, std, N, nx):
+    """`compute_problem_nnguess`'s initial guess (AL/triplependulum_class_al.py:180-192): stage 0 is the state itself,
+    stages 1..N the de-normalised network output."""
+    import torch
+    dev = next(model_guess.parameters()).device
+    with torch.no_grad():
+        inp = (torch.as_tensor(np.asarray(X), dtype=torch.float32, device=dev) - mean) / std
+        out = (model_guess(inp) * std + mean).cpu().numpy().astype(np.float64)
+    xg = np.empty((len(X), N + 1, nx))
+    xg[:, 0] = X
+    xg[:, 1:] = out.reshape(len(X), N, nx)
+    return xg
+
+
+def _rows(X, labels, traj):
+    """X_iter rows [x, one-hot label] (label 1 -> [0, 1], else [1, 0]) and X_traj rows [x, trajectory]
+    (AL/triplependulum_al.py:24-43)."""
+    viable = labels == 1
+    onehot = np.where(viable[:, None], [0.0, 1.0], [1.0, 0.0])
+    it_rows = np.hstack([X, onehot])
+    tr_rows = np.hstack([X[viable], traj[viable].reshape(int(viable.sum()), -1)])
+    return it_rows, tr_rows
+
+
+def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, fit_guess, etp_stop=0.1,
+                    max_rounds=100, N=100, Tf=1.0, device=0, label_fn=None, query_fn=None, history=None):
+    """Run the loop; returns (X_iter, X_traj, remaining pool).  `fit_cls(model, X_iter)` / `fit_guess(model_guess,
+    X_traj)` retrain in place; `history` (list) receives one dict per round."""
+    from . import nn as vnn
+    label_fn = label_fn or (lambda X, xg: drivers.al_label_batch(n, X, device=device, N=N, Tf=Tf, x_guess=xg))
+    pool = np.asarray(pool, dtype=float)
+    nx = 2 * n
+    # initial labelling without a trained guess (testing(s0), :131-137)
+    labels, traj = label_fn(pool[:N_init], None)
+    X_iter, X_traj = _rows(pool[:N_init], labels, traj[:, :, :nx])
+    pool = pool[N_init:]
+    fit_cls(model, X_iter)
+    if len(X_traj):
+        fit_guess(model_guess, X_traj)
+    k, etpmax = 0, 1.0
+    while not (etpmax < etp_stop or len(pool) == 0) and k < max_rounds:
+        Bk = min(B, len(pool))
+        if query_fn is not None:
+            idx, etp = query_fn(model, pool, Bk)
+        else:
+            net = vnn.MLP.from_torch(model, device=device)
+            idx, etp = drivers.al_query(net, pool, float(mean), float(std), Bk)
+            net.close()
+        idx = np.asarray(idx, dtype=np.int64)
+        etpmax = float(np.max(etp[idx]))
+        k += 1
+        elems = pool[idx]
+        pool = np.delete(pool, idx, axis=0)
+        xg = predict_guess(model_guess, elems, mean, std, N, nx) if len(X_traj) else None
+        labels, traj = label_fn(elems, xg)
+        new_it, new_tr = _rows(elems, labels, traj[:, :, :nx])
+        # sliding windows (:284-293): drop as many old rows as the batch size, append the new ones
+        qt, qi = min(Bk, len(X_traj)), min(Bk, len(X_iter))
+        X_traj = np.vstack([X_traj[qt:], new_tr]) if len(new_tr) or len(X_traj) else X_traj
+        X_iter = np.vstack([X_iter[qi:], new_it])
+        fit_cls(model, X_iter)
+        if len(X_traj):
+            fit_guess(model_guess, X_traj)
+        if history is not None:
+            history.append(dict(round=k, etpmax=etpmax, labelled=int(len(elems)), viable=int((labels == 1).sum()),
+                                pool=int(len(pool)), window=int(len(X_iter)), traj_window=int(len(X_traj))))
+    return X_iter, X_traj, pool

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vboc_b200.h"
@@ -309,7 +310,7 @@ struct vboc_stream {
     cudaStream_t sim_stream;
     double *sx, *su, *sxn;  // mapped pinned, sim_cap rows
     int sim_cap;
-    long long launches, solved;
+    long long launches, solved, idle_polls;
 };
 
 template <int NQ, int FAM>
@@ -855,7 +856,7 @@ int vboc_stream_create(int n_dof, int family, int capacity, int N_max, int devic
     vboc_stream *s = new vboc_stream();
     s->n = n_dof, s->family = family, s->cap = capacity, s->Nmax = N_max, s->device = device;
     s->nxr = 2 * n_dof + (family == VBOC_FAMILY_VBOC), s->nu = n_dof;
-    s->launches = s->solved = 0;
+    s->launches = s->solved = s->idle_polls = 0;
     vboc_default_opts(family, &s->opts);
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -962,6 +963,7 @@ int vboc_stream_submit(vboc_stream *s, int mode, int count, const int *N, const 
             if (!s->rec[i].busy) r = i;
         }
         cudaGetLastError();  // cudaErrorNotReady of the queries is not an error
+        if (r < 0) std::this_thread::yield();  // every record holds a running launch: wait for one to finish
     }
     // validate everything before touching a slot
     std::vector<double> h(count), dir((size_t)count * n);
@@ -1030,8 +1032,8 @@ int vboc_stream_poll(vboc_stream *s, int max, int *tickets) {
         }
     }
     s->inflight.resize(keep);
-    if (nout == 0 && keep) {
-        // surface a failed launch / a faulted kernel instead of polling forever
+    if (nout == 0 && keep && (++s->idle_polls & 255) == 0) {
+        // now and then: surface a failed launch / a faulted kernel instead of polling forever
         cudaError_t e = cudaPeekAtLastError();
         if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("vboc_stream_poll: ") + cudaGetErrorString(e));
         for (int i = 0; i < vboc_stream::NREC; ++i)

@@ -123,6 +123,21 @@ int vboc_solve_resident(vboc_solver *s, int mode);
 int vboc_solve_resident_async(vboc_solver *s, int mode);
 int vboc_sync(vboc_solver *s);
 int vboc_download(vboc_solver *s, double *x, double *u, vboc_stats *stats);
+/*
+ * KKT multipliers at the returned iterate, so that acados' exit test (ocp_nlp_sqp: res_stat < tol_stat,
+ * res_eq / res_ineq / res_comp < tol; options at VBOC/triplependulum_class_vboc.py:129-141) can be recomputed
+ * from the results without trusting the solver (tools/certify.py).  Call vboc_export_multipliers(s, 1)
+ * before the solve (allocates the device arrays), then after it
+ *   pi  [batch][N_max][2n]        multipliers of the shooting equalities  Phi_h(x_k, u_k) - x_{k+1} = 0
+ *   lam [batch][N_max+1][3n][2]   multipliers (lower, upper) of the bounds on z_k = [u_k; q_k; v_k]
+ * in the engine's reduced coordinates (the pinned dt state is eliminated, so its bound multipliers do not
+ * appear; the multipliers of the eliminated equalities -- fixed initial components, (I - d d') v_0 = 0,
+ * v_N = const -- are free in sign and follow from stationarity).  The Lagrangian is
+ *   cost + sum_k pi_k'(Phi(x_k, u_k) - x_{k+1}) + sum lam_u (z - ub) + lam_l (lb - z).
+ * Warp kernel only (VBOC_ERR_UNSUPPORTED for the 1-DOF free-dt problem).
+ */
+int vboc_export_multipliers(vboc_solver *s, int on);
+int vboc_download_multipliers(vboc_solver *s, double *pi, double *lam);
 /* Device time of the last vboc_solve_resident kernel in milliseconds (CUDA events on the solver's
  * stream); negative if none. */
 double vboc_last_kernel_ms(vboc_solver *s);

@@ -30,14 +30,16 @@ def test_active_learning_two_rounds_on_gpu():
     optg = torch.optim.Adam(guess.parameters(), lr=1e-3)
     fit_cls = lambda m, Xi: al_loop.fit_minibatch(m, opt, torch.nn.BCEWithLogitsLoss(), Xi[:, :nx], Xi[:, nx:], mean, std,
                                                   n_minibatch=128, it_max=200)
-    fit_guess = lambda m, Xt: al_loop.fit_minibatch(m, optg, torch.nn.MSELoss(), Xt[:, :nx], Xt[:, 2 * nx:], mean, std,
+    fit_guess = lambda m, Xt: al_loop.fit_minibatch(m, optg, torch.nn.MSELoss(), Xt[:, :nx], Xt[:, nx:], mean, std,
                                                     n_minibatch=128, it_max=100, normalize_targets=True)
     hist = []
     Xi, Xt, rest = al_loop.active_learning(n, pool, 400, 200, model, guess, mean, std, fit_cls, fit_guess,
                                            etp_stop=0.0, max_rounds=2, N=N, history=hist)
     assert len(hist) == 2 and len(rest) == 1200 - 400 - 400
-    assert Xi.shape == (400, nx + 2) and Xt.shape[1] == nx + (N + 1) * nx
+    assert Xi.shape == (400, nx + 2) and Xt.shape[1] == (N + 1) * nx
     assert all(0 < h["viable"] < h["labelled"] for h in hist)  # the queried states straddle the boundary
     # viable rows carry a trajectory that starts at the state and ends at rest
-    tr = Xt[:, nx:].reshape(len(Xt), N + 1, nx)
-    assert np.allclose(tr[:, 0], Xt[:, :nx], atol=1e-9) and np.abs(tr[:, -1, n:]).max() < 1e-6
+    tr = Xt.reshape(len(Xt), N + 1, nx)
+    assert np.abs(tr[:, -1, n:]).max() < 1e-6
+    mdl = pr.Model(n)
+    assert (tr[:, :, :n] >= mdl.thetamin - 1e-6).all() and (tr[:, :, :n] <= mdl.thetamax + 1e-6).all()

@@ -1,0 +1,71 @@
+"""At-scale, solver-independent certification of the CUDA engine (tools/certify.py, numpy / scipy only -- neither
+the oracle nor the engine's solver code takes part in the check):
+
+  * every status-0 result of >= 4096 C4 problems and >= 2048 C2 / C3 problems passes acados' SQP exit test
+    (res_stat < 1e-3, res_eq / res_ineq / res_comp < 1e-6, VBOC/triplependulum_class_vboc.py:129-141) recomputed in
+    numpy from the returned iterate and the exported multipliers, and no status != 0 result would have passed;
+  * AL labels of >= 2048 3-DOF states equal LP feasibility (HiGHS) of the linearised stopping problem;
+  * K4: one linearised QP solved by the kernel satisfies the dense KKT conditions of that QP.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from vboc_b200 import problems as pr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import certify  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag,n,B,seed", [("c4", 3, 4096, 4242), ("c3", 2, 2048, 4243), ("c2", 2, 2048, 4244)])
+def test_status0_is_certified_by_the_exit_test(tag, n, B, seed):
+    bp = pr.sample_testdata(n, B, seed=seed) if tag == "c2" else pr.sample_vboc(n, B, seed=seed)
+    out = certify._solve_with_multipliers(n, "vboc", bp, 0)
+    res = certify.kkt_residuals(n, bp, out["x"], out["u"], out["pi"], out["lam"])
+    ok = out["status"] == 0
+    cert = certify.passes_exit_test(res)
+    assert ok.mean() > 0.97, ok.mean()
+    assert cert[ok].all(), {k: float(v[ok & ~cert].max()) for k, v in res.items()}
+    assert not cert[~ok].any()            # nothing reported as failed is a point the exit test accepts
+    # the engine's own residuals are the independently recomputed ones
+    for k in ("res_stat", "res_eq", "res_ineq", "res_comp"):
+        assert np.abs(res[k][ok] - out[k][ok]).max() < 1e-7, k
+    # the reported cost is p . v_0 at the returned point
+    v0 = out["x"][:, 0, n:2 * n]
+    assert np.abs(out["cost"] - np.einsum("bi,bi->b", bp["p"][:, :n], v0))[ok].max() < 1e-12
+
+
+@pytest.mark.parametrize("n,B", [(3, 2048), (2, 2048)])
+def test_al_labels_are_lp_feasibility(n, B):
+    from vboc_b200._lib import MODE_RTI
+    bp = pr.sample_al(n, B, seed=4245)
+    out = certify._solve_with_multipliers(n, "al", bp, MODE_RTI)
+    lab = out["status"] == 0
+    assert set(np.unique(out["status"]).tolist()) <= {0, 4}
+    feas = certify.al_lp_labels(n, np.asarray(bp["lbx0"])[:, :2 * n])
+    agree = lab == feas
+    assert lab.any() and (~lab).any()
+    assert agree.mean() >= 0.999, (agree.mean(), np.where(~agree)[0])
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_k4_gpu_qp_satisfies_dense_kkt(n):
+    from vboc_b200 import engine
+    from vboc_b200._lib import MODE_RTI
+    bp = pr.sample_vboc(n, 64, seed=5)
+    o = engine.default_opts("vboc")
+    o.qp_tol_stat = o.qp_tol_eq = o.qp_tol_ineq = o.qp_tol_comp = 1e-9
+    out = certify._solve_with_multipliers(n, "vboc", bp, MODE_RTI, o)
+    assert (out["qp_status"] == 0).all()
+    for b in range(64):
+        N = int(bp["N"][b])
+        dx = out["x"][b, :N + 1, :2 * n] - bp["x_guess"][b, :N + 1, :2 * n]
+        du = out["u"][b, :N] - bp["u_guess"][b, :N]
+        r = certify.qp_kkt(n, bp, b, dx, du, out["pi"][b], out["lam"][b])
+        assert max(r["res_g"], r["res_b"], r["res_d"], r["res_m"]) < 1e-8, (b, r)
+        assert r["lam_min"] >= 0.0

@@ -12,6 +12,10 @@
 
 using namespace vboc;
 
+// optional multiplier export of the warp solver (set before emu_solve_batch, reset to null afterwards)
+static double *g_pi = nullptr, *g_lam = nullptr;
+extern "C" void emu_set_multiplier_out(double *pi, double *lam) { g_pi = pi, g_lam = lam; }
+
 template <int NQ, int FAM>
 static void run(int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug,
                 const double *p, const double *lbx0, const double *ubx0, const double *lbx,
@@ -39,6 +43,7 @@ static void run(int mode, int batch, int Nmax, const int *N, const double *xg, c
             pb.dir = dir ? dir + (size_t)b * NQ : nullptr;
             pb.x = x + (size_t)b * (Nmax + 1) * nxr, pb.u = u + (size_t)b * Nmax * nu;
             pb.st = st + b;
+            if (g_pi) pb.pi_out = g_pi + (size_t)b * Nmax * 2 * NQ, pb.lam_out = g_lam + (size_t)b * (Nmax + 1) * 6 * NQ;
             WarpSolver<NQ, FAM> sol(*sm, w, *o);
             sol.solve(pb, mode);
         }

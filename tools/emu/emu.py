@@ -39,7 +39,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def solve_batch(n, family, mode, bp, opts, kernel="warp"):
+def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False):
     lib = C.CDLL(build() if not os.path.exists(os.path.join(_HERE, "libemu.so")) else os.path.join(_HERE, "libemu.so"))
     c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
     xg, ug = c(bp["x_guess"]), c(bp["u_guess"])
@@ -55,10 +55,17 @@ def solve_batch(n, family, mode, bp, opts, kernel="warp"):
         d = None
     x, u = np.zeros_like(xg), np.zeros_like(ug)
     st = (Stats * B)()
+    pi = lam = None
+    if multipliers:
+        assert kernel == "warp"
+        pi, lam = np.zeros((B, Nmax, 2 * n)), np.zeros((B, Nmax + 1, 3 * n, 2))
+        lib.emu_set_multiplier_out(_p(pi), _p(lam))
     fn = {"warp": lib.emu_solve_batch, "lane": lib.emu_lane_solve_batch, "lane_dts": lib.emu_lane_dts_solve_batch}[kernel]
     fn(n, family, mode, B, Nmax, Nv.ctypes.data_as(C.POINTER(C.c_int)), _p(xg), _p(ug),
                         *[_p(a) for a in keep], _p(d), _p(h), C.byref(opts), _p(x), _p(u), st)
+    if multipliers:
+        lib.emu_set_multiplier_out(None, None)
     f = lambda name: np.array([getattr(s_, name) for s_ in st])
-    return dict(status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),
+    return dict(pi=pi, lam=lam, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),
                 ls_evals=f("ls_evals"), qp_status=f("qp_status"),
                 res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))

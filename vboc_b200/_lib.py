@@ -18,7 +18,7 @@ ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA = -1, -2, -3
 EXPORTS = (
     "vboc_default_opts", "vboc_create", "vboc_destroy", "vboc_set_opts", "vboc_set_stream",
     "vboc_solve_batch", "vboc_upload", "vboc_solve_resident", "vboc_solve_resident_async", "vboc_sync",
-    "vboc_download", "vboc_last_kernel_ms",
+    "vboc_download", "vboc_last_kernel_ms", "vboc_export_multipliers", "vboc_download_multipliers",
     "vboc_stream_create", "vboc_stream_destroy", "vboc_stream_set_opts", "vboc_stream_free_slots",
     "vboc_stream_pending", "vboc_stream_submit", "vboc_stream_poll", "vboc_stream_fetch", "vboc_stream_sim_step",
     "vboc_sim_step", "vboc_mlp_create", "vboc_mlp_destroy", "vboc_mlp_forward", "vboc_mlp_last_kernel_ms", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
@@ -79,6 +79,8 @@ def lib():
         L.vboc_solve_resident_async.argtypes = [vp, C.c_int]
         L.vboc_sync.argtypes = [vp]
         L.vboc_download.argtypes = [vp, dp, dp, C.POINTER(Stats)]
+        L.vboc_export_multipliers.argtypes = [vp, C.c_int]
+        L.vboc_download_multipliers.argtypes = [vp, dp, dp]
         L.vboc_last_kernel_ms.argtypes = [vp]
         L.vboc_last_kernel_ms.restype = C.c_double
         L.vboc_sim_step.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, dp]

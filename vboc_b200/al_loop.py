@@ -51,47 +51,89 @@ def predict_guess(model_guess, X, mean, std, N, nx):
 
 
 def _rows(X, labels, traj):
-    """X_iter rows [x, one-hot label] (label 1 -> [0, 1], else [1, 0]) and X_traj rows [x, trajectory]
-    (AL/triplependulum_al.py:24-43)."""
-    viable = labels == 1
-    onehot = np.where(viable[:, None], [0.0, 1.0], [1.0, 0.0])
-    it_rows = np.hstack([X, onehot])
-    tr_rows = np.hstack([X[viable], traj[viable].reshape(int(viable.sum()), -1)])
-    return it_rows, tr_rows
+    """X_iter rows [x, one-hot label] (label 1 -> [0, 1], label 0 -> [1, 0]) and X_traj rows = the flattened
+    (N+1) x nx trajectory of every viable sample, stage 0 being the sample itself -- the reference's layout
+    (AL/triplependulum_al.py:24-43, :183-184: the guess network is trained with X_traj[i][:nx] as input and
+    X_traj[i][nx:] as target).  Samples whose solve ended with any other status (label 2) produce NO row, as in
+    the reference (`testing` returns nothing for them); their count is the third return value."""
+    viable, unviable = labels == 1, labels == 0
+    keep = viable | unviable
+    onehot = np.where(viable[keep][:, None], [0.0, 1.0], [1.0, 0.0])
+    it_rows = np.hstack([X[keep], onehot])
+    tr_rows = traj[viable].reshape(int(viable.sum()), traj.shape[1] * traj.shape[2])
+    return it_rows, tr_rows, int((~keep).sum())
 
 
 def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, fit_guess, etp_stop=0.1,
-                    max_rounds=100, N=100, Tf=1.0, device=0, label_fn=None, query_fn=None, history=None):
+                    max_rounds=100, N=100, Tf=1.0, device=0, label_fn=None, query_fn=None, history=None,
+                    sharded=False):
     """Run the loop; returns (X_iter, X_traj, remaining pool).  `fit_cls(model, X_iter)` / `fit_guess(model_guess,
-    X_traj)` retrain in place; `history` (list) receives one dict per round."""
+    X_traj)` retrain in place; `history` (list) receives one dict per round.
+
+    sharded=True (under torch.distributed): `pool` is THIS rank's shard of the unlabeled pool and
+    N_init / B are global numbers.  Every rank scores its shard, the query is the global top-B, each rank labels and
+    removes the selected states that live in its shard, and the new rows are all-gathered so that all ranks hold
+    identical training windows (and, with identical seeds, train identical networks).  `query_fn(model, pool, Bk)`
+    must then return (local indices, entropies, global maximum of the selected entropies)."""
+    from . import distributed as vd
     from . import nn as vnn
+    world = rank = 0
+    if sharded:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+
+    def gather(it_rows, tr_rows, width_tr):
+        if not sharded:
+            return it_rows, tr_rows
+        return vd.all_gather_rows(it_rows), vd.all_gather_rows(tr_rows.reshape(-1, width_tr))
+
     label_fn = label_fn or (lambda X, xg: drivers.al_label_batch(n, X, device=device, N=N, Tf=Tf, x_guess=xg))
     pool = np.asarray(pool, dtype=float)
     nx = 2 * n
     # initial labelling without a trained guess (testing(s0), :131-137)
-    labels, traj = label_fn(pool[:N_init], None)
-    X_iter, X_traj = _rows(pool[:N_init], labels, traj[:, :, :nx])
-    pool = pool[N_init:]
+    n0 = N_init
+    if sharded:
+        lo, hi = vd.shard_range(N_init, rank, world)
+        n0 = min(hi - lo, len(pool))
+    labels, traj = label_fn(pool[:n0], None)
+    X_iter, X_traj, dropped = _rows(pool[:n0], labels, traj[:, :, :nx])
+    X_iter, X_traj = gather(X_iter, X_traj, (N + 1) * nx)
+    pool = pool[n0:]
     fit_cls(model, X_iter)
     if len(X_traj):
         fit_guess(model_guess, X_traj)
     k, etpmax = 0, 1.0
-    while not (etpmax < etp_stop or len(pool) == 0) and k < max_rounds:
-        Bk = min(B, len(pool))
+
+    def pool_left():
+        if not sharded:
+            return len(pool)
+        return int(vd.all_gather_rows(np.array([[float(len(pool))]])).sum())
+
+    while k < max_rounds:
+        total = pool_left()
+        if etpmax < etp_stop or total == 0:
+            break
+        Bk = min(B, total)
         if query_fn is not None:
-            idx, etp = query_fn(model, pool, Bk)
+            q = query_fn(model, pool, Bk)
+            idx, etp = q[0], q[1]
+            etpmax = float(q[2]) if len(q) > 2 else float(np.max(np.asarray(etp)[np.asarray(idx, dtype=np.int64)]))
         else:
             net = vnn.MLP.from_torch(model, device=device)
-            idx, etp = drivers.al_query(net, pool, float(mean), float(std), Bk)
+            idx, etp, etpmax = drivers.al_query(net, pool, float(mean), float(std), Bk, sharded=sharded)
             net.close()
         idx = np.asarray(idx, dtype=np.int64)
-        etpmax = float(np.max(etp[idx]))
         k += 1
         elems = pool[idx]
         pool = np.delete(pool, idx, axis=0)
-        xg = predict_guess(model_guess, elems, mean, std, N, nx) if len(X_traj) else None
-        labels, traj = label_fn(elems, xg)
-        new_it, new_tr = _rows(elems, labels, traj[:, :, :nx])
+        xg = predict_guess(model_guess, elems, mean, std, N, nx) if (model_guess is not None and len(X_traj) and len(elems)) else None
+        if len(elems):
+            labels, traj = label_fn(elems, xg)
+        else:
+            labels, traj = np.zeros(0, dtype=np.int64), np.zeros((0, N + 1, nx))
+        new_it, new_tr, drop = _rows(elems, labels, traj[:, :, :nx])
+        dropped += drop
+        new_it, new_tr = gather(new_it, new_tr, (N + 1) * nx)
         # sliding windows (:284-293): drop as many old rows as the batch size, append the new ones
         qt, qi = min(Bk, len(X_traj)), min(Bk, len(X_iter))
         X_traj = np.vstack([X_traj[qt:], new_tr]) if len(new_tr) or len(X_traj) else X_traj
@@ -101,5 +143,6 @@ def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, 
             fit_guess(model_guess, X_traj)
         if history is not None:
             history.append(dict(round=k, etpmax=etpmax, labelled=int(len(elems)), viable=int((labels == 1).sum()),
-                                pool=int(len(pool)), window=int(len(X_iter)), traj_window=int(len(X_traj))))
+                                pool=int(len(pool)), window=int(len(X_iter)), traj_window=int(len(X_traj)),
+                                dropped_label2=int(dropped)))
     return X_iter, X_traj, pool

@@ -39,6 +39,9 @@ struct Prob {
     const double *dir;  // unit direction d of the stage-0 constraint (I - d d')v_0 = 0, or nullptr
     double *x, *u;
     vboc_stats *st;
+    // optional export of the KKT multipliers at the returned iterate (vboc_download_multipliers):
+    // pi [N][2n] of the shooting equalities, lam [N+1][3n][2] of the (lower, upper) bounds on z = [u; q; v]
+    double *pi_out = nullptr, *lam_out = nullptr;
 };
 
 template <int NQ>
@@ -381,6 +384,13 @@ struct WarpSolver {
             pb.u[idx] = w.Z[k * NZ + i];
         }
         if (lane == 0) *pb.st = st;
+        if (pb.pi_out) {
+            for (int idx = lane; idx < N * NX; idx += 32) pb.pi_out[idx] = w.PI[idx];
+            for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
+                int k = idx / NZ, i = idx - k * NZ;
+                pb.lam_out[2 * idx] = w.LAM[CI(k, i, 0)], pb.lam_out[2 * idx + 1] = w.LAM[CI(k, i, 1)];
+            }
+        }
         END_LANES
     }
 

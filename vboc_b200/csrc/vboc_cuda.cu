@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -57,6 +58,7 @@ struct Batch {
     const double *xg, *ug, *p, *lbx0, *ubx0, *lbx, *ubx, *lbxN, *ubxN, *lbu, *ubu, *dir, *h;
     double *x, *u;
     vboc_stats *st;
+    double *pi_out = nullptr, *lam_out = nullptr;  // optional multiplier export (vboc_download_multipliers)
     double *work;  // slots * work_doubles
     size_t work_doubles;
     unsigned int *counter;
@@ -125,6 +127,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VB_LB_MINB(MINB)) solve_ke
         if constexpr (STREAM) pb.dir = (B.dir && B.dir[(size_t)b * NQ] == B.dir[(size_t)b * NQ]) ? pb.dir : nullptr;
         pb.x = B.x + (size_t)b * (B.Nmax + 1) * B.nxr, pb.u = B.u + (size_t)b * B.Nmax * nu;
         pb.st = B.st + b;
+        if (B.pi_out) {
+            pb.pi_out = B.pi_out + (size_t)b * B.Nmax * 2 * NQ;
+            pb.lam_out = B.lam_out + (size_t)b * (B.Nmax + 1) * 6 * NQ;
+        }
         sol.solve(pb, B.mode);
         __syncwarp();
         if constexpr (STREAM) {
@@ -236,6 +242,7 @@ struct vboc_solver {
     int *dN;
     double *dxg, *dug, *dp, *dlbx0, *dubx0, *dlbx, *dubx, *dlbxN, *dubxN, *dlbu, *dubu, *ddir, *dh;
     double *dx, *du, *dwork;
+    double *dpi, *dlam;  // multiplier export, allocated by vboc_export_multipliers
     vboc_stats *dst;
     unsigned int *dcounter;
     size_t work_doubles;
@@ -346,6 +353,9 @@ void vboc_default_opts(int family, vboc_opts *o) {
     }
 }
 
+static int solver_create_impl(vboc_solver *s, int n_dof, int family, int batch_capacity, int N_max, int device);
+static int stream_create_impl(vboc_stream *s, int n_dof, int family, int capacity, int N_max, int device);
+
 static size_t work_doubles_for(int n, int Nmax) {
     return n == 1 ? Work<1>::doubles(Nmax) : (n == 2 ? Work<2>::doubles(Nmax) : Work<3>::doubles(Nmax));
 }
@@ -360,6 +370,19 @@ int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device
     CUDA_OK(cudaSetDevice(device));
     vboc_solver *s = new vboc_solver();
     memset(s, 0, sizeof(*s));
+    // single cleanup path: a failure below frees whatever the half-built handle already owns
+    int rc = solver_create_impl(s, n_dof, family, batch_capacity, N_max, device);
+    if (rc) {
+        const std::string keep = g_err;
+        vboc_destroy(s);
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+static int solver_create_impl(vboc_solver *s, int n_dof, int family, int batch_capacity, int N_max, int device) {
     s->n = n_dof, s->family = family, s->cap = batch_capacity, s->Nmax = N_max, s->device = device;
     s->nxr = 2 * n_dof + (family == VBOC_FAMILY_VBOC), s->nu = n_dof;
     s->last_ms = -1.0;
@@ -417,7 +440,6 @@ int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device
     CUDA_OK(cudaEventCreate(&s->ev1));
     s->stage_bytes = B * (N_max + 1) * nxr * sizeof(double);
     CUDA_OK(cudaMallocHost((void **)&s->stage, s->stage_bytes));
-    *out = s;
     return 0;
 }
 
@@ -426,7 +448,7 @@ void vboc_destroy(vboc_solver *s) {
     cudaSetDevice(s->device);
     void *ptrs[] = {s->dN,    s->dxg,   s->dug,  s->dp,   s->dlbx0, s->dubx0, s->dlbx,
                     s->dubx,  s->dlbxN, s->dubxN, s->dlbu, s->dubu,  s->ddir,  s->dh,
-                    s->dx,    s->du,    s->dst,  s->dcounter, s->dwork};
+                    s->dx,    s->du,    s->dst,  s->dcounter, s->dwork, s->dpi, s->dlam};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (s->dwork_free_dt) cudaFree(s->dwork_free_dt);
@@ -614,6 +636,7 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
     B.lbxN = s->dlbxN, B.ubxN = s->dubxN, B.lbu = s->dlbu, B.ubu = s->dubu;
     B.dir = s->has_dir ? s->ddir : nullptr, B.h = s->dh;
     B.x = s->dx, B.u = s->du, B.st = s->dst;
+    B.pi_out = s->dpi, B.lam_out = s->dpi ? s->dlam : nullptr;
     B.work = s->dwork, B.work_doubles = s->work_doubles, B.counter = s->dcounter;
     B.mode = mode, B.opts = s->opts;
     CUDA_OK(cudaMemsetAsync(s->dcounter, 0, sizeof(unsigned int), s->stream));
@@ -665,6 +688,34 @@ int vboc_download(vboc_solver *s, double *x, double *u, vboc_stats *stats) {
     if (x && (rc = d2h(s, x, s->dx, B * (s->Nmax + 1) * s->nxr * sizeof(double)))) return rc;
     if (u && (rc = d2h(s, u, s->du, B * s->Nmax * s->nu * sizeof(double)))) return rc;
     if (stats && (rc = d2h(s, stats, s->dst, B * sizeof(vboc_stats)))) return rc;
+    return 0;
+}
+
+int vboc_export_multipliers(vboc_solver *s, int on) {
+    if (!s) return fail(VBOC_ERR_ARG, "vboc_export_multipliers: null handle");
+    CUDA_OK(cudaSetDevice(s->device));
+    if (on && (s->lane_kernel || (s->n == 1 && s->family == VBOC_FAMILY_VBOC && s->free_dt)))
+        return fail(VBOC_ERR_UNSUPPORTED, "vboc_export_multipliers: served by the warp kernel only");
+    if (on && !s->dpi) {
+        const size_t B = s->cap;
+        CUDA_OK(cudaMalloc((void **)&s->dpi, B * s->Nmax * 2 * s->n * sizeof(double)));
+        CUDA_OK(cudaMalloc((void **)&s->dlam, B * (s->Nmax + 1) * 6 * s->n * sizeof(double)));
+    } else if (!on && s->dpi) {
+        cudaFree(s->dpi), cudaFree(s->dlam);
+        s->dpi = s->dlam = nullptr;
+    }
+    return 0;
+}
+
+int vboc_download_multipliers(vboc_solver *s, double *pi, double *lam) {
+    if (!s || !s->batch) return fail(VBOC_ERR_ARG, "vboc_download_multipliers: nothing resident");
+    if (!s->dpi) return fail(VBOC_ERR_ARG, "vboc_download_multipliers: call vboc_export_multipliers(s, 1) before the solve");
+    if (s->free_dt) return fail(VBOC_ERR_UNSUPPORTED, "vboc_download_multipliers: not available for the free-dt kernel");
+    CUDA_OK(cudaSetDevice(s->device));
+    const size_t B = s->batch;
+    int rc;
+    if (pi && (rc = d2h(s, pi, s->dpi, B * s->Nmax * 2 * s->n * sizeof(double)))) return rc;
+    if (lam && (rc = d2h(s, lam, s->dlam, B * (s->Nmax + 1) * 6 * s->n * sizeof(double)))) return rc;
     return 0;
 }
 
@@ -823,25 +874,49 @@ int vboc_fp64_peak(int device, double *tflops) {
     return 0;
 }
 
+// vboc_sim_step keeps one grow-on-demand set of device / pinned buffers and a non-blocking stream per device
+// (the drop-in simulator shim calls it once per RK4 step: no cudaMalloc, no legacy-stream serialisation per call)
+namespace {
+struct SimCache {
+    double *d = nullptr, *h = nullptr;  // device / pinned host: x | u | x_next
+    size_t rows = 0;
+    cudaStream_t stream = nullptr;
+};
+SimCache g_sim[64];
+std::mutex g_sim_mu;
+}  // namespace
+
 int vboc_sim_step(int n_dof, int device, int batch, const double *x, const double *u, double T,
                   double *x_next) {
-    if (n_dof < 1 || n_dof > 3 || batch < 1 || !x || !u || !x_next)
+    if (n_dof < 1 || n_dof > 3 || batch < 1 || !x || !u || !x_next || device < 0 || device >= 64)
         return fail(VBOC_ERR_ARG, "vboc_sim_step: bad argument");
     CUDA_OK(cudaSetDevice(device));
-    double *dx = nullptr, *du = nullptr, *dxn = nullptr;
-    size_t nx = 2 * n_dof, B = batch;
-    CUDA_OK(cudaMalloc((void **)&dx, B * nx * sizeof(double)));
-    CUDA_OK(cudaMalloc((void **)&du, B * n_dof * sizeof(double)));
-    CUDA_OK(cudaMalloc((void **)&dxn, B * nx * sizeof(double)));
-    CUDA_OK(cudaMemcpy(dx, x, B * nx * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(du, u, B * n_dof * sizeof(double), cudaMemcpyHostToDevice));
+    std::lock_guard<std::mutex> lock(g_sim_mu);
+    SimCache &c = g_sim[device];
+    const size_t B = batch, nx = 2 * n_dof, per_row = 5 * 3;  // doubles per row, sized for n = 3
+    if (!c.stream) CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (B > c.rows) {
+        if (c.d) cudaFree(c.d);
+        if (c.h) cudaFreeHost(c.h);
+        c.d = c.h = nullptr, c.rows = 0;
+        size_t rows = B < 1024 ? 1024 : B + B / 2;
+        CUDA_OK(cudaMalloc((void **)&c.d, rows * per_row * sizeof(double)));
+        CUDA_OK(cudaMallocHost((void **)&c.h, rows * per_row * sizeof(double)));
+        c.rows = rows;
+    }
+    double *dx = c.d, *du = c.d + B * nx, *dxn = du + B * n_dof;
+    memcpy(c.h, x, B * nx * sizeof(double));
+    memcpy(c.h + B * nx, u, B * n_dof * sizeof(double));
+    CUDA_OK(cudaMemcpyAsync(dx, c.h, B * (nx + n_dof) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     int th = 128, bl = (batch + th - 1) / th;
-    if (n_dof == 1) sim_kernel<1><<<bl, th>>>(batch, dx, du, T, dxn);
-    if (n_dof == 2) sim_kernel<2><<<bl, th>>>(batch, dx, du, T, dxn);
-    if (n_dof == 3) sim_kernel<3><<<bl, th>>>(batch, dx, du, T, dxn);
+    if (n_dof == 1) sim_kernel<1><<<bl, th, 0, c.stream>>>(batch, dx, du, T, dxn);
+    if (n_dof == 2) sim_kernel<2><<<bl, th, 0, c.stream>>>(batch, dx, du, T, dxn);
+    if (n_dof == 3) sim_kernel<3><<<bl, th, 0, c.stream>>>(batch, dx, du, T, dxn);
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaMemcpy(x_next, dxn, B * nx * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(dx), cudaFree(du), cudaFree(dxn);
+    double *hxn = c.h + B * (nx + n_dof);
+    CUDA_OK(cudaMemcpyAsync(hxn, dxn, B * nx * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_OK(cudaStreamSynchronize(c.stream));
+    memcpy(x_next, hxn, B * nx * sizeof(double));
     return 0;
 }
 
@@ -854,6 +929,18 @@ int vboc_stream_create(int n_dof, int family, int capacity, int N_max, int devic
     if (device < 0 || device >= ndev) return fail(VBOC_ERR_CUDA, "vboc_stream_create: no such CUDA device");
     CUDA_OK(cudaSetDevice(device));
     vboc_stream *s = new vboc_stream();
+    int rc = stream_create_impl(s, n_dof, family, capacity, N_max, device);
+    if (rc) {
+        const std::string keep = g_err;
+        vboc_stream_destroy(s);
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+static int stream_create_impl(vboc_stream *s, int n_dof, int family, int capacity, int N_max, int device) {
     s->n = n_dof, s->family = family, s->cap = capacity, s->Nmax = N_max, s->device = device;
     s->nxr = 2 * n_dof + (family == VBOC_FAMILY_VBOC), s->nu = n_dof;
     s->launches = s->solved = s->idle_polls = 0;
@@ -911,7 +998,6 @@ int vboc_stream_create(int n_dof, int family, int capacity, int N_max, int devic
     CUDA_OK(cudaMalloc((void **)&s->dcounters, vboc_stream::NREC * sizeof(unsigned int)));
     s->free_slots.reserve(C);
     for (int i = capacity - 1; i >= 0; --i) s->free_slots.push_back(i);
-    *out = s;
     return 0;
 }
 
@@ -929,7 +1015,10 @@ void vboc_stream_destroy(vboc_stream *s) {
         if (s->rec[r].ev) cudaEventDestroy(s->rec[r].ev);
     }
     if (s->sim_stream) cudaStreamDestroy(s->sim_stream);
-    cudaFree(s->dwork), cudaFree(s->ws_mask), cudaFree(s->dcounters);
+    if (s->dwork) cudaFree(s->dwork);
+    if (s->ws_mask) cudaFree(s->ws_mask);
+    if (s->dcounters) cudaFree(s->dcounters);
+    cudaGetLastError();
     delete s;
 }
 
@@ -1003,16 +1092,33 @@ int vboc_stream_submit(vboc_stream *s, int mode, int count, const int *N, const 
     B.work = s->dwork, B.work_doubles = s->work_doubles, B.counter = s->dcounters + r;
     B.mode = mode, B.opts = s->opts;
     B.index = R.index, B.done = s->done, B.ws_mask = s->ws_mask, B.ws_per_sm = s->ws_per_sm;
-    CUDA_OK(cudaMemsetAsync(s->dcounters + r, 0, sizeof(unsigned int), R.stream));
+    // on any failure from here on the slots go back to the free list and the tickets leave `inflight`: nothing
+    // was launched for them, so a poll loop must not wait for them
+    auto rollback = [&]() {
+        for (int b = 0; b < count; ++b) {
+            s->free_slots.push_back(tickets[b]);
+            s->inflight.pop_back();
+        }
+    };
+    cudaError_t e = cudaMemsetAsync(s->dcounters + r, 0, sizeof(unsigned int), R.stream);
+    if (e != cudaSuccess) {
+        rollback();
+        return fail(VBOC_ERR_CUDA, std::string("vboc_stream_submit: counter reset: ") + cudaGetErrorString(e));
+    }
     int grid = (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA, maxg = s->num_sms * 5;
     if (grid > maxg) grid = maxg;
-    cudaError_t e = cudaErrorInvalidValue;
+    e = cudaErrorInvalidValue;
 #define GO(NQ, FAM) \
     if (n == NQ && s->family == FAM) e = launch_stream<NQ, FAM>(grid, R.stream, B);
     VB_ALL_SYSTEMS(GO)
 #undef GO
-    if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("solve_kernel (stream) launch: ") + cudaGetErrorString(e));
-    CUDA_OK(cudaEventRecord(R.ev, R.stream));
+    if (e != cudaSuccess) {
+        rollback();
+        return fail(VBOC_ERR_CUDA, std::string("solve_kernel (stream) launch: ") + cudaGetErrorString(e));
+    }
+    // the kernel is queued: if the event cannot be recorded the record is simply treated as busy until the stream
+    // drains (cudaEventQuery on an unrecorded event reports success)
+    if ((e = cudaEventRecord(R.ev, R.stream)) != cudaSuccess) cudaStreamSynchronize(R.stream);
     R.busy = true;
     ++s->launches;
     return 0;

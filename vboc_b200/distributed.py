@@ -51,3 +51,24 @@ def global_topk(values, k, index_offset=0):
     allc = all_gather_rows(cand)
     order = np.argsort(-allc[:, 0], kind="stable")[:k]
     return allc[order, 1].astype(np.int64), allc[order, 0]
+
+
+def sharded_topk(values, k):
+    """Global top-k over a pool that is SHARDED across the ranks (every rank holds different rows).  Returns the
+    LOCAL indices (into this rank's `values`, largest index first, as AL/triplependulum_al.py:267-270 sorts them)
+    of the entries of the global top-k that live on this rank, and the global maximum of the selected values.
+    The ranks' selections are disjoint and their sizes add up to min(k, total pool size), so each rank labels and
+    removes its own part.  Without an initialised process group this is the plain single-process selection."""
+    values = np.asarray(values, dtype=np.float64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        kk = min(k, values.shape[0])
+        loc = np.argpartition(-values, kk - 1)[:kk] if kk > 0 else np.empty(0, dtype=np.int64)
+        return np.sort(loc)[::-1].astype(np.int64), (float(values[loc].max()) if kk else 0.0)
+    world, rank, dev = dist.get_world_size(), dist.get_rank(), _dev()
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([values.shape[0]], dtype=torch.int64, device=dev))
+    counts = [int(c.item()) for c in counts]
+    lo = sum(counts[:rank])
+    gidx, gval = global_topk(values, k, index_offset=lo)
+    mine = gidx[(gidx >= lo) & (gidx < lo + counts[rank])] - lo
+    return np.sort(mine)[::-1].astype(np.int64), (float(gval.max()) if gval.size else 0.0)

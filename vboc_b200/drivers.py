@@ -16,7 +16,9 @@ stays per-problem and faithful while the solves of a round run side by side on t
 The random draws follow the reference's distributions but come from a per-problem Philox stream
 (seed, problem id): the reference uses the unseeded `random` module.
 Deliberate deviation: `testing` retries forever in the reference (`while True`); here a problem gives up
-after `max_solves` solves and is reported as failed.
+after `max_solves` solves and is reported as failed (None): only a point that passed the reference's
+convergence test `cost_new > round(cost) - tol` is ever returned.  Likewise a horizon that would grow past N_CAP
+ends the problem as failed instead of accepting the capped solve.
 """
 import numpy as np
 
@@ -60,11 +62,14 @@ def _pm(rng):
     return -1.0 if rng.random() < 0.5 else 1.0
 
 
-def _pack(n, reqs):
-    """SolveReq list -> batched problem dict for `BatchSolver.solve` (stage N takes the last guess row)."""
+def _pack(n, reqs, N_max=N_CAP):
+    """SolveReq list -> batched problem dict for `BatchSolver.solve` / `StreamSolver.submit` (stage N takes the last
+    guess row); guesses are laid out for a solver created with horizon capacity `N_max`."""
     B, nx = len(reqs), 2 * n + 1
+    if any(r.N > N_max for r in reqs):
+        raise ValueError(f"a request needs horizon {max(r.N for r in reqs)} but the solver was created for N_max = {N_max}")
     bp = dict(n=n, family="vboc", N=np.array([r.N for r in reqs], dtype=np.int32),
-              x_guess=np.zeros((B, N_CAP + 1, nx)), u_guess=np.zeros((B, N_CAP, n)),
+              x_guess=np.zeros((B, N_max + 1, nx)), u_guess=np.zeros((B, N_max, n)),
               p=np.stack([r.p for r in reqs]))
     for b, r in enumerate(reqs):
         xg, ug = pr.expand_guess(r.x_guess, r.u_guess, r.N)
@@ -96,7 +101,7 @@ def run_workers(n, workers, solver, sim_step, stats=None):
         sol_ids = [i for i, r in pending.items() if isinstance(r, SolveReq)]
         sim_ids = [i for i, r in pending.items() if isinstance(r, SimReq)]
         if sol_ids:
-            out = solver.solve(_pack(n, [pending[i] for i in sol_ids]), MODE_SQP)
+            out = solver.solve(_pack(n, [pending[i] for i in sol_ids], getattr(solver, "N_max", N_CAP)), MODE_SQP)
             for b, i in enumerate(sol_ids):
                 N = pending[i].N
                 answers[i] = SolveAns(int(out["status"][b]), float(out["cost"][b]), out["x"][b, :N + 1].copy(),
@@ -157,16 +162,19 @@ def run_workers_stream(n, workers, ssol, stats=None, max_launch=1024, idle_sleep
         if sols:
             k = min(len(sols), ssol.free_slots, max_launch)
             if k:
-                tk = ssol.submit(_pack(n, [r for _, r in sols[:k]]), MODE_SQP)
+                tk = ssol.submit(_pack(n, [r for _, r in sols[:k]], getattr(ssol, "N_max", N_CAP)), MODE_SQP)
                 for t, (i, r) in zip(tk.tolist(), sols[:k]):
                     owner[t] = (i, r.N)
             ready.extend(sols[k:])  # no free slot yet: next turn
         if sims:
             T = sims[0][1].T
-            Xn = ssol.sim_step(np.stack([r.x for _, r in sims]), np.stack([r.u for _, r in sims]), T)
+            cap = getattr(ssol, "cap", len(sims))  # vboc_stream_sim_step takes at most `capacity` rows per call
+            for lo in range(0, len(sims), cap):
+                part = sims[lo:lo + cap]
+                Xn = ssol.sim_step(np.stack([r.x for _, r in part]), np.stack([r.u for _, r in part]), T)
+                for b, (i, _) in enumerate(part):
+                    advance(i, Xn[b])
             nsim += len(sims)
-            for b, (i, _) in enumerate(sims):
-                advance(i, Xn[b])
         done = ssol.poll()
         for t in done:
             i, N = owner.pop(t)
@@ -225,16 +233,16 @@ def testing_worker(n, rng, N0=100, dt_sym=1e-2, max_solves=60):
 
     N, cost = N0, 1e6
     xg, ug = fresh(N)
-    last = None
     for _ in range(max_solves):
         p = np.concatenate([ran / np.linalg.norm(ran), [0.0]])
         lb0 = np.concatenate([q_init, np.full(n, -mdl.dthetamax), [dt_sym]])
         ub0 = np.concatenate([q_init, np.full(n, mdl.dthetamax), [dt_sym]])
         ans = yield SolveReq(N, xg, ug, p, q_lb, q_ub, u_lb, u_ub, lb0, ub0, q_fin_lb, q_fin_ub)
         if ans.status == 0:
-            last = ans
-            if ans.cost > round(cost, digits) - cost_tol or N + 1 > N_CAP:
+            if ans.cost > round(cost, digits) - cost_tol:
                 return ans.x[0, :2 * n].copy()
+            if N + 1 > N_CAP:
+                return None
             cost = ans.cost
             xg, ug = _extended_guess(ans, n)
             N += 1
@@ -244,7 +252,7 @@ def testing_worker(n, rng, N0=100, dt_sym=1e-2, max_solves=60):
             q_init = q_init + np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
             xg, ug = fresh(N)
             cost = 1e6
-    return None if last is None else last.x[0, :2 * n].copy()
+    return None
 
 
 def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
@@ -288,9 +296,11 @@ def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
     for _ in range(10):
         ans = yield SolveReq(N, xg, ug, p, q_lb, q_ub, u_lb, u_ub, lb0, ub0, q_fin_lb, q_fin_ub)
         if ans.status == 0:
-            if ans.cost > cost - tol or N + 1 > N_CAP:
+            if ans.cost > cost - tol:
                 sol = ans
                 break
+            if N + 1 > N_CAP:
+                return None
             cost = ans.cost
             xg, ug = _extended_guess(ans, n)
             N += 1
@@ -348,8 +358,10 @@ def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
                         break
                     sub = ans
                     norm_new = np.linalg.norm(ans.x[0, n:2 * n])
-                    if norm_new < norm_bef + tol or N_t + 1 > N_CAP:
+                    if norm_new < norm_bef + tol:
                         ok = True
+                        break
+                    if N_t + 1 > N_CAP:
                         break
                     norm_bef = norm_new
                     xg, ug = _extended_guess(ans, n)
@@ -536,36 +548,37 @@ def al_label_batch(n, X, device=0, solver=None, N=100, Tf=1.0, x_guess=None):
     return labels, traj
 
 
-def al_query(net, pool, mean, std, B, world_offset=0):
+def al_query(net, pool, mean, std, B, sharded=False):
     """Entropy of sigmoid(model((x - mean)/std)) over the unlabeled pool on the GPU and the B most
-    uncertain samples, largest index first (AL/triplependulum_al.py:253-281).  Returns (indices, entropy
-    of the pool); under torch.distributed the selection is global (`distributed.global_topk`)."""
-    import torch.distributed as dist
+    uncertain samples, largest index first (AL/triplependulum_al.py:253-281).  Returns (indices into `pool`,
+    entropy of `pool`, largest selected entropy).
+
+    sharded=False: `pool` is the whole pool (single process, or every rank holds a replica and selects the same
+    rows).  sharded=True (under torch.distributed): every rank holds a DIFFERENT shard of the pool; the selection
+    is the global top-B (`distributed.sharded_topk`) and the returned indices are this rank's part of it, local
+    to its shard -- the ranks' parts are disjoint and add up to B."""
     from . import distributed as vd
     from . import nn as vnn
     _, etp = net.entropy(pool, mean, std)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        idx, _ = vd.global_topk(etp, B, index_offset=world_offset)
-        return sorted(idx.tolist(), reverse=True), etp
-    return vnn.select_max_entropy(etp, B), etp
+    if sharded:
+        idx, emax = vd.sharded_topk(etp, B)
+        return idx.tolist(), etp, emax
+    idx = vnn.select_max_entropy(etp, B)
+    return idx, etp, float(np.max(etp[idx])) if len(idx) else 0.0
 
 
 # ------------------------------------------------------------------------------------------------
-# on-disk formats read by the untouched *_comparison.py scripts (SURVEY 8(f)3)
+# on-disk formats read by the untouched *_comparison.py scripts (SURVEY 8(f)3): vboc_b200/io.py
 def save_testdata(n, X_test, directory="."):
     """`np.save('data3_test.npy', X_test)` (triplependulum_testdata.py:144-145): rows [q, v]."""
-    import os
-    path = os.path.join(directory, f"data{n}_test.npy")
-    np.save(path, np.asarray(X_test, dtype=float))
-    return path
+    from . import io as vio
+    return vio.save_testdata(n, X_test, directory)
 
 
 def save_vboc_data(n, X_save, directory="."):
     """`np.save('data_3dof_vboc', np.asarray(X_save))` (VBOC/triplependulum_vboc.py:575-584): rows [q, v]."""
-    import os
-    path = os.path.join(directory, f"data_{n}dof_vboc.npy")
-    np.save(path, np.asarray(X_save, dtype=float))
-    return path
+    from . import io as vio
+    return vio.save_run(n, "vboc", directory, data=X_save)["data"]
 
 
 def pendulum_data_generation(device=0, backend=None, stats=None):

@@ -103,6 +103,18 @@ class BatchSolver:
         check(_lib.lib().vboc_download(self._h, _dp(x), _dp(u), st.ctypes.data_as(C.POINTER(Stats))))
         return self._result(x, u, st)
 
+    def export_multipliers(self, on=True):
+        """Have the next solves keep the KKT multipliers of the returned iterates (`multipliers()`)."""
+        check(_lib.lib().vboc_export_multipliers(self._h, int(bool(on))))
+
+    def multipliers(self):
+        """pi (B, N_max, 2n), lam (B, N_max+1, 3n, 2) of the last solve, see include/vboc_b200.h."""
+        B, n = self._batch, self.n
+        pi = np.zeros((B, self.N_max, 2 * n))
+        lam = np.zeros((B, self.N_max + 1, 3 * n, 2))
+        check(_lib.lib().vboc_download_multipliers(self._h, _dp(pi), _dp(lam)))
+        return pi, lam
+
     def solve(self, bp, mode=MODE_SQP):
         """upload + solve + download in one C call (host buffers in, host buffers out)."""
         B, Nv, arrs, Tf = self._pack(bp)

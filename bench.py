@@ -22,8 +22,11 @@ of the boundary states afterwards, as the drivers do before the NN fit).
 `pipeline`: (N = 1) the full `data_generation` of `--pipeline` problems -- extension loop, retries, sub-OCP
            chains, twin simulation (VBOC/triplependulum_vboc.py:19-370) -- through the streaming engine
            (`vboc_stream_*`): SURVEY 8(d)(ii).
-`cpu_baseline`: the oracle port (kind "port": acados is not installable here) on the host cores, on a
-           bounded sample of the same workload.
+`cpu_baseline`: the CPU arm on the host cores, on a bounded sample of the same workload.  kind "acados" when
+           `acados_template` + the reference scripts are importable on the box (tools/acados_arm.py: the UNMODIFIED
+           reference classes under Pool(os.cpu_count())); otherwise kind "port": the oracle restatement, compiled on
+           the box with -O3 -march=native and compile-time dimensions (oracle/Makefile, `_native/`), OpenMP over
+           problems -- "restated CPU baseline, not acados".
 """
 import argparse
 import json
@@ -41,6 +44,7 @@ import numpy as np  # noqa: E402
 N_DOF, N_STAGES = 3, 100
 F_LIN, F_IPM, F_SIM = 7348.0, 3395.0, 856.0  # SURVEY.md 8(d), VBOC n = 3, per stage
 METRIC = "converged OCP solves/sec, 3-DOF VBOC"
+TRAFFIC_FILE = "r2_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_traffic.json")) else "r1_traffic.json"
 UNIT = "OCP/s"
 
 
@@ -88,15 +92,78 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WORKLOAD = "triplependulum_vboc single SQP solve per problem, N=100, nx=7, nu=3"
+
+
+def shared_config(batch, world):
+    """`config` of BOTH arms (the reference arm runs on our arm's config; what differs between the arms -- the
+    bounded CPU sample, the stream overlap -- is reported outside `config`)."""
+    return {"workload": WORKLOAD, "batch_per_gpu_per_step": batch, "parallelism": f"dp{world} (index-sharded problems)",
+            "sampler": "vboc_b200.problems.sample_vboc (VBOC/triplependulum_vboc.py:33-103), Philox seeds 10000*(rank+1)+step"}
+
+
+_CPU_KIND = None
+
+
+def cpu_backend():
+    """('acados', None) when the reference's own solver path can run here, else ('port', oracle module) with the
+    natively compiled baseline build of the oracle."""
+    global _CPU_KIND
+    if _CPU_KIND is None:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import acados_arm
+        ok, why = acados_arm.available()
+        if ok:
+            _CPU_KIND = ("acados", acados_arm, why)
+        else:
+            from oracle import oracle as orc
+            try:
+                orc.use_native_baseline_build()
+                how = "oracle port, -O3 -march=native, compile-time dimensions"
+            except Exception as e:  # no compiler on the box: the portable build
+                orc.lib()
+                how = f"oracle port, portable -O2 build (native build failed: {e})"
+            _CPU_KIND = ("port", orc, how + "; acados probe: " + why)
+    return _CPU_KIND
+
+
 def cpu_sample(nprob, seed, threads):
-    """Time the oracle port on `nprob` problems of the workload with `threads` host threads."""
-    from oracle import oracle as orc
+    """Time the CPU arm on `nprob` problems of the workload with `threads` host threads / processes."""
     from vboc_b200 import problems as pr
+    kind, mod, _ = cpu_backend()
     bp = pr.sample_vboc(N_DOF, nprob, seed=seed)
+    if kind == "acados":
+        r = mod.solve_batch(N_DOF, bp, processes=threads)
+        return int((r["status"] == 0).sum()), r["wall_s"]
     t0 = time.perf_counter()
-    r = orc.solve_batch(N_DOF, orc.FAMILY_VBOC, orc.MODE_SQP, bp, nthreads=threads)
+    r = mod.solve_batch(N_DOF, mod.FAMILY_VBOC, mod.MODE_SQP, bp, nthreads=threads)
     dt = time.perf_counter() - t0
     return int((r["status"] == 0).sum()), dt
+
+
+def cpu_pipeline(nprob, seed):
+    """The full `data_generation` (VBOC/triplependulum_vboc.py:19-370) of `nprob` problems on the host cores: the
+    same generators as the GPU pipeline leg over the oracle backend, every round's solves as one OpenMP batch."""
+    from vboc_b200 import drivers
+    kind, mod, _ = cpu_backend()
+    if kind != "port":
+        return None
+
+    class Backend:
+        N_max = drivers.N_CAP
+
+        def solve(self, bp, mode):
+            return mod.solve_batch(N_DOF, mod.FAMILY_VBOC, mode, bp)
+
+    def sim(n, X, U, T):
+        return np.stack([mod.rk4(n, 1, x, u, T) for x, u in zip(X, U)])
+
+    st = {}
+    t0 = time.perf_counter()
+    rows = drivers.data_generation_batch(N_DOF, nprob, seed=seed, backend=(Backend(), sim), stats=st)
+    dt = time.perf_counter() - t0
+    return {"problems": nprob, "rows": int(rows.shape[0]), "solves": st.get("solves", 0), "converged": st.get("converged", 0),
+            "wall_s": dt, "converged_solves_per_s": st.get("converged", 0) / dt, "rounds": st.get("rounds")}
 
 
 def run_reference(args):
@@ -106,25 +173,38 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nprob = args.cpu_sample
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kind, _, how = cpu_backend()
+    # bounded sample per step: >= 64 problems per core so that the heavy tail of the iteration counts (0.5 % of the
+    # problems run all 1000 SQP iterations = seconds on one core) amortises, sized from a short calibration so that
+    # the whole --steps/--warmup run stays within a few minutes
+    nprob = args.cpu_sample if args.cpu_sample > 0 else 64 * cores
+    c0, dt0 = cpu_sample(4 * cores, 899, cores)
+    rate0 = max(4 * cores / dt0, 1e-9)
+    budget = args.cpu_budget / max(args.steps + args.warmup, 1)
+    if args.cpu_sample <= 0 and nprob / rate0 > budget:
+        nprob = max(8 * cores, int(rate0 * budget))
     for i in range(args.warmup):
-        cpu_sample(min(nprob, 2 * cores), 900 + i, cores)
+        cpu_sample(nprob, 900 + i, cores)
     conv, tot = 0, 0.0
     for i in range(args.steps):
-        c, dt = cpu_sample(nprob, 1000 + i, cores)
+        c, dt = cpu_sample(nprob, 10_000 + i, cores)  # rank 0's problems of the GPU arm, first nprob of each step
         conv += c
         tot += dt
     v = conv / tot
-    sample = f"{nprob} problems per step x {args.steps} steps, seeded like the GPU arm"
-    print(json.dumps({
+    sample = (f"{nprob} problems per step (= {nprob / cores:.0f} per core) x {args.steps} steps: the first {nprob} problems "
+              f"of each of rank 0's GPU-arm steps; {how}")
+    line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "triplependulum_vboc single SQP solve per problem, N=100, nx=7, nu=3",
-                   "batch_per_step": nprob, "parallelism": f"openmp{cores}"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": shared_config(args.batch, world),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if args.pipeline > 0 and kind == "port":
+        line["pipeline"] = cpu_pipeline(min(args.pipeline, args.cpu_pipeline), 77)
+    print(json.dumps(line))
 
 
 def main():
@@ -134,7 +214,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32768, help="problems per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=256, help="problems of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="problems per step of the CPU arm (0 = 64 per host core, shrunk to fit --cpu-budget)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the whole CPU arm may take")
+    ap.add_argument("--cpu-pipeline", type=int, default=256, help="problems of the CPU data_generation pipeline leg")
     ap.add_argument("--pipeline", type=int, default=1024,
                     help="problems of the data_generation pipeline leg (N = 1 only; 0 = skip)")
     args = ap.parse_args()
@@ -260,11 +343,12 @@ def main():
                     "t_done_p50_p90_p99_max_s": pst.get("t_done_p50_p90_p99_max")}
     if rank == 0:
         cores = os.cpu_count() or 1
-        c_conv, c_dt = cpu_sample(args.cpu_sample, 4242, cores) if world == 1 else (0, 1.0)
+        c_n = args.cpu_sample if args.cpu_sample > 0 else 32 * cores   # ~10-30 s of CPU work
+        c_conv, c_dt = cpu_sample(c_n, 10_000, cores) if world == 1 else (0, 1.0)
         achieved_tf = flops / t_dev_local / 1e12  # rank 0's launches
         traffic = hbm = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
             ipm_iters = float(sum(int(o["qp_iter"].sum()) for o in outs))
             total_bytes = tj["dram_bytes_per_ipm_iteration"] * ipm_iters
             traffic = total_bytes / args.steps
@@ -278,31 +362,38 @@ def main():
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)" if peak_gbs else "unavailable",
                    "bytes_per_ipm_iteration": tj["dram_bytes_per_ipm_iteration"],
                    "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one bounded launch "
-                             "(profiles/r1_traffic.json) scaled by this launch's IPM iterations"}
+                             f"(profiles/{TRAFFIC_FILE}) scaled by this launch's IPM iterations"}
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": conv / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "triplependulum_vboc single SQP solve per problem, N=100, nx=7, nu=3",
-                       "batch_per_gpu_per_step": B, "parallelism": f"dp{world} (index-sharded problems)",
-                       "l2": "inputs + per-warp workspaces (>700 MB) exceed the 126 MB L2; no flush needed",
-                       "steps_overlap": "the K timed steps run on K CUDA streams (K solver handles); elapsed = first launch to last completion",
-                       "converged_fraction": conv / (B * world * args.steps)},
+            "config": shared_config(B, world),
+            "run": {"l2": "inputs + per-warp workspaces (>700 MB) exceed the 126 MB L2; no flush needed",
+                    "steps_overlap": "the K timed steps run on K CUDA streams (K solver handles); elapsed = first launch to last completion",
+                    "converged_fraction": conv / (B * world * args.steps)},
             "e2e": {"value": conv_e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                         "peak_source": "DFMA micro-benchmark run live by bench.py (MEASURED_PEAKS.json has no FP64 entry)",
+                         "peak_source": "DFMA micro-benchmark run live by bench.py before the timed region "
+                                        "(vboc_fp64_peak; MEASURED_PEAKS.json has no FP64 entry); nominal 148 SMs x 64 FMA/clk x 2 x "
+                                        "1.965 GHz = 37.2",
                          "flops_per_launch": flops / args.steps, "hbm": hbm},
             "clocks": clocks,
         }
         if pipeline is not None:
             line["pipeline"] = pipeline
         if world == 1:
-            line["cpu_baseline"] = {"value": c_conv / c_dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample} problems of the same sampler, oracle port, OpenMP over problems"}
+            kind, _, how = cpu_backend()
+            line["cpu_baseline"] = {"value": c_conv / c_dt, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"the first {c_n} problems (= {c_n // cores} per core) of step 0 of this run; {how}"}
+            if pipeline is not None and args.cpu_pipeline > 0:
+                cp = cpu_pipeline(min(args.pipeline, args.cpu_pipeline), 77)
+                if cp:
+                    line["pipeline"]["cpu"] = cp
+                    line["pipeline"]["vs_cpu"] = pipeline["converged_solves_per_s"] / cp["converged_solves_per_s"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -57,6 +57,21 @@ def lib():
     return _LIB
 
 
+def use_native_baseline_build():
+    """Switch this module to oracle/_native/liboracle_n3.so, built here and now with -O3 -march=native and the 3-DOF
+    dimensions fixed at compile time (the CPU-baseline build; bench.py only).  Results follow the same algorithm
+    but are not bit-identical to liboracle.so (FMA contraction), so the parity tests never use it."""
+    global _LIB
+    so = os.path.join(_HERE, "_native", "liboracle_n3.so")
+    subprocess.check_call(["make", "-C", _HERE, "-B", "_native/liboracle_n3.so"], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
+    _LIB = C.CDLL(so)
+    _LIB.orc_solve.restype = C.c_int
+    _LIB.orc_solve_batch.restype = C.c_int
+    _LIB.orc_first_qp.restype = C.c_int
+    return so
+
+
 def _p(a):
     if a is None:
         return None

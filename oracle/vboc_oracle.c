@@ -29,6 +29,18 @@
 #include <omp.h>
 #endif
 
+/* CPU-baseline build (bench.py --impl reference): -DORC_FIXED_N=<n> fixes the dimensions of the dt-eliminated
+ * problem at compile time so that the small dense loops unroll and vectorise; prepare() refuses anything else.
+ * The default build reads them from the problem (all systems, both families, free dt). */
+#ifdef ORC_FIXED_N
+#define DIM_NX(P) (2 * ORC_FIXED_N)
+#define DIM_NU(P) (ORC_FIXED_N)
+#define DIM_NZ(P) (3 * ORC_FIXED_N)
+#else
+#define DIM_NX(P) ((P)->nx)
+#define DIM_NU(P) ((P)->nu)
+#define DIM_NZ(P) ((P)->nz)
+#endif
 #define NXI 7  /* max internal nx (3 q + 3 v + dt) */
 #define NUI 3
 #define NZI 10 /* nu + nx */
@@ -293,7 +305,7 @@ static inline int bnd_active(const iocp *P, int k, int i) {
 
 /* e = (I - Z0 Z0')(x - c0): violation of the stage-0 equalities at the state x */
 static void eq0_violation(const iocp *P, const double *x, double *e) {
-    int nx = P->nx;
+    int nx = DIM_NX(P);
     double y[NXI];
     for (int c = 0; c < P->ny0; ++c) {
         double s = 0.0;
@@ -308,7 +320,7 @@ static void eq0_violation(const iocp *P, const double *x, double *e) {
 }
 /* v <- Z0 Z0' v */
 static void proj0(const iocp *P, double *v) {
-    int nx = P->nx;
+    int nx = DIM_NX(P);
     double y[NXI], o[NXI];
     for (int c = 0; c < P->ny0; ++c) {
         double s = 0.0;
@@ -383,7 +395,7 @@ static void work_free(work *W) {
 /* Stage cost (acados cost modules EXTERNAL / LINEAR_LS scaled by the time step [restated])     */
 /* ------------------------------------------------------------------------------------------ */
 static double total_cost(const iocp *P, const double *X, const double *U) {
-    int n = P->n, nx = P->nx, N = P->N;
+    int n = P->n, nx = DIM_NX(P), N = P->N;
     (void)U;
     double c = 0.0;
     if (P->family == ORC_FAMILY_VBOC) {
@@ -405,7 +417,7 @@ static double total_cost(const iocp *P, const double *X, const double *U) {
 }
 
 static void cost_grad_hess(const iocp *P, const orc_opts *o, work *W) {
-    int n = P->n, nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int n = P->n, nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     for (int k = 0; k <= N; ++k) {
         double *g = W->g + k * nz, *hd = W->hd + k * nz;
         for (int i = 0; i < nz; ++i) g[i] = 0.0, hd[i] = o->levenberg_marquardt;
@@ -427,7 +439,7 @@ static void cost_grad_hess(const iocp *P, const orc_opts *o, work *W) {
 /* Linearisation: multiple shooting over all intervals                                          */
 /* ------------------------------------------------------------------------------------------ */
 static void linearize(const iocp *P, work *W) {
-    int nx = P->nx, nu = P->nu, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), N = P->N;
     for (int k = 0; k < N; ++k) {
         double phi[NXI];
         integrate(P->n, P->dts, P->h, W->X + k * nx, W->U + k * nu, phi, W->A + k * nx * nx,
@@ -446,7 +458,7 @@ static void linearize(const iocp *P, work *W) {
 /* matching gradient components (stage 0: only the Z0-reduced gradient counts).                  */
 /* ------------------------------------------------------------------------------------------ */
 static void nlp_residuals(const iocp *P, work *W, double *rs, double *re, double *ri, double *rc) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     double s = 0, e = 0, in = 0, c = 0;
     for (int k = 0; k <= N; ++k) {
         int sc = stage_class(P, k);
@@ -552,7 +564,7 @@ static int small_inverse(int n, double G[NUI][NUI], double Gi[NUI][NUI]) {
 
 /* hh: (N+1)*nz effective Hessian diagonal (hd + Gamma_l + Gamma_u). */
 static int riccati_factor(const iocp *P, work *W, const double *hh) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     for (int i = 0; i < nx; ++i) W->hhN[i] = hh[N * nz + nu + i];
     for (int k = N - 1; k >= 0; --k) {
         const double *A = W->A + k * nx * nx, *B = W->B + k * nx * nu;
@@ -642,7 +654,7 @@ static int riccati_factor(const iocp *P, work *W, const double *hh) {
 
 /* y = P_k x with P_k = Lxx_k Lxx_k' (factor stored in stage k) */
 static void P_times(const work *W, int k, const double *x, double *y) {
-    int nx = W->nx, nu = W->nu, nz = W->nz;
+    int nx = DIM_NX(W), nu = DIM_NU(W), nz = DIM_NZ(W);
     const double *L = W->L + k * nz * nz;
     double t1[NXI];
     for (int i = 0; i < nx; ++i) {
@@ -661,7 +673,7 @@ static void P_times(const work *W, int k, const double *x, double *y) {
  * outputs dv ((N+1)*nz) and dpi (N*nx). */
 static void riccati_solve(const iocp *P, work *W, const double *r, const double *beta,
                           const double *e0, const double *eN, double *dv, double *dpi) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     double *pv = W->pv, *yv = W->yv;
     for (int i = 0; i < nx; ++i) pv[N * nx + i] = W->rN[i] = r[N * nz + nu + i];
     for (int k = N - 1; k >= 0; --k) {
@@ -798,7 +810,7 @@ static void riccati_solve(const iocp *P, work *W, const double *r, const double 
 /* ------------------------------------------------------------------------------------------ */
 static double qp_residuals(const iocp *P, work *W, double *ng_, double *nb_, double *nd_,
                            double *nm_) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     const double *lbd = W->lbd, *ubd = W->ubd;
     double rg = 0, rb = 0, rd = 0, rm = 0, mu = 0;
     int nc = 0;
@@ -863,7 +875,7 @@ static double qp_residuals(const iocp *P, work *W, double *ng_, double *nb_, dou
  * and the maximum step alpha. */
 static double ipm_step(const iocp *P, const orc_opts *o, work *W, int factor, const double *rm,
                        int *ok) {
-    int nz = P->nz, N = P->N;
+    int nz = DIM_NZ(P), N = P->N;
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nz; ++i) {
             double h = W->hd[k * nz + i] + o->qp_reg_prim, r = W->rg[k * nz + i];
@@ -885,7 +897,7 @@ static double ipm_step(const iocp *P, const orc_opts *o, work *W, int factor, co
     }
     riccati_solve(P, W, W->rr, W->rb, W->e0, W->eN, W->dv, W->dpi);
     if (P->nb) {
-        int nx = P->nx, nu = P->nu, nb = P->nb, S = N + 1;
+        int nx = DIM_NX(P), nu = DIM_NU(P), nb = P->nb, S = N + 1;
         double ze[NXI] = {0};
         if (factor) /* basis solves: unit terminal gradient on one fixed component, everything else zero */
             for (int j = 0; j < nb; ++j) {
@@ -940,7 +952,7 @@ static double ipm_step(const iocp *P, const orc_opts *o, work *W, int factor, co
 }
 
 static double mu_aff(const iocp *P, work *W, double alpha) {
-    int nz = P->nz, N = P->N, nc = 0;
+    int nz = DIM_NZ(P), N = P->N, nc = 0;
     double mu = 0;
     for (int k = 0; k <= N; ++k)
         for (int i = 0; i < nz; ++i) {
@@ -955,7 +967,7 @@ static double mu_aff(const iocp *P, work *W, double alpha) {
 }
 
 static int ipm_solve(const iocp *P, const orc_opts *o, work *W, int *iters) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     double *lbd = W->lbd, *ubd = W->ubd;
     const double thr0 = 0.1; /* HPIPM d_ocp_qp_init_var cold start threshold [restated] */
     /* bounds of the step: lb - z <= dz <= ub - z */
@@ -1082,7 +1094,7 @@ static int ipm_solve(const iocp *P, const orc_opts *o, work *W, int *iters) {
 /*   cost + sum w_dyn |gap| + sum w_ineq max(0, violation) (+ the eliminated equalities)         */
 /* ------------------------------------------------------------------------------------------ */
 static double merit(const iocp *P, work *W, const double *X, const double *U) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     double m = total_cost(P, X, U);
     for (int k = 0; k < N; ++k) {
         double phi[NXI];
@@ -1108,7 +1120,7 @@ static double merit(const iocp *P, work *W, const double *X, const double *U) {
 }
 
 static double line_search(const iocp *P, const orc_opts *o, work *W, int sqp_iter, int *evals) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     /* merit weights from the QP multipliers: first iteration w = |mult|, afterwards
      * w = max(|mult|, (w + |mult|)/2)  (acados ocp_nlp_line_search [restated]) */
 #define WUPD(w, a) (w) = sqp_iter == 0 ? (a) : fmax((a), 0.5 * ((w) + (a)))
@@ -1140,7 +1152,7 @@ static double line_search(const iocp *P, const orc_opts *o, work *W, int sqp_ite
 /* SQP / RTI driver (acados ocp_nlp_sqp / ocp_nlp_sqp_rti [restated])                            */
 /* ------------------------------------------------------------------------------------------ */
 static int sqp(const iocp *P, const orc_opts *o, int mode, work *W, orc_stats *st) {
-    int nx = P->nx, nu = P->nu, nz = P->nz, N = P->N;
+    int nx = DIM_NX(P), nu = DIM_NU(P), nz = DIM_NZ(P), N = P->N;
     memset(st, 0, sizeof(*st));
     int status = ORC_MAXITER;
     int it = 0;
@@ -1259,6 +1271,9 @@ static work *prepare(prep *pp, int n, int family, int N, const double *xg, const
     }
     P->nx = 2 * n + P->dts;
     P->nz = P->nx + P->nu;
+#ifdef ORC_FIXED_N
+    if (n != ORC_FIXED_N || P->dts) return NULL; /* this build serves one dimension set only */
+#endif
     int nx = P->nx, nu = P->nu;
     const double *lbs[3] = {lbx0, lbx, lbxN}, *ubs[3] = {ubx0, ubx, ubxN};
     for (int s = 0; s < 3; ++s) {

@@ -27,12 +27,12 @@ def test_testing_batch_matches_oracle_run(oracle, n):
     assert np.abs(ref - out).max() < 1e-5
 
 
-def test_data_generation_matches_oracle_run(oracle):
-    n = 3
+@pytest.mark.parametrize("n,num", [(3, 8), (2, 16)])
+def test_data_generation_matches_oracle_run(oracle, n, num):
     ob = OracleBackend(oracle, n)
     s1, s2 = {}, {}
-    ref = drivers.data_generation_batch(n, 6, seed=4, backend=(ob, ob.sim), stats=s1)
-    out = drivers.data_generation_batch(n, 6, seed=4, stats=s2)
+    ref = drivers.data_generation_batch(n, num, seed=4, backend=(ob, ob.sim), stats=s1)
+    out = drivers.data_generation_batch(n, num, seed=4, stats=s2)
     assert s1["solves"] == s2["solves"] and s1["problems_ok"] == s2["problems_ok"]
     assert ref.shape == out.shape
     assert np.abs(ref - out).max() < 1e-5
@@ -64,8 +64,8 @@ def test_al_query_selects_most_uncertain():
     m.linear_relu_stack = nn.Sequential(nn.Linear(4, 300), nn.ReLU(), nn.Linear(300, 300), nn.ReLU(), nn.Linear(300, 2))
     net = vnn.MLP.from_torch(m)
     pool = np.random.default_rng(1).uniform(-3, 3, (5000, 4)).astype(np.float32)
-    idx, etp = drivers.al_query(net, pool, 0.0, 1.0, 50)
-    assert len(idx) == 50 and idx == sorted(idx, reverse=True)
+    idx, etp, emax = drivers.al_query(net, pool, 0.0, 1.0, 50)
+    assert len(idx) == 50 and idx == sorted(idx, reverse=True) and emax == etp[idx].max()
     assert etp[idx].min() >= np.sort(etp)[-50] - 1e-7
     net.close()
 
@@ -75,3 +75,39 @@ def test_pendulum_data_generation_matches_oracle_run(oracle):
     ref = drivers.pendulum_data_generation(backend=(ob, ob.sim))
     out = drivers.pendulum_data_generation()
     assert ref.shape == out.shape and np.abs(ref - out).max() < 1e-5
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_al_labels_from_nn_guess_match_oracle(oracle, n):
+    """`compute_problem_nnguess` at scale (AL/triplependulum_class_al.py:171-201, AL/triplependulum_al.py:45-62): the
+    RTI solve started from the trajectory a guess network predicts -- the steady-state labeller of every AL round
+    after the first.  A guess network is fitted for a few hundred Adam steps on the trajectories of a first labelled
+    batch (constant guess), then 2048 NEW states are labelled from its predictions on the GPU and by the oracle."""
+    import torch
+    from vboc_b200 import al_loop, problems as pr
+    from vboc_b200.shim.my_nn import NeuralNetCLS
+    torch.manual_seed(0)
+    N, nx = 100, 2 * n
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    X0 = pr.sample_al(n, 2048, seed=21)["x0"]
+    lab0, traj0 = drivers.al_label_batch(n, X0)
+    v = lab0 == 1
+    assert v.sum() > 100
+    mean, std = float(X0.mean()), float(X0.std())
+    guess = NeuralNetCLS(nx, 300, N * nx).to(dev)   # same stack as the reference's guess net (no final ReLU)
+    opt = torch.optim.Adam(guess.parameters(), lr=1e-3)
+    Xt = traj0[v].reshape(int(v.sum()), -1)
+    al_loop.fit_minibatch(guess, opt, torch.nn.MSELoss(), Xt[:, :nx], Xt[:, nx:], mean, std, n_minibatch=256,
+                          loss_stop=1e-3, it_max=400, normalize_targets=True)
+    X1 = pr.sample_al(n, 2048, seed=22)["x0"]
+    mdl = pr.Model(n)
+    X1 = X1[np.all(np.abs(X1[:, n:]) <= mdl.dthetamax, axis=1)]
+    xg = al_loop.predict_guess(guess, X1, mean, std, N, nx)
+    assert np.abs(xg[:, 1:] - xg[:, :1]).max() > 1e-3          # a genuinely non-constant guess
+    labels, traj = drivers.al_label_batch(n, X1, x_guess=xg)
+    ref = oracle.solve_batch(n, 1, 1, pr.al_problems(n, X1, x_guess=xg))
+    want = np.where(ref["status"] == 0, 1, np.where(ref["status"] == 4, 0, 2))
+    assert (labels == want).mean() >= 0.999, np.where(labels != want)[0]
+    both = (labels == 1) & (want == 1)
+    assert both.sum() > 50
+    assert np.abs(traj[both] - ref["x"][both][:, :N + 1]).max() < 1e-6

@@ -72,7 +72,8 @@ def test_sim_integrator_like_the_driver(oracle):
     assert np.abs(sim.acados_integrator.get("x") - oracle.rk4(3, 1, x, u, 1e-2)).max() < 1e-12
 
 
-@pytest.mark.parametrize("mod,cls,n", [("doublependulum_class_al", "OCPdoublependulumINIT", 2),
+@pytest.mark.parametrize("mod,cls,n", [("pendulum_class_al", "OCPpendulumINIT", 1),
+                                       ("doublependulum_class_al", "OCPdoublependulumINIT", 2),
                                        ("triplependulum_class_al", "OCPtriplependulumINIT", 3)])
 def test_compute_problem_labels(oracle, mod, cls, n):
     """AL/triplependulum_al.py:24-41 `testing`"""
@@ -148,3 +149,34 @@ def test_pendulum_vboc_free_dt_like_the_driver():
         assert np.abs(np.diff(x[:, 2])).max() < 1e-9          # dt is constant along the horizon (dt' = 0)
         assert abs(abs(x[0, 1]) - v_max) < 1e-6               # the velocity limit is reachable from the far limit
         assert abs(ocp.ocp_solver.get_cost() - (cd * x[0, 1] + x[:N, 2].sum())) < 1e-9
+
+
+@pytest.mark.parametrize("mod,cls,n", [("doublependulum_class_al", "OCPdoublependulumINIT", 2),
+                                       ("triplependulum_class_al", "OCPtriplependulumINIT", 3)])
+def test_compute_problem_nnguess_labels(oracle, mod, cls, n):
+    """AL/triplependulum_class_al.py:171-201 called as AL/triplependulum_al.py:45-62 does: the guess network's
+    (de-normalised) output becomes the state guess of stages 1..N; label and trajectory against the oracle started
+    from the same guess."""
+    import torch
+    from vboc_b200.shim.my_nn import NeuralNetCLS
+    torch.manual_seed(n)
+    ocp = getattr(_load("AL", mod), cls)()
+    N, nx = ocp.N, 2 * n
+    model = NeuralNetCLS(nx, 64, N * nx)
+    with torch.no_grad():           # small weights: the predicted trajectory stays near the (normalised) state mean
+        for prm in model.parameters():
+            prm.mul_(0.05)
+    bp = pr.sample_al(n, 10, seed=8)
+    X = bp["x0"][np.all(np.abs(bp["x0"][:, n:]) <= ocp.dthetamax, axis=1)]
+    mean, std = torch.tensor(float(X.mean())), torch.tensor(float(X.std()))
+    for x0 in X:
+        lab = ocp.compute_problem_nnguess(x0[:n], x0[n:], model, mean, std)
+        with torch.no_grad():
+            out = (model((torch.Tensor([x0.tolist()]) - mean) / std) * std + mean).numpy().reshape(N, nx)
+        xg = np.vstack([x0[None], out.astype(np.float64)])[None]
+        ref = oracle.solve_batch(n, 1, 1, pr.al_problems(n, x0[None], x_guess=xg))
+        want = 1 if ref["status"][0] == 0 else (0 if ref["status"][0] == 4 else 2)
+        assert lab == want
+        if lab == 1:
+            traj = np.array([ocp.ocp_solver.get(i, "x") for i in range(N + 1)])
+            assert np.abs(traj - ref["x"][0]).max() < 1e-6

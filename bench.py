@@ -19,9 +19,10 @@ of the boundary states afterwards, as the drivers do before the NN fit).
            `traffic` = DRAM bytes per launch: the ncu-measured bytes per IPM iteration of this kernel
            (profiles/r1_traffic.json, one `ncu --set full` capture) times the IPM iterations of the launch;
            `hbm` restates the same launch against the measured copy bandwidth (MEASURED_PEAKS.json).
-`pipeline`: (N = 1) the full `data_generation` of `--pipeline` problems -- extension loop, retries, sub-OCP
-           chains, twin simulation (VBOC/triplependulum_vboc.py:19-370) -- through the streaming engine
-           (`vboc_stream_*`): SURVEY 8(d)(ii).
+`pipeline`: the full `data_generation` of `--pipeline` problems per GPU -- extension loop, retries, sub-OCP
+           chains, twin simulation (VBOC/triplependulum_vboc.py:19-370) -- as the per-problem state machine on the
+           device (`vboc_datagen_run`): SURVEY 8(d)(ii), 8(f)1; at N = 1 with the same generators on the CPU arm
+           beside it (`pipeline.cpu`).
 `cpu_baseline`: the CPU arm on the host cores, on a bounded sample of the same workload.  kind "acados" when
            `acados_template` + the reference scripts are importable on the box (tools/acados_arm.py: the UNMODIFIED
            reference classes under Pool(os.cpu_count())); otherwise kind "port": the oracle restatement, compiled on
@@ -219,7 +220,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the whole CPU arm may take")
     ap.add_argument("--cpu-pipeline", type=int, default=256, help="problems of the CPU data_generation pipeline leg")
     ap.add_argument("--pipeline", type=int, default=1024,
-                    help="problems of the data_generation pipeline leg (N = 1 only; 0 = skip)")
+                    help="problems PER GPU of the data_generation pipeline leg (0 = skip); the reference's round is 1000")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -328,19 +329,40 @@ def main():
     for sv in sols:  # free the batch workspaces before the pipeline leg
         sv.close()
     pipeline = None
-    if world == 1 and args.pipeline > 0:
+    if args.pipeline > 0:
+        # the full data_generation of `--pipeline` problems PER GPU (weak scaling) as the per-problem
+        # state machine on the device (vboc_datagen_run): host -> inputs, one launch, rows back; then the all-gather of
+        # the rows the drivers do before the NN fit.  Timed host to host, max over ranks.
         from vboc_b200 import drivers
         pst = {}
+        dgen = engine.DataGenerator(N_DOF, args.pipeline, device=local)
+        drivers.data_generation_device(N_DOF, min(64, args.pipeline), seed=76, device=local, dgen=dgen)  # warm-up
+        inp = drivers.dg_inputs(N_DOF, args.pipeline, 77, first=rank * args.pipeline)
+        barrier()
         tp0 = time.perf_counter()
-        rows = drivers.data_generation_stream(N_DOF, args.pipeline, seed=77, device=local, stats=pst)
+        rows, dst = dgen.run(inp)
+        if world > 1:
+            from vboc_b200 import distributed as vd
+            rows = vd.all_gather_rows(rows)
+        barrier()
         tp = time.perf_counter() - tp0
-        pipeline = {"workload": "triplependulum_vboc data_generation (extensions, retries, sub-OCP chains, twin simulation) "
-                                "through the streaming engine",
-                    "problems": args.pipeline, "rows": int(rows.shape[0]), "solves": pst.get("solves", 0),
-                    "converged": pst.get("converged", 0), "sim_steps": pst.get("sim_steps", 0), "wall_s": tp,
-                    "converged_solves_per_s": pst.get("converged", 0) / tp,
-                    "solves_per_s_first_90pct": pst.get("solves_per_s_first_90pct"),
-                    "t_done_p50_p90_p99_max_s": pst.get("t_done_p50_p90_p99_max")}
+        kms = dgen.last_kernel_ms
+        dgen.close()
+        pagg = torch.tensor([tp, float(dst["solves"].sum()), float(dst["converged"].sum()), float(dst["sim_steps"].sum()),
+                             float((dst["status"] != 1).sum())], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmx = pagg[:1].clone()
+            dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+            psum = pagg[1:].clone()
+            dist.all_reduce(psum, op=dist.ReduceOp.SUM)
+            tp, (p_solves, p_conv, p_sim, p_ok) = float(tmx.item()), psum.tolist()
+        else:
+            _, p_solves, p_conv, p_sim, p_ok = pagg.tolist()
+        pipeline = {"workload": "triplependulum_vboc data_generation (extensions, retries, sub-OCP chains, twin simulation): "
+                                "per-problem state machine on the device, one warp per problem (vboc_datagen_run)",
+                    "problems_per_gpu": args.pipeline, "problems": args.pipeline * world, "problems_ok": int(p_ok),
+                    "rows": int(rows.shape[0]), "solves": int(p_solves), "converged": int(p_conv), "sim_steps": int(p_sim),
+                    "wall_s": tp, "kernel_ms_rank0": kms, "converged_solves_per_s": p_conv / tp}
     if rank == 0:
         cores = os.cpu_count() or 1
         c_n = args.cpu_sample if args.cpu_sample > 0 else 32 * cores   # ~10-30 s of CPU work

@@ -21,6 +21,8 @@
  *                                (VBOC/triplependulum_vboc.py:399-402)
  *   vboc_upload / vboc_solve_resident / vboc_download
  *                                the same three steps split so that inputs may stay resident in HBM
+ *   vboc_datagen_*               data_generation(v) as a per-problem state machine on the device
+ *                                VBOC/triplependulum_vboc.py:19-370, VBOC/doublependulum_vboc.py:19-402
  *   vboc_stream_*                the same solves as a ticket queue (see below): the drivers' per-problem loops
  *                                VBOC/triplependulum_vboc.py:107-136, 232-289, triplependulum_testdata.py:77-125
  *   vboc_mlp_create / _forward   model_dir(...) / sigmoid(model(...)) + entropy: my_nn.py:4-34,
@@ -169,6 +171,34 @@ int vboc_stream_submit(vboc_stream *s, int mode, int count, const int *N, const 
 int vboc_stream_poll(vboc_stream *s, int max, int *tickets);
 int vboc_stream_fetch(vboc_stream *s, int ticket, double *x, double *u, vboc_stats *stats);
 int vboc_stream_sim_step(vboc_stream *s, int count, const double *x, const double *u, double T, double *x_next);
+
+/*
+ * Device-resident data generation: `Pool.map(data_generation, range(count))` (VBOC/triplependulum_vboc.py:399-405,
+ * VBOC/doublependulum_vboc.py:431-437) as ONE kernel -- one warp runs the whole per-problem state machine of
+ * `data_generation(v)` (:19-370): the extreme trajectory with horizon extension and restarts, the walk along it with
+ * its sub-OCP chains and the simulated unviable twin, the row filter.  No host round trip between the solves.
+ * The random draws of the reference's worker are inputs (the host draws them from a seeded per-problem stream):
+ *   joint_sel [count]            the joint that starts at a position limit
+ *   p         [count][n+1]       cost direction (unit vector, then 0)
+ *   lb0, ub0  [count][2n+1]      bounds of the initial state (fixed positions lb == ub, velocities +-v_max, dt)
+ *   retry     [count][10][n+1]   per restart: perturbation added to the direction (n) and to the free positions (1)
+ * Outputs: rows [rows_capacity][2n]: the saved states [q, v] of all problems back to back in problem order (problem b
+ * owns stats[b].n_rows of them; at most VBOC_DG_ROWS_MAX each), *total_rows their number, and the per-problem
+ * counters.  n_dof 2 or 3; N0 = initial horizon (100), dt = pinned time step (1e-2), tol (1e-3).
+ */
+#define VBOC_DG_ROWS_MAX 258
+typedef struct {
+    int status;    /* 0 rows returned, 1 no extreme trajectory found (the generator returns None), 2 row buffer overflow */
+    int n_rows, solves, converged, sim_steps, sqp_iter, qp_iter, pad_;
+} vboc_dg_stats;
+typedef struct vboc_datagen vboc_datagen;
+int vboc_datagen_create(int n_dof, int capacity, int device, vboc_datagen **out);
+void vboc_datagen_destroy(vboc_datagen *s);
+int vboc_datagen_set_opts(vboc_datagen *s, const vboc_opts *o);
+int vboc_datagen_run(vboc_datagen *s, int count, int N0, double dt, double tol, const int *joint_sel, const double *p,
+                     const double *lb0, const double *ub0, const double *retry, double *rows, long long rows_capacity,
+                     long long *total_rows, vboc_dg_stats *stats);
+double vboc_datagen_last_kernel_ms(vboc_datagen *s);
 
 /* One classical RK4 step of the unscaled 2n-state model: x_next = Phi_T(x, u).  HOST arrays
  * x [batch][2n], u [batch][n], x_next [batch][2n]. */

@@ -42,15 +42,22 @@ def test_status0_is_certified_by_the_exit_test(tag, n, B, seed):
 
 @pytest.mark.parametrize("n,B", [(3, 2048), (2, 2048)])
 def test_al_labels_are_lp_feasibility(n, B):
+    """Label 1 with a CONVERGED QP (qp_status 0) must be LP-feasible, label 0 (the IPM stopped on the minimum step,
+    qp_status 2 -> acados status 4) must be LP-infeasible.  A third outcome exists in the reference's semantics:
+    the IPM runs out of its 50 iterations (qp_status 1), which acados tolerates (ocp_nlp_sqp_rti returns success
+    for ACADOS_MAXITER of the QP solver), so `compute_problem` returns 1 although nothing was decided; these are
+    counted, bounded, and listed in profiles/r2_certify.md."""
     from vboc_b200._lib import MODE_RTI
     bp = pr.sample_al(n, B, seed=4245)
     out = certify._solve_with_multipliers(n, "al", bp, MODE_RTI)
     lab = out["status"] == 0
     assert set(np.unique(out["status"]).tolist()) <= {0, 4}
     feas = certify.al_lp_labels(n, np.asarray(bp["lbx0"])[:, :2 * n])
-    agree = lab == feas
+    decided = out["qp_status"] != 1
+    assert decided.mean() >= 0.99, decided.mean()
+    agree = (lab == feas)[decided]
     assert lab.any() and (~lab).any()
-    assert agree.mean() >= 0.999, (agree.mean(), np.where(~agree)[0])
+    assert agree.mean() >= 0.999, (agree.mean(), np.where(decided & (lab != feas))[0])
 
 
 @pytest.mark.parametrize("n", [2, 3])

@@ -169,10 +169,14 @@ def al_lp_feasible(n, x0, N=100, Tf=1.0, x_guess=None, u_guess=None):
     nx, h = 2 * n, Tf / N
     xg = np.tile(np.concatenate([x0[:n], np.zeros(n)]), (N + 1, 1)) if x_guess is None else np.array(x_guess, dtype=float)
     ug = np.zeros((N, n)) if u_guess is None else np.asarray(u_guess, dtype=float)
-    xg[0] = x0                                                  # constraints.x0 (lbx_0 = ubx_0 = x0)
+    # acados linearises at the ITERATE, i.e. at the guess -- also at stage 0, where `compute_problem` sets the guess
+    # [q0, 0] (AL/triplependulum_class_al.py:157-160) while the bounds lbx_0 = ubx_0 pin x_0 = [q0, v0]: the QP's
+    # first step is dx_0 = x0 - guess_0, not zero
+    dx0 = np.asarray(x0, dtype=float) - xg[0]
     xn, A, Bm = rk4_jac(n, xg[:N], ug, h)
     b = xn - xg[1:]                                             # gap:  dx_{k+1} = A dx_k + B du_k + b
-    # variables: dx_1..dx_N (nx each), du_0..du_{N-1} (n each); dx_0 = 0
+    b[0] = b[0] + A[0] @ dx0
+    # variables: dx_1..dx_N (nx each), du_0..du_{N-1} (n each); dx_0 is data
     nvx = N * nx
     rows, cols, vals, rhs = [], [], [], []
     for k in range(N):
@@ -349,18 +353,24 @@ def main():
     lab = np.where(out["status"] == 0, 1, np.where(out["status"] == 4, 0, 2))
     X0 = np.asarray(bp["lbx0"])[:, :2 * n]
     feas = al_lp_labels(n, X0)
+    decided = out["qp_status"] != 1
     agree = (lab == 1) == feas
     log(f"## C5 `triplependulum_al.py`: {a.c5} states, label vs LP feasibility (HiGHS) of the linearised problem\n")
     log(f"* engine: viable {int((lab == 1).sum())}, unviable {int((lab == 0).sum())}, other {int((lab == 2).sum())}; "
         f"LP feasible {int(feas.sum())}")
-    log(f"* agreement: **{agree.mean() * 100:.3f} %** ({int((~agree).sum())} disagreements)\n")
-    if (~agree).any():
+    log(f"* QP decided by the IPM (converged -> label 1, minimum step -> status 4 -> label 0): {int(decided.sum())} states, "
+        f"agreement with LP feasibility **{agree[decided].mean() * 100:.3f} %** ({int((~agree[decided]).sum())} disagreements)")
+    log(f"* QP NOT decided (the IPM used up its 50 iterations; acados tolerates the QP solver's max-iter status, so "
+        f"`compute_problem` returns 1): {int((~decided).sum())} states, of which LP-feasible {int(feas[~decided].sum())}. "
+        "These labels are the reference's semantics, not a feasibility statement.\n")
+    if (~agree[decided]).any() or (~decided).any():
         log("| state | engine label (qp status, ipm iterations) | LP feasible | explanation |")
         log("|---|---|---|---|")
-        for b in np.where(~agree)[0]:
-            log(f"| {b} | {lab[b]} ({out['qp_status'][b]}, {out['qp_iter'][b]}) | {bool(feas[b])} | QP at the edge of feasibility: "
-                "the interior-point method needs a strictly feasible interior; a feasible set of (near) zero width ends in "
-                "the minimum step / iteration limit |")
+        for b in np.where(~agree | ~decided)[0]:
+            why = ("iteration limit of the QP solver reached: label 1 by acados' tolerance of max-iter, feasibility undecided"
+                   if not decided[b] else
+                   "QP at the edge of feasibility: a feasible set of (near) zero width has no interior for the IPM")
+            log(f"| {b} | {lab[b]} ({out['qp_status'][b]}, {out['qp_iter'][b]}) | {bool(feas[b])} | {why} |")
         log("")
 
 

@@ -9,6 +9,7 @@
 
 #include "../../vboc_b200/csrc/ocp_warp.h"
 #include "../../vboc_b200/csrc/ocp_lane.h"
+#include "../../vboc_b200/csrc/datagen_warp.h"
 
 using namespace vboc;
 
@@ -135,4 +136,40 @@ extern "C" int emu_solve_batch(int n, int family, int mode, int batch, int Nmax,
     GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
 #undef GO
     return -1;
+}
+
+// the device-resident data generation state machine (datagen_warp.h) on the host
+template <int NQ>
+static void run_datagen(int count, const DgParams &P, const vboc_opts *o, const int *js, const double *p, const double *lb0,
+                        const double *ub0, const double *retry, double *rows, DgCounters *cnt) {
+#pragma omp parallel
+    {
+        std::vector<double> buf(Work<NQ>::TOTAL + DgWork<NQ>::TOTAL);
+        Smem<NQ> *sm = new Smem<NQ>();
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < count; ++b) {
+            Work<NQ> w;
+            w.carve(buf.data(), DG_N_CAP);
+            DgWork<NQ> g;
+            g.carve(buf.data() + Work<NQ>::TOTAL);
+            WarpSolver<NQ, VBOC_FAMILY_VBOC> sol(*sm, w, *o);
+            DataGen<NQ> dg(sol, g, P);
+            DgIO<NQ> io{js, p, lb0, ub0, retry, rows, cnt};
+            dg.run(io, b);
+            cnt[b] = dg.c;
+        }
+        delete sm;
+    }
+}
+
+extern "C" int emu_datagen_run(int n, int count, int N0, double dt, double tol, const int *js, const double *p,
+                               const double *lb0, const double *ub0, const double *retry, const vboc_opts *o,
+                               double *rows, DgCounters *cnt) {
+    DgParams P;
+    P.N0 = N0, P.dt = dt, P.tol = tol;
+    P.q_min = M_PI - M_PI / 4, P.q_max = M_PI + M_PI / 4, P.v_max = 10.0, P.u_max = 10.0;
+    if (n == 2) run_datagen<2>(count, P, o, js, p, lb0, ub0, retry, rows, cnt);
+    else if (n == 3) run_datagen<3>(count, P, o, js, p, lb0, ub0, retry, rows, cnt);
+    else return -1;
+    return 0;
 }

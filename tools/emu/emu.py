@@ -69,3 +69,26 @@ def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False):
     return dict(pi=pi, lam=lam, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),
                 ls_evals=f("ls_evals"), qp_status=f("qp_status"),
                 res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))
+
+
+class DgStats(C.Structure):
+    _fields_ = [("status", C.c_int), ("n_rows", C.c_int), ("solves", C.c_int), ("converged", C.c_int),
+                ("sim_steps", C.c_int), ("sqp_iter", C.c_int), ("qp_iter", C.c_int), ("pad_", C.c_int)]
+
+
+ROWS_MAX = 258
+
+
+def datagen_run(n, inp, opts, N0=100, dt=1e-2, tol=1e-3):
+    """The device state machine (vboc_b200/csrc/datagen_warp.h) on the host.  inp: drivers.dg_inputs(...).
+    Returns (list of per-problem row arrays or None, stats list)."""
+    lib = C.CDLL(os.path.join(_HERE, "libemu.so"))
+    B = len(inp["joint_sel"])
+    rows = np.zeros((B, ROWS_MAX, 2 * n))
+    st = (DgStats * B)()
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    rc = lib.emu_datagen_run(n, B, N0, C.c_double(dt), C.c_double(tol), ip(inp["joint_sel"]), _p(inp["p"]), _p(inp["lb0"]),
+                             _p(inp["ub0"]), _p(inp["retry"]), C.byref(opts), _p(rows), st)
+    assert rc == 0
+    out = [rows[b, :st[b].n_rows].copy() if st[b].status != 1 else None for b in range(B)]
+    return out, [dict((f, getattr(s_, f)) for f, _ in DgStats._fields_) for s_ in st]

@@ -21,6 +21,7 @@ EXPORTS = (
     "vboc_download", "vboc_last_kernel_ms", "vboc_export_multipliers", "vboc_download_multipliers",
     "vboc_stream_create", "vboc_stream_destroy", "vboc_stream_set_opts", "vboc_stream_free_slots",
     "vboc_stream_pending", "vboc_stream_submit", "vboc_stream_poll", "vboc_stream_fetch", "vboc_stream_sim_step",
+    "vboc_datagen_create", "vboc_datagen_destroy", "vboc_datagen_set_opts", "vboc_datagen_run", "vboc_datagen_last_kernel_ms",
     "vboc_sim_step", "vboc_mlp_create", "vboc_mlp_destroy", "vboc_mlp_forward", "vboc_mlp_last_kernel_ms", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
 )
 
@@ -45,6 +46,15 @@ class Stats(C.Structure):
         ("qp_status", C.c_int), ("pad_", C.c_int), ("cost", C.c_double),
         ("res_stat", C.c_double), ("res_eq", C.c_double), ("res_ineq", C.c_double), ("res_comp", C.c_double),
     ]
+
+
+class DgStats(C.Structure):
+    """vboc_dg_stats"""
+    _fields_ = [("status", C.c_int), ("n_rows", C.c_int), ("solves", C.c_int), ("converged", C.c_int),
+                ("sim_steps", C.c_int), ("sqp_iter", C.c_int), ("qp_iter", C.c_int), ("pad_", C.c_int)]
+
+
+DG_ROWS_MAX = 258
 
 
 class VbocError(RuntimeError):
@@ -94,6 +104,14 @@ def lib():
         L.vboc_stream_poll.argtypes = [vp, C.c_int, ip]
         L.vboc_stream_fetch.argtypes = [vp, C.c_int, dp, dp, C.POINTER(Stats)]
         L.vboc_stream_sim_step.argtypes = [vp, C.c_int, dp, dp, C.c_double, dp]
+        L.vboc_datagen_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.vboc_datagen_destroy.argtypes = [vp]
+        L.vboc_datagen_destroy.restype = None
+        L.vboc_datagen_set_opts.argtypes = [vp, C.POINTER(Opts)]
+        L.vboc_datagen_run.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, ip, dp, dp, dp, dp, dp, C.c_longlong,
+                                       C.POINTER(C.c_longlong), C.POINTER(DgStats)]
+        L.vboc_datagen_last_kernel_ms.argtypes = [vp]
+        L.vboc_datagen_last_kernel_ms.restype = C.c_double
         fp = C.POINTER(C.c_float)
         L.vboc_mlp_create.argtypes = [C.c_int] * 5 + [fp] * 6 + [C.POINTER(vp)]
         L.vboc_mlp_destroy.argtypes = [vp]

@@ -21,6 +21,7 @@
 #include "mlp_tc.cuh"
 #include "ocp_lane.h"
 #include "ocp_warp.h"
+#include "datagen_warp.h"
 
 using namespace vboc;
 
@@ -227,6 +228,43 @@ __global__ void nsmid_kernel(unsigned int *out) {
     unsigned int v;
     asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
     *out = v;
+}
+
+// datagen_kernel: one warp = one data_generation(v) problem, start to finish (datagen_warp.h).  Persistent CTAs,
+// problems handed out by a global counter like the solves of solve_kernel.
+template <int NQ>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) datagen_kernel(const DgIO<NQ> io, int count, const DgParams P,
+                                                                      const vboc_opts opts, double *work,
+                                                                      size_t work_doubles, unsigned int *counter) {
+    __shared__ Smem<NQ> smem[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * WARPS_PER_CTA + warp;
+    double *base = work + (size_t)slot * work_doubles;
+    Work<NQ> w;
+    w.carve(base, DG_N_CAP);
+    DgWork<NQ> g;
+    g.carve(base + Work<NQ>::TOTAL);
+    WarpSolver<NQ, VBOC_FAMILY_VBOC> sol(smem[warp], w, opts);
+    DataGen<NQ> dg(sol, g, P);
+    for (;;) {
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned)count) break;
+        dg.run(io, (int)b);
+        __syncwarp();
+        if (lane == 0) io.cnt[b] = dg.c;
+        __syncwarp();
+    }
+}
+
+// gathers the saved rows of all problems into one contiguous array (problem order)
+__global__ void dg_compact_kernel(const double *rows, const DgCounters *cnt, const long long *off, double *out, int nx) {
+    const int b = blockIdx.x;
+    const size_t n = (size_t)cnt[b].n_rows * nx;
+    const double *src = rows + (size_t)b * DG_ROWS_MAX * nx;
+    double *dst = out + (size_t)off[b] * nx;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
 }  // namespace
@@ -871,6 +909,175 @@ int vboc_fp64_peak(int device, double *tflops) {
     }
     cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(out);
     *tflops = best;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Device-resident data generation (include/vboc_b200.h: vboc_datagen_*)
+struct vboc_datagen {
+    int n, cap, device, grid;
+    vboc_opts opts;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int *djs;
+    double *dp, *dlb0, *dub0, *dretry, *drows, *dwork;
+    DgCounters *dcnt;
+    unsigned int *dcounter;
+    size_t work_doubles;
+    char *stage;  // pinned staging
+    size_t stage_bytes;
+    double last_ms;
+};
+static_assert(sizeof(DgCounters) == sizeof(vboc_dg_stats), "vboc_dg_stats mirrors DgCounters");
+
+static int datagen_create_impl(vboc_datagen *s, int n_dof, int capacity, int device) {
+    s->n = n_dof, s->cap = capacity, s->device = device, s->last_ms = -1.0;
+    vboc_default_opts(VBOC_FAMILY_VBOC, &s->opts);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    int max_grid = prop.multiProcessorCount * 5, need = (capacity + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    s->grid = need < max_grid ? need : max_grid;
+    s->work_doubles = n_dof == 2 ? Work<2>::TOTAL + DgWork<2>::TOTAL : Work<3>::TOTAL + DgWork<3>::TOTAL;
+    const size_t B = capacity, nxr = 2 * n_dof + 1, nx = 2 * n_dof;
+    CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&s->ev0));
+    CUDA_OK(cudaEventCreate(&s->ev1));
+    CUDA_OK(cudaMalloc((void **)&s->djs, B * sizeof(int)));
+    CUDA_OK(cudaMalloc((void **)&s->dp, B * (n_dof + 1) * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&s->dlb0, B * nxr * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&s->dub0, B * nxr * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&s->dretry, B * DG_RETRIES * (n_dof + 1) * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&s->drows, B * DG_ROWS_MAX * nx * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&s->dcnt, B * sizeof(DgCounters)));
+    CUDA_OK(cudaMalloc((void **)&s->dcounter, sizeof(unsigned int)));
+    CUDA_OK(cudaMalloc((void **)&s->dwork, (size_t)s->grid * WARPS_PER_CTA * s->work_doubles * sizeof(double)));
+    s->stage_bytes = (size_t)8 << 20;
+    CUDA_OK(cudaMallocHost((void **)&s->stage, s->stage_bytes));
+    return 0;
+}
+
+int vboc_datagen_create(int n_dof, int capacity, int device, vboc_datagen **out) {
+    if (!out || (n_dof != 2 && n_dof != 3) || capacity < 1) return fail(VBOC_ERR_ARG, "vboc_datagen_create: bad argument");
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(VBOC_ERR_CUDA, "vboc_datagen_create: no such CUDA device");
+    CUDA_OK(cudaSetDevice(device));
+    vboc_datagen *s = new vboc_datagen();
+    memset(s, 0, sizeof(*s));
+    int rc = datagen_create_impl(s, n_dof, capacity, device);
+    if (rc) {
+        const std::string keep = g_err;
+        vboc_datagen_destroy(s);
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+void vboc_datagen_destroy(vboc_datagen *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    void *ptrs[] = {s->djs, s->dp, s->dlb0, s->dub0, s->dretry, s->drows, s->dcnt, s->dcounter, s->dwork};
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    if (s->stage) cudaFreeHost(s->stage);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError();
+    delete s;
+}
+
+int vboc_datagen_set_opts(vboc_datagen *s, const vboc_opts *o) {
+    if (!s || !o) return fail(VBOC_ERR_ARG, "vboc_datagen_set_opts: null argument");
+    s->opts = *o;
+    return 0;
+}
+
+double vboc_datagen_last_kernel_ms(vboc_datagen *s) { return s ? s->last_ms : -1.0; }
+
+// pinned-staged copies on the handle's stream
+static int dg_copy(vboc_datagen *s, void *dst, const void *src, size_t bytes, bool to_device) {
+    const char *ps = (const char *)src;
+    char *pd = (char *)dst;
+    while (bytes) {
+        size_t c = bytes < s->stage_bytes ? bytes : s->stage_bytes;
+        if (to_device) {
+            memcpy(s->stage, ps, c);
+            CUDA_OK(cudaMemcpyAsync(pd, s->stage, c, cudaMemcpyHostToDevice, s->stream));
+            CUDA_OK(cudaStreamSynchronize(s->stream));
+        } else {
+            CUDA_OK(cudaMemcpyAsync(s->stage, ps, c, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_OK(cudaStreamSynchronize(s->stream));
+            memcpy(pd, s->stage, c);
+        }
+        ps += c, pd += c, bytes -= c;
+    }
+    return 0;
+}
+
+int vboc_datagen_run(vboc_datagen *s, int count, int N0, double dt, double tol, const int *joint_sel, const double *p,
+                     const double *lb0, const double *ub0, const double *retry, double *rows, long long rows_capacity,
+                     long long *total_rows, vboc_dg_stats *stats) {
+    if (!s) return fail(VBOC_ERR_ARG, "vboc_datagen_run: null handle");
+    if (count < 1 || count > s->cap) return fail(VBOC_ERR_ARG, "vboc_datagen_run: count exceeds capacity");
+    if (!joint_sel || !p || !lb0 || !ub0 || !retry || !rows || !stats || !total_rows)
+        return fail(VBOC_ERR_ARG, "vboc_datagen_run: null array");
+    if (N0 < 2 || N0 > DG_N_CAP || !(dt > 0.0) || !(tol > 0.0)) return fail(VBOC_ERR_ARG, "vboc_datagen_run: bad N0 / dt / tol");
+    const int n = s->n;
+    const size_t B = count, nxr = 2 * n + 1, nx = 2 * n;
+    for (int b = 0; b < count; ++b) {
+        if (joint_sel[b] < 0 || joint_sel[b] >= n) return fail(VBOC_ERR_ARG, "vboc_datagen_run: joint_sel out of range");
+        if (lb0[b * nxr + 2 * n] != dt || ub0[b * nxr + 2 * n] != dt)
+            return fail(VBOC_ERR_UNSUPPORTED, "vboc_datagen_run: the dt state must be pinned to dt");
+    }
+    CUDA_OK(cudaSetDevice(s->device));
+    int rc;
+    if ((rc = dg_copy(s, s->djs, joint_sel, B * sizeof(int), true))) return rc;
+    if ((rc = dg_copy(s, s->dp, p, B * (n + 1) * sizeof(double), true))) return rc;
+    if ((rc = dg_copy(s, s->dlb0, lb0, B * nxr * sizeof(double), true))) return rc;
+    if ((rc = dg_copy(s, s->dub0, ub0, B * nxr * sizeof(double), true))) return rc;
+    if ((rc = dg_copy(s, s->dretry, retry, B * DG_RETRIES * (n + 1) * sizeof(double), true))) return rc;
+    DgParams P;
+    P.N0 = N0, P.dt = dt, P.tol = tol;
+    // limits of the reference models (VBOC/triplependulum_class_vboc.py:90-93, VBOC/doublependulum_class_vboc.py:114-117)
+    P.q_min = M_PI - M_PI / 4, P.q_max = M_PI + M_PI / 4, P.v_max = 10.0, P.u_max = 10.0;
+    CUDA_OK(cudaMemsetAsync(s->dcounter, 0, sizeof(unsigned int), s->stream));
+    CUDA_OK(cudaEventRecord(s->ev0, s->stream));
+    if (n == 2) {
+        DgIO<2> io{s->djs, s->dp, s->dlb0, s->dub0, s->dretry, s->drows, s->dcnt};
+        datagen_kernel<2><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(io, count, P, s->opts, s->dwork, s->work_doubles,
+                                                                       s->dcounter);
+    } else {
+        DgIO<3> io{s->djs, s->dp, s->dlb0, s->dub0, s->dretry, s->drows, s->dcnt};
+        datagen_kernel<3><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(io, count, P, s->opts, s->dwork, s->work_doubles,
+                                                                       s->dcounter);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("datagen_kernel launch: ") + cudaGetErrorString(e));
+    CUDA_OK(cudaEventRecord(s->ev1, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_ms = ms;
+    if ((rc = dg_copy(s, stats, s->dcnt, B * sizeof(DgCounters), false))) return rc;
+    // rows: compacted on the device (problem order), one copy back
+    std::vector<long long> off(B + 1, 0);
+    for (size_t b = 0; b < B; ++b) off[b + 1] = off[b] + stats[b].n_rows;
+    *total_rows = off[B];
+    if (off[B] > rows_capacity) return fail(VBOC_ERR_ARG, "vboc_datagen_run: rows_capacity too small (see *total_rows)");
+    if (off[B] > 0) {
+        // the per-slot workspaces are idle now: their head serves as the offset table and the compact buffer
+        long long *doff = reinterpret_cast<long long *>(s->dwork);
+        double *dcompact = s->dwork + ((B + 2) & ~(size_t)1);
+        const size_t avail = (size_t)s->grid * WARPS_PER_CTA * s->work_doubles;
+        if (((B + 2) & ~(size_t)1) + (size_t)off[B] * nx > avail) return fail(VBOC_ERR_CUDA, "vboc_datagen_run: compaction buffer");
+        if ((rc = dg_copy(s, doff, off.data(), (B + 1) * sizeof(long long), true))) return rc;
+        dg_compact_kernel<<<(unsigned)B, 128, 0, s->stream>>>(s->drows, s->dcnt, doff, dcompact, (int)nx);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("dg_compact_kernel launch: ") + cudaGetErrorString(e));
+        if ((rc = dg_copy(s, rows, dcompact, (size_t)off[B] * nx * sizeof(double), false))) return rc;
+    }
     return 0;
 }
 

@@ -24,6 +24,7 @@
 
 #define VB_HD __host__ __device__ __forceinline__
 #define VB_DEV __device__ __forceinline__
+#define VB_DEV_NOINLINE __device__ __noinline__  // one copy of a large callee shared by several call sites
 #define FOR_LANES {                                   \
     const int lane = (int)(threadIdx.x & 31u);        \
     (void)lane;
@@ -140,6 +141,7 @@ __device__ __forceinline__ void vb_ring_wait(VbRing &r, int slot) {
 #include <cmath>
 #define VB_HD inline
 #define VB_DEV inline
+#define VB_DEV_NOINLINE inline
 #define FOR_LANES for (int lane = 0; lane < 32; ++lane) {
 #define END_LANES }
 #define LV(type, name) type name[32]

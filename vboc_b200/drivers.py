@@ -255,14 +255,11 @@ def testing_worker(n, rng, N0=100, dt_sym=1e-2, max_solves=60):
     return None
 
 
-def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
-    """One VBOC problem: an extreme trajectory from a position limit of a randomly selected joint, then the
-    walk along it that classifies every state (on the boundary of the viability kernel, on a state limit,
-    or inside) with sub-OCPs and the simulated unviable twin.  Returns the list of saved rows [q, v] or None."""
-    mdl = pr.Model(n)
-    eps = 10 * tol
+def _dg_initial(n, rng, mdl, dt_sym, eps):
+    """The sampling block of `data_generation` (VBOC/triplependulum_vboc.py:33-83): selected joint and side, cost
+    direction, initial positions.  Shared by the host generator and by the inputs of the device state machine, so
+    both consume the per-problem stream identically."""
     q_min, q_max, v_max = mdl.thetamin, mdl.thetamax, mdl.dthetamax
-    q_lb, q_ub, u_lb, u_ub, q_fin_lb, q_fin_ub = _limits(n, mdl, dt_sym)
 
     def nudge(q):
         q = q - eps if q > q_max - eps else q
@@ -281,6 +278,54 @@ def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
     lb0 = np.concatenate([q0, np.full(n, -v_max), [dt_sym]])
     ub0 = np.concatenate([q0, np.full(n, v_max), [dt_sym]])
     lb0[joint_sel] = ub0[joint_sel] = q_min + eps if vel_sel < 0 else q_max - eps
+    return dict(joint_sel=joint_sel, vel_sel=vel_sel, p=p, lb0=lb0, ub0=ub0, q_init_sel=q_init_sel, q_fin_sel=q_fin_sel)
+
+
+def _dg_retry(n, rng):
+    """Draws of one restart after a failed solve (VBOC/triplependulum_vboc.py:138-174): perturbation of the cost
+    direction (n components) and of the free initial positions (one value)."""
+    dp = np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
+    dev = rng.random() * _pm(rng) * 0.01
+    return dp, dev
+
+
+DG_RETRIES = 10  # the extreme-trajectory loop makes at most 10 solves, so at most 10 restarts
+
+
+def dg_inputs(n, num_prob, seed, first=0, dt_sym=1e-2, tol=1e-3):
+    """Inputs of the device state machine (`vboc_datagen_run`) for problems first .. first + num_prob - 1: everything
+    `data_generation_worker` would draw from its per-problem stream, drawn in the same order."""
+    mdl = pr.Model(n)
+    out = dict(joint_sel=np.zeros(num_prob, dtype=np.int32), p=np.zeros((num_prob, n + 1)),
+               lb0=np.zeros((num_prob, 2 * n + 1)), ub0=np.zeros((num_prob, 2 * n + 1)),
+               retry=np.zeros((num_prob, DG_RETRIES, n + 1)))
+    for b in range(num_prob):
+        rng = _rng(seed, first + b)
+        ini = _dg_initial(n, rng, mdl, dt_sym, 10 * tol)
+        out["joint_sel"][b], out["p"][b], out["lb0"][b], out["ub0"][b] = ini["joint_sel"], ini["p"], ini["lb0"], ini["ub0"]
+        for r in range(DG_RETRIES):
+            dp, dev = _dg_retry(n, rng)
+            out["retry"][b, r, :n], out["retry"][b, r, n] = dp, dev
+    return out
+
+
+def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
+    """One VBOC problem: an extreme trajectory from a position limit of a randomly selected joint, then the
+    walk along it that classifies every state (on the boundary of the viability kernel, on a state limit,
+    or inside) with sub-OCPs and the simulated unviable twin.  Returns the list of saved rows [q, v] or None."""
+    mdl = pr.Model(n)
+    eps = 10 * tol
+    q_min, q_max, v_max = mdl.thetamin, mdl.thetamax, mdl.dthetamax
+    q_lb, q_ub, u_lb, u_ub, q_fin_lb, q_fin_ub = _limits(n, mdl, dt_sym)
+
+    def nudge(q):
+        q = q - eps if q > q_max - eps else q
+        return q + eps if q < q_min + eps else q
+
+    ini = _dg_initial(n, rng, mdl, dt_sym, eps)
+    joint_sel, p, lb0, ub0 = ini["joint_sel"], ini["p"], ini["lb0"], ini["ub0"]
+    q_init_sel, q_fin_sel = ini["q_init_sel"], ini["q_fin_sel"]
+    others = [j for j in range(n) if j != joint_sel]
 
     def ramp_guess(N):
         tau = np.linspace(0, 1, N)
@@ -306,9 +351,9 @@ def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
             N += 1
         else:
             N = N0
-            d = p[:n] + np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
+            dp, dev = _dg_retry(n, rng)
+            d = p[:n] + dp
             p = np.concatenate([d / np.linalg.norm(d), [0.0]])
-            dev = rng.random() * _pm(rng) * 0.01
             for j in others:
                 lb0[j] = ub0[j] = nudge(lb0[j] + dev)
             xg, ug = ramp_guess(N)
@@ -513,6 +558,40 @@ def data_generation_stream(n, num_prob, seed, device=0, ssol=None, stats=None):
         stats["problems"] = num_prob
         stats["problems_ok"] = len(rows)
     return np.concatenate(rows).reshape(-1, 2 * n) if rows else np.empty((0, 2 * n))
+
+
+def data_generation_device(n, num_prob, seed, device=0, dgen=None, stats=None, first=0, sharded=False):
+    """`data_generation_batch` with the per-problem state machine ON THE DEVICE (`vboc_datagen_run`): one
+    kernel launch, one warp per problem, the host only prepares the random draws and harvests the rows.  Same seed,
+    same rows as the host generators.  sharded=True (under torch.distributed): this rank runs its contiguous shard of
+    the problem range and the rows of all ranks are all-gathered (rank order = problem order)."""
+    from . import engine
+    lo, hi = first, first + num_prob
+    if sharded:
+        import torch.distributed as dist
+        from . import distributed as vd
+        a, b = vd.shard_range(num_prob, dist.get_rank(), dist.get_world_size())
+        lo, hi = first + a, first + b
+    own = dgen is None
+    rows = np.empty((0, 2 * n))
+    st = None
+    if hi > lo:
+        dgen = dgen or engine.DataGenerator(n, hi - lo, device=device)
+        rows, st = dgen.run(dg_inputs(n, hi - lo, seed, first=lo))
+        if own:
+            dgen.close()
+    if stats is not None and st is not None:
+        stats["problems"] = hi - lo
+        stats["problems_ok"] = int((st["status"] != 1).sum())
+        stats["solves"] = int(st["solves"].sum())
+        stats["converged"] = int(st["converged"].sum())
+        stats["sim_steps"] = int(st["sim_steps"].sum())
+        stats["kernel_ms"] = dgen.last_kernel_ms if not own else stats.get("kernel_ms")
+        stats["overflow"] = int((st["status"] == 2).sum())
+    if sharded:
+        from . import distributed as vd
+        rows = vd.all_gather_rows(rows)
+    return rows
 
 
 # ------------------------------------------------------------------------------------------------

@@ -231,6 +231,47 @@ class StreamSolver:
         return [got[t] for t in tk]
 
 
+_DG_DTYPE = np.dtype([(f, "i4") for f in ("status", "n_rows", "solves", "converged", "sim_steps", "sqp_iter", "qp_iter", "pad_")])
+
+
+class DataGenerator:
+    """`vboc_datagen_*`: the whole `data_generation(v)` of a batch of problems as one kernel launch (one warp per problem,
+    csrc/datagen_warp.h).  `run(inputs)` takes `drivers.dg_inputs(...)` and returns (rows (total, 2n) in problem order,
+    per-problem counters as a structured array)."""
+
+    def __init__(self, n, capacity, device=0, opts=None):
+        self.n, self.cap, self.device = int(n), int(capacity), int(device)
+        self._h = C.c_void_p()
+        check(_lib.lib().vboc_datagen_create(self.n, self.cap, self.device, C.byref(self._h)))
+        if opts is not None:
+            check(_lib.lib().vboc_datagen_set_opts(self._h, C.byref(opts)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().vboc_datagen_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    @property
+    def last_kernel_ms(self):
+        return _lib.lib().vboc_datagen_last_kernel_ms(self._h)
+
+    def run(self, inp, N0=100, dt=1e-2, tol=1e-3):
+        B, n = len(inp["joint_sel"]), self.n
+        js = np.ascontiguousarray(inp["joint_sel"], dtype=np.int32)
+        arrs = [_c(inp[k]) for k in ("p", "lb0", "ub0", "retry")]
+        assert arrs[0].shape == (B, n + 1) and arrs[1].shape == (B, 2 * n + 1) and arrs[3].shape == (B, 10, n + 1)
+        cap_rows = B * _lib.DG_ROWS_MAX
+        rows = np.empty((cap_rows, 2 * n))
+        st = np.zeros(B, dtype=_DG_DTYPE)
+        total = C.c_longlong(0)
+        check(_lib.lib().vboc_datagen_run(self._h, B, int(N0), float(dt), float(tol), js.ctypes.data_as(C.POINTER(C.c_int)),
+                                          *[_dp(a) for a in arrs], _dp(rows), cap_rows, C.byref(total),
+                                          st.ctypes.data_as(C.POINTER(_lib.DgStats))))
+        return rows[:total.value].copy(), st
+
+
 def sim_step(n, x, u, T, device=0):
     """Batched RK4 step of the unscaled model (the reference's `sim.acados_integrator`)."""
     x, u = _c(np.atleast_2d(x)), _c(np.atleast_2d(u))

@@ -189,7 +189,8 @@ int vboc_stream_sim_step(vboc_stream *s, int count, const double *x, const doubl
 #define VBOC_DG_ROWS_MAX 258
 typedef struct {
     int status;    /* 0 rows returned, 1 no extreme trajectory found (the generator returns None), 2 row buffer overflow */
-    int n_rows, solves, converged, sim_steps, sqp_iter, qp_iter, pad_;
+    int n_rows, solves, converged, sim_steps, sqp_iter, qp_iter;
+    int t_done_us; /* completion time of the problem, microseconds after the kernel start (device clock) */
 } vboc_dg_stats;
 typedef struct vboc_datagen vboc_datagen;
 int vboc_datagen_create(int n_dof, int capacity, int device, vboc_datagen **out);
@@ -225,6 +226,30 @@ int vboc_mlp_forward(vboc_mlp *m, int batch, const float *x, int mode, double me
                      double safety_margin, float *out, float *aux, int *label);
 /* Device time of the last vboc_mlp_forward kernel in milliseconds (CUDA events around the launch). */
 double vboc_mlp_last_kernel_ms(vboc_mlp *m);
+
+/*
+ * Resident unlabeled pool of the AL drivers (AL/triplependulum_al.py:100-123, 241-293): the pool (15^6 = 1.14e7 states
+ * for the 3-DOF system) is uploaded ONCE and stays in HBM across the rounds of the loop; per round
+ *   vboc_pool_score            entropy of sigmoid(model((x - mean) / std)) of every pool row (:253-264), scores stay
+ *                              on the device;
+ *   vboc_pool_select           the k most uncertain rows (`np.argpartition(etp, -k)[-k:]`, :267-270) by a radix select
+ *                              on the device; idx [k] comes back sorted largest index first as the drivers sort it;
+ *                              x [k][n_in] / score [k] (optional) are the selected rows / their entropies in that order;
+ *   vboc_pool_remove_selected  `np.delete(X_prova, idx)` (:281): stable compaction of the pool on the device.
+ * Only the k indices / rows per round cross the host link.  Ties at the k-th score are broken arbitrarily (as
+ * argpartition does).  vboc_pool_download / _download_scores read the pool back (tests).
+ */
+typedef struct vboc_pool vboc_pool;
+int vboc_pool_create(int device, int n_in, long long capacity, vboc_pool **out);
+void vboc_pool_destroy(vboc_pool *p);
+int vboc_pool_upload(vboc_pool *p, long long count, const float *x);
+long long vboc_pool_size(vboc_pool *p);
+int vboc_pool_score(vboc_pool *p, vboc_mlp *m, double mean, double stdv);
+int vboc_pool_select(vboc_pool *p, int k, long long *idx, float *x, float *score);
+int vboc_pool_remove_selected(vboc_pool *p);
+int vboc_pool_download(vboc_pool *p, float *x);
+int vboc_pool_download_scores(vboc_pool *p, float *score);
+double vboc_pool_last_score_ms(vboc_pool *p);
 
 /* Measured FP64 FMA peak of the device in TFLOP/s (dependent-free DFMA chains on every SM): the
  * roofline denominator bench.py reports against (MEASURED_PEAKS.json has no FP64 entry). */

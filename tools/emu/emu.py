@@ -73,7 +73,7 @@ def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False):
 
 class DgStats(C.Structure):
     _fields_ = [("status", C.c_int), ("n_rows", C.c_int), ("solves", C.c_int), ("converged", C.c_int),
-                ("sim_steps", C.c_int), ("sqp_iter", C.c_int), ("qp_iter", C.c_int), ("pad_", C.c_int)]
+                ("sim_steps", C.c_int), ("sqp_iter", C.c_int), ("qp_iter", C.c_int), ("t_done_us", C.c_int)]
 
 
 ROWS_MAX = 258

@@ -22,6 +22,8 @@ EXPORTS = (
     "vboc_stream_create", "vboc_stream_destroy", "vboc_stream_set_opts", "vboc_stream_free_slots",
     "vboc_stream_pending", "vboc_stream_submit", "vboc_stream_poll", "vboc_stream_fetch", "vboc_stream_sim_step",
     "vboc_datagen_create", "vboc_datagen_destroy", "vboc_datagen_set_opts", "vboc_datagen_run", "vboc_datagen_last_kernel_ms",
+    "vboc_pool_create", "vboc_pool_destroy", "vboc_pool_upload", "vboc_pool_size", "vboc_pool_score", "vboc_pool_select",
+    "vboc_pool_remove_selected", "vboc_pool_download", "vboc_pool_download_scores", "vboc_pool_last_score_ms",
     "vboc_sim_step", "vboc_mlp_create", "vboc_mlp_destroy", "vboc_mlp_forward", "vboc_mlp_last_kernel_ms", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
 )
 
@@ -51,7 +53,7 @@ class Stats(C.Structure):
 class DgStats(C.Structure):
     """vboc_dg_stats"""
     _fields_ = [("status", C.c_int), ("n_rows", C.c_int), ("solves", C.c_int), ("converged", C.c_int),
-                ("sim_steps", C.c_int), ("sqp_iter", C.c_int), ("qp_iter", C.c_int), ("pad_", C.c_int)]
+                ("sim_steps", C.c_int), ("sqp_iter", C.c_int), ("qp_iter", C.c_int), ("t_done_us", C.c_int)]
 
 
 DG_ROWS_MAX = 258
@@ -119,6 +121,20 @@ def lib():
         L.vboc_mlp_forward.argtypes = [vp, C.c_int, fp, C.c_int, C.c_double, C.c_double, C.c_double, fp, fp, ip]
         L.vboc_mlp_last_kernel_ms.argtypes = [vp]
         L.vboc_mlp_last_kernel_ms.restype = C.c_double
+        llp = C.POINTER(C.c_longlong)
+        L.vboc_pool_create.argtypes = [C.c_int, C.c_int, C.c_longlong, C.POINTER(vp)]
+        L.vboc_pool_destroy.argtypes = [vp]
+        L.vboc_pool_destroy.restype = None
+        L.vboc_pool_upload.argtypes = [vp, C.c_longlong, fp]
+        L.vboc_pool_size.argtypes = [vp]
+        L.vboc_pool_size.restype = C.c_longlong
+        L.vboc_pool_score.argtypes = [vp, vp, C.c_double, C.c_double]
+        L.vboc_pool_select.argtypes = [vp, C.c_int, llp, fp, fp]
+        L.vboc_pool_remove_selected.argtypes = [vp]
+        L.vboc_pool_download.argtypes = [vp, fp]
+        L.vboc_pool_download_scores.argtypes = [vp, fp]
+        L.vboc_pool_last_score_ms.argtypes = [vp]
+        L.vboc_pool_last_score_ms.restype = C.c_double
         L.vboc_fp64_peak.argtypes = [C.c_int, dp]
         L.vboc_last_error.restype = C.c_char_p
         L.vboc_version.restype = C.c_char_p

@@ -66,7 +66,7 @@ def _rows(X, labels, traj):
 
 def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, fit_guess, etp_stop=0.1,
                     max_rounds=100, N=100, Tf=1.0, device=0, label_fn=None, query_fn=None, history=None,
-                    sharded=False):
+                    sharded=False, resident=False):
     """Run the loop; returns (X_iter, X_traj, remaining pool).  `fit_cls(model, X_iter)` / `fit_guess(model_guess,
     X_traj)` retrain in place; `history` (list) receives one dict per round.
 
@@ -74,7 +74,12 @@ def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, 
     N_init / B are global numbers.  Every rank scores its shard, the query is the global top-B, each rank labels and
     removes the selected states that live in its shard, and the new rows are all-gathered so that all ranks hold
     identical training windows (and, with identical seeds, train identical networks).  `query_fn(model, pool, Bk)`
-    must then return (local indices, entropies, global maximum of the selected entropies)."""
+    must then return (local indices, entropies, global maximum of the selected entropies).
+
+    resident=True: after the initial labelling the pool is uploaded ONCE to the device (`nn.ResidentPool`) and stays
+    there; every round's scoring, top-B and removal run on the device (`drivers.al_query_resident`) and only the
+    queried rows travel.  The host keeps the float64 states (the OCPs are solved from those, not from the float32
+    copies the network sees) and the map from pool position to original row."""
     from . import distributed as vd
     from . import nn as vnn
     world = rank = 0
@@ -103,18 +108,33 @@ def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, 
     if len(X_traj):
         fit_guess(model_guess, X_traj)
     k, etpmax = 0, 1.0
+    rp = orig = None
+    if resident:
+        rp = vnn.ResidentPool(pool, device=device)
+        orig = np.arange(len(pool), dtype=np.int64)   # pool position -> row of `pool` (the float64 states)
+        alive = np.ones(len(pool), dtype=bool)
 
     def pool_left():
+        n_loc = len(rp) if resident else len(pool)
         if not sharded:
-            return len(pool)
-        return int(vd.all_gather_rows(np.array([[float(len(pool))]])).sum())
+            return n_loc
+        return int(vd.all_gather_rows(np.array([[float(n_loc)]])).sum())
 
     while k < max_rounds:
         total = pool_left()
         if etpmax < etp_stop or total == 0:
             break
         Bk = min(B, total)
-        if query_fn is not None:
+        if resident:
+            net = vnn.MLP.from_torch(model, device=device)
+            idx, _, etpmax = drivers.al_query_resident(rp, net, float(mean), float(std), Bk, sharded=sharded)
+            net.close()
+            rows = orig[idx]
+            orig = np.delete(orig, idx)
+            alive[rows] = False
+            elems = pool[rows]
+            k += 1
+        elif query_fn is not None:
             q = query_fn(model, pool, Bk)
             idx, etp = q[0], q[1]
             etpmax = float(q[2]) if len(q) > 2 else float(np.max(np.asarray(etp)[np.asarray(idx, dtype=np.int64)]))
@@ -122,10 +142,11 @@ def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, 
             net = vnn.MLP.from_torch(model, device=device)
             idx, etp, etpmax = drivers.al_query(net, pool, float(mean), float(std), Bk, sharded=sharded)
             net.close()
-        idx = np.asarray(idx, dtype=np.int64)
-        k += 1
-        elems = pool[idx]
-        pool = np.delete(pool, idx, axis=0)
+        if not resident:
+            idx = np.asarray(idx, dtype=np.int64)
+            k += 1
+            elems = pool[idx]
+            pool = np.delete(pool, idx, axis=0)
         xg = predict_guess(model_guess, elems, mean, std, N, nx) if (model_guess is not None and len(X_traj) and len(elems)) else None
         if len(elems):
             labels, traj = label_fn(elems, xg)
@@ -143,6 +164,9 @@ def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, 
             fit_guess(model_guess, X_traj)
         if history is not None:
             history.append(dict(round=k, etpmax=etpmax, labelled=int(len(elems)), viable=int((labels == 1).sum()),
-                                pool=int(len(pool)), window=int(len(X_iter)), traj_window=int(len(X_traj)),
-                                dropped_label2=int(dropped)))
+                                pool=int(len(rp) if resident else len(pool)), window=int(len(X_iter)),
+                                traj_window=int(len(X_traj)), dropped_label2=int(dropped)))
+    if resident:
+        rp.close()
+        pool = pool[alive]
     return X_iter, X_traj, pool

@@ -30,7 +30,8 @@ struct DgParams {
 };
 struct DgCounters {
     int status;    // 0 rows returned, 1 no extreme trajectory (the generator returns None), 2 row buffer overflow
-    int n_rows, solves, converged, sim_steps, sqp_iter, qp_iter, pad_;
+    int n_rows, solves, converged, sim_steps, sqp_iter, qp_iter;
+    int t_done_us;  // when the problem finished, microseconds after the kernel started (device clock)
 };
 
 template <int NQ>
@@ -191,7 +192,7 @@ struct DataGen {
     // the whole of data_generation(v) for problem b
     VB_DEV void run(const DgIO<NQ> &io, int b) {
         const double eps = 10.0 * P.tol, tol = P.tol;
-        c.status = 1, c.n_rows = 0, c.solves = 0, c.converged = 0, c.sim_steps = 0, c.sqp_iter = 0, c.qp_iter = 0, c.pad_ = 0;
+        c.status = 1, c.n_rows = 0, c.solves = 0, c.converged = 0, c.sim_steps = 0, c.sqp_iter = 0, c.qp_iter = 0, c.t_done_us = 0;
         const int joint_sel = io.joint_sel[b];
         double *rows = io.rows + (size_t)b * DG_ROWS_MAX * NX;
         const double *retry = io.retry + (size_t)b * DG_RETRIES * (NQ + 1);

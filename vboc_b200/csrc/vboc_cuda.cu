@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -19,6 +20,8 @@
 #include "../../include/vboc_b200.h"
 #include "mlp_forward.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_pipe.cuh"
+#include "pool_select.cuh"
 #include "ocp_lane.h"
 #include "ocp_warp.h"
 #include "datagen_warp.h"
@@ -235,10 +238,19 @@ __global__ void nsmid_kernel(unsigned int *out) {
 template <int NQ>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) datagen_kernel(const DgIO<NQ> io, int count, const DgParams P,
                                                                       const vboc_opts opts, double *work,
-                                                                      size_t work_doubles, unsigned int *counter) {
+                                                                      size_t work_doubles, unsigned int *counter,
+                                                                      unsigned long long *t_start) {
     __shared__ Smem<NQ> smem[WARPS_PER_CTA];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WARPS_PER_CTA + warp;
+    // kernel start on the device clock: the first warp to arrive sets it
+    unsigned long long t0 = 0;
+    if (lane == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        const unsigned long long prev = atomicCAS(t_start, 0ull, now);
+        t0 = prev ? prev : now;
+    }
     double *base = work + (size_t)slot * work_doubles;
     Work<NQ> w;
     w.carve(base, DG_N_CAP);
@@ -253,7 +265,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) datagen_kernel(const Dg
         if (b >= (unsigned)count) break;
         dg.run(io, (int)b);
         __syncwarp();
-        if (lane == 0) io.cnt[b] = dg.c;
+        if (lane == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            dg.c.t_done_us = (int)((now - t0) / 1000ull);
+            io.cnt[b] = dg.c;
+        }
         __syncwarp();
     }
 }
@@ -772,20 +789,33 @@ int vboc_solve_batch(vboc_solver *s, int mode, int batch, const int *N, const do
 struct vboc_mlp {
     int device, n_in, hidden, n_out, final_relu;
     float *W1, *b1, *W2T, *b2, *W3, *b3;  // CUDA-core kernel (W2 transposed)
-    int Hp;                               // hidden size padded to a multiple of 32 (tensor-core kernel)
+    int Hp;                               // hidden size padded to a multiple of 32 (tensor-core kernels)
     float *W1p, *b1p, *W2p, *b2p, *W3p;   // zero padded
-    double last_ms;                       // device time of the last forward kernel (CUDA events)
+    unsigned char *W2img;                 // hi / lo split of W2p as shared-memory chunk images (mlp_pipe.cuh)
+    int num_sms;
+    // persistent, grow-on-demand I/O buffers of vboc_mlp_forward (host arrays in, host arrays out)
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    float *dx, *dout, *daux;
+    int *dlab;
+    long long io_rows;
+    char *stage;                          // pinned staging for the copies
+    size_t stage_bytes;
+    double last_ms;                       // device time of the last forward kernel (CUDA events); < 0 before the first
 };
 
-int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu, const float *W1,
-                    const float *b1, const float *W2, const float *b2, const float *W3, const float *b3,
-                    vboc_mlp **out) {
-    if (!out || n_in < 2 || n_in > MLP_MAX_IN || hidden < 1 || hidden > 1024 || n_out < 1 || n_out > MLP_MAX_OUT ||
-        !W1 || !b1 || !W2 || !b2 || !W3 || !b3)
-        return fail(VBOC_ERR_ARG, "vboc_mlp_create: bad argument");
-    CUDA_OK(cudaSetDevice(device));
-    vboc_mlp *m = new vboc_mlp();
+static int mlp_create_impl(vboc_mlp *m, int device, int n_in, int hidden, int n_out, int final_relu, const float *W1,
+                           const float *b1, const float *W2, const float *b2, const float *W3, const float *b3) {
     m->device = device, m->n_in = n_in, m->hidden = hidden, m->n_out = n_out, m->final_relu = final_relu;
+    m->last_ms = -1.0;
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    m->num_sms = prop.multiProcessorCount;
+    CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&m->ev0));
+    CUDA_OK(cudaEventCreate(&m->ev1));
+    m->stage_bytes = (size_t)16 << 20;
+    CUDA_OK(cudaMallocHost((void **)&m->stage, m->stage_bytes));
     std::vector<float> w2t((size_t)hidden * hidden);
     for (int j = 0; j < hidden; ++j)
         for (int k = 0; k < hidden; ++k) w2t[(size_t)k * hidden + j] = W2[(size_t)j * hidden + k];
@@ -798,7 +828,7 @@ int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu,
     UPF(b2, b2, hidden);
     UPF(W3, W3, n_out * hidden);
     UPF(b3, b3, n_out);
-    {   // zero-padded copies for the tcgen05 kernel
+    {   // zero-padded copies for the tcgen05 kernels
         const int Hp = (hidden + 31) / 32 * 32;
         m->Hp = Hp;
         std::vector<float> w1p((size_t)Hp * n_in, 0.f), b1p(Hp, 0.f), w2p((size_t)Hp * Hp, 0.f), b2p(Hp, 0.f),
@@ -814,8 +844,50 @@ int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu,
         UPF(W2p, w2p.data(), w2p.size());
         UPF(b2p, b2p.data(), b2p.size());
         UPF(W3p, w3p.data(), w3p.size());
+        // W2 split into hi / lo ONCE, laid out as the shared-memory image of every K-chunk of the B operand:
+        // chunk ch (K = 8 ch .. 8 ch + 7), part (hi, lo), 16-byte K-group c (2), output unit n (Hp + 1 padded), 4 floats
+        if (Hp <= 512) {
+            const TpLayout lay(Hp, n_in, n_out);
+            const size_t nch = Hp / TP_KC, img = (size_t)lay.b_bytes / 4;  // floats per (hi or lo) image
+            std::vector<float> blob(nch * 2 * img, 0.f);
+            for (size_t ch = 0; ch < nch; ++ch)
+                for (int c = 0; c < TP_KC / 4; ++c)
+                    for (int nn = 0; nn < Hp; ++nn)
+                        for (int e = 0; e < 4; ++e) {
+                            const float wv = w2p[(size_t)nn * Hp + ch * TP_KC + 4 * c + e];
+                            uint32_t bits;
+                            memcpy(&bits, &wv, 4);
+                            bits &= 0xFFFFE000u;
+                            float hi;
+                            memcpy(&hi, &bits, 4);
+                            const size_t o = (size_t)c * (lay.b_lbo / 4) + (size_t)nn * 4 + e;
+                            blob[(ch * 2 + 0) * img + o] = hi;
+                            blob[(ch * 2 + 1) * img + o] = wv - hi;
+                        }
+            CUDA_OK(cudaMalloc((void **)&m->W2img, blob.size() * sizeof(float)));
+            CUDA_OK(cudaMemcpy(m->W2img, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
     }
 #undef UPF
+    return 0;
+}
+
+int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu, const float *W1,
+                    const float *b1, const float *W2, const float *b2, const float *W3, const float *b3,
+                    vboc_mlp **out) {
+    if (!out || n_in < 2 || n_in > MLP_MAX_IN || hidden < 1 || hidden > 1024 || n_out < 1 || n_out > MLP_MAX_OUT ||
+        !W1 || !b1 || !W2 || !b2 || !W3 || !b3)
+        return fail(VBOC_ERR_ARG, "vboc_mlp_create: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    vboc_mlp *m = new vboc_mlp();
+    memset(m, 0, sizeof(*m));
+    int rc = mlp_create_impl(m, device, n_in, hidden, n_out, final_relu, W1, b1, W2, b2, W3, b3);
+    if (rc) {
+        const std::string keep = g_err;
+        vboc_mlp_destroy(m);
+        g_err = keep;
+        return rc;
+    }
     *out = m;
     return 0;
 }
@@ -823,65 +895,313 @@ int vboc_mlp_create(int device, int n_in, int hidden, int n_out, int final_relu,
 void vboc_mlp_destroy(vboc_mlp *m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->W1), cudaFree(m->b1), cudaFree(m->W2T), cudaFree(m->b2), cudaFree(m->W3), cudaFree(m->b3);
-    cudaFree(m->W1p), cudaFree(m->b1p), cudaFree(m->W2p), cudaFree(m->b2p), cudaFree(m->W3p);
+    void *ptrs[] = {m->W1, m->b1, m->W2T, m->b2, m->W3, m->b3, m->W1p, m->b1p, m->W2p, m->b2p, m->W3p, m->W2img,
+                    m->dx, m->dout, m->daux, m->dlab};
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    if (m->stage) cudaFreeHost(m->stage);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    cudaGetLastError();
     delete m;
+}
+
+// Launch of the fused MLP on DEVICE arrays (x [batch][n_in] -> out [batch][n_out] / aux / label, any of the outputs may
+// be null) on `stream`; events ev0 / ev1 of the handle bracket the kernel.  Kernel choice: the pipelined tcgen05
+// kernel (mlp_pipe.cuh) for hidden sizes the 512-column TMEM holds; VBOC_MLP_SERIAL=1 selects the serial tcgen05
+// kernel of round 1, VBOC_MLP_CUDA_CORES=1 the plain FP32 kernel (both kept as cross-checks).
+static int mlp_launch(vboc_mlp *m, long long batch, const float *dx, int mode, double mean, double stdv,
+                      double safety_margin, float *dout, float *daux, int *dlab, cudaStream_t stream) {
+    MlpParams P;
+    P.batch = (int)(batch > 0x7fffffff ? 0x7fffffff : batch), P.n_in = m->n_in, P.hidden = m->hidden, P.n_out = m->n_out;
+    P.mode = mode, P.final_relu = m->final_relu;
+    P.mean = (float)mean, P.stdv = (float)stdv, P.margin_scale = (float)((100.0 - safety_margin) / 100.0);
+    P.W1 = m->W1, P.b1 = m->b1, P.W2T = m->W2T, P.b2 = m->b2, P.W3 = m->W3, P.b3 = m->b3;
+    P.x = dx, P.out = dout, P.aux = daux, P.label = dlab;
+    const char *force = getenv("VBOC_MLP_CUDA_CORES"), *serial = getenv("VBOC_MLP_SERIAL");
+    CUDA_OK(cudaEventRecord(m->ev0, stream));
+    if (m->Hp <= 512 && !(force && atoi(force))) {
+        P.W1 = m->W1p, P.b1 = m->b1p, P.W2T = m->W2p, P.b2 = m->b2p, P.W3 = m->W3p;
+        int cols = 32;
+        while (cols < m->Hp) cols *= 2;
+        const long long tiles = (batch + TC_ROWS - 1) / TC_ROWS;
+        if (serial && atoi(serial)) {
+            if (!dout) return fail(VBOC_ERR_ARG, "mlp: the serial kernel needs an output array");
+            TcLayout lay(m->Hp);
+            CUDA_OK(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total()));
+            mlp_tc_kernel<<<(unsigned)tiles, TC_THREADS, lay.total(), stream>>>(P, m->Hp, cols);
+        } else {
+            TpLayout lay(m->Hp, m->n_in, m->n_out);
+            CUDA_OK(cudaFuncSetAttribute(mlp_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total()));
+            const unsigned grid = (unsigned)(tiles < m->num_sms ? tiles : m->num_sms);  // persistent: one CTA per SM
+            mlp_pipe_kernel<<<grid, TC_THREADS, lay.total(), stream>>>(P, m->Hp, cols, m->W2img, batch);
+        }
+    } else {
+        if (!dout) return fail(VBOC_ERR_ARG, "mlp: the CUDA-core kernel needs an output array");
+        size_t smem = mlp_smem_bytes(m->hidden);
+        CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = (int)((batch + MLP_ROWS - 1) / MLP_ROWS);
+        mlp_forward_kernel<<<grid, MLP_THREADS, smem, stream>>>(P);
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(m->ev1, stream));
+    return 0;
+}
+
+static int mlp_finish(vboc_mlp *m, cudaStream_t stream) {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) m->last_ms = ms;
+    return 0;
+}
+
+// pinned-staged copy on the handle's stream (host arrays may be pageable)
+static int mlp_copy(vboc_mlp *m, void *dst, const void *src, size_t bytes, bool to_device) {
+    const char *ps = (const char *)src;
+    char *pd = (char *)dst;
+    while (bytes) {
+        size_t c = bytes < m->stage_bytes ? bytes : m->stage_bytes;
+        if (to_device) {
+            memcpy(m->stage, ps, c);
+            CUDA_OK(cudaMemcpyAsync(pd, m->stage, c, cudaMemcpyHostToDevice, m->stream));
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+        } else {
+            CUDA_OK(cudaMemcpyAsync(m->stage, ps, c, cudaMemcpyDeviceToHost, m->stream));
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+            memcpy(pd, m->stage, c);
+        }
+        ps += c, pd += c, bytes -= c;
+    }
+    return 0;
 }
 
 int vboc_mlp_forward(vboc_mlp *m, int batch, const float *x, int mode, double mean, double stdv,
                      double safety_margin, float *out, float *aux, int *label) {
     if (!m || batch < 1 || !x || !out || mode < 0 || mode > 2) return fail(VBOC_ERR_ARG, "vboc_mlp_forward: bad argument");
     CUDA_OK(cudaSetDevice(m->device));
-    float *dx = nullptr, *dout = nullptr, *daux = nullptr;
-    int *dlab = nullptr;
-    size_t B = batch;
-    CUDA_OK(cudaMalloc((void **)&dx, B * m->n_in * sizeof(float)));
-    CUDA_OK(cudaMalloc((void **)&dout, B * m->n_out * sizeof(float)));
-    CUDA_OK(cudaMalloc((void **)&daux, B * sizeof(float)));
-    CUDA_OK(cudaMalloc((void **)&dlab, B * sizeof(int)));
-    CUDA_OK(cudaMemcpy(dx, x, B * m->n_in * sizeof(float), cudaMemcpyHostToDevice));
-    MlpParams P;
-    P.batch = batch, P.n_in = m->n_in, P.hidden = m->hidden, P.n_out = m->n_out, P.mode = mode;
-    P.final_relu = m->final_relu;
-    P.mean = (float)mean, P.stdv = (float)stdv, P.margin_scale = (float)((100.0 - safety_margin) / 100.0);
-    P.W1 = m->W1, P.b1 = m->b1, P.W2T = m->W2T, P.b2 = m->b2, P.W3 = m->W3, P.b3 = m->b3;
-    P.x = dx, P.out = dout, P.aux = daux, P.label = dlab;
-    // tensor cores (tcgen05, 3xTF32) for hidden sizes the 512-column TMEM holds; VBOC_MLP_CUDA_CORES=1 selects
-    // the plain FP32 kernel (kept as the cross-check of the tensor-core path)
-    const char *force = getenv("VBOC_MLP_CUDA_CORES");
-    cudaEvent_t e0, e1;
-    CUDA_OK(cudaEventCreate(&e0));
-    CUDA_OK(cudaEventCreate(&e1));
-    CUDA_OK(cudaEventRecord(e0));
-    if (m->Hp <= 512 && !(force && atoi(force))) {
-        P.W1 = m->W1p, P.b1 = m->b1p, P.W2T = m->W2p, P.b2 = m->b2p, P.W3 = m->W3p;
-        TcLayout lay(m->Hp);
-        int cols = 32;
-        while (cols < m->Hp) cols *= 2;
-        CUDA_OK(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total()));
-        int grid = (batch + TC_ROWS - 1) / TC_ROWS;
-        mlp_tc_kernel<<<grid, TC_THREADS, lay.total()>>>(P, m->Hp, cols);
-    } else {
-        size_t smem = mlp_smem_bytes(m->hidden);
-        CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int grid = (batch + MLP_ROWS - 1) / MLP_ROWS;
-        mlp_forward_kernel<<<grid, MLP_THREADS, smem>>>(P);
+    const size_t B = batch;
+    if ((long long)B > m->io_rows) {  // grow-on-demand persistent buffers: no allocation on the steady-state path
+        void *old[] = {m->dx, m->dout, m->daux, m->dlab};
+        for (void *q : old)
+            if (q) cudaFree(q);
+        m->dx = m->dout = m->daux = nullptr, m->dlab = nullptr, m->io_rows = 0;
+        const size_t rows = B + B / 4;
+        CUDA_OK(cudaMalloc((void **)&m->dx, rows * m->n_in * sizeof(float)));
+        CUDA_OK(cudaMalloc((void **)&m->dout, rows * m->n_out * sizeof(float)));
+        CUDA_OK(cudaMalloc((void **)&m->daux, rows * sizeof(float)));
+        CUDA_OK(cudaMalloc((void **)&m->dlab, rows * sizeof(int)));
+        m->io_rows = (long long)rows;
     }
-    CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaEventRecord(e1));
-    CUDA_OK(cudaDeviceSynchronize());
-    {
-        float ms = -1.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        m->last_ms = ms;
-        cudaEventDestroy(e0), cudaEventDestroy(e1);
-    }
-    CUDA_OK(cudaMemcpy(out, dout, B * m->n_out * sizeof(float), cudaMemcpyDeviceToHost));
-    if (aux) CUDA_OK(cudaMemcpy(aux, daux, B * sizeof(float), cudaMemcpyDeviceToHost));
-    if (label) CUDA_OK(cudaMemcpy(label, dlab, B * sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(dx), cudaFree(dout), cudaFree(daux), cudaFree(dlab);
+    int rc;
+    if ((rc = mlp_copy(m, m->dx, x, B * m->n_in * sizeof(float), true))) return rc;
+    if ((rc = mlp_launch(m, batch, m->dx, mode, mean, stdv, safety_margin, m->dout, m->daux, m->dlab, m->stream))) return rc;
+    if ((rc = mlp_finish(m, m->stream))) return rc;
+    if ((rc = mlp_copy(m, out, m->dout, B * m->n_out * sizeof(float), false))) return rc;
+    if (aux && (rc = mlp_copy(m, aux, m->daux, B * sizeof(float), false))) return rc;
+    if (label && (rc = mlp_copy(m, label, m->dlab, B * sizeof(int), false))) return rc;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Resident unlabeled pool of the AL drivers (include/vboc_b200.h: vboc_pool_*): the pool lives in HBM across
+// rounds; scoring, the top-B query and the removal of the queried rows run on the device (pool_select.cuh).
+struct vboc_pool {
+    int device, n_in;
+    long long cap, size;
+    float *x[2];        // double buffer: the stable compaction writes the surviving rows to the other one
+    int cur;
+    float *score;
+    unsigned int *hist;     // 2048 bins
+    long long *sel;         // indices of the last selection (device), sel_count of them
+    int *flags;             // 1 = selected (to be removed)
+    unsigned int *counters; // [0] selected above the threshold, [1] ties taken
+    long long *blk;         // per-block kept counts / offsets
+    int sel_count;
+    cudaStream_t stream;
+    char *stage;
+    size_t stage_bytes;
+    double last_score_ms;
+};
+
+static int pool_copy(vboc_pool *s, void *dst, const void *src, size_t bytes, bool to_device) {
+    const char *ps = (const char *)src;
+    char *pd = (char *)dst;
+    while (bytes) {
+        size_t c = bytes < s->stage_bytes ? bytes : s->stage_bytes;
+        if (to_device) {
+            memcpy(s->stage, ps, c);
+            CUDA_OK(cudaMemcpyAsync(pd, s->stage, c, cudaMemcpyHostToDevice, s->stream));
+            CUDA_OK(cudaStreamSynchronize(s->stream));
+        } else {
+            CUDA_OK(cudaMemcpyAsync(s->stage, ps, c, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_OK(cudaStreamSynchronize(s->stream));
+            memcpy(pd, s->stage, c);
+        }
+        ps += c, pd += c, bytes -= c;
+    }
+    return 0;
+}
+
+static int pool_create_impl(vboc_pool *s, int device, int n_in, long long capacity) {
+    s->device = device, s->n_in = n_in, s->cap = capacity, s->size = 0, s->cur = 0, s->sel_count = 0, s->last_score_ms = -1.0;
+    CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) CUDA_OK(cudaMalloc((void **)&s->x[i], (size_t)capacity * n_in * sizeof(float)));
+    CUDA_OK(cudaMalloc((void **)&s->score, (size_t)capacity * sizeof(float)));
+    CUDA_OK(cudaMalloc((void **)&s->hist, 2048 * sizeof(unsigned int)));
+    CUDA_OK(cudaMalloc((void **)&s->sel, (size_t)capacity * sizeof(long long)));
+    CUDA_OK(cudaMalloc((void **)&s->flags, (size_t)capacity * sizeof(int)));
+    CUDA_OK(cudaMalloc((void **)&s->counters, 4 * sizeof(unsigned int)));
+    CUDA_OK(cudaMalloc((void **)&s->blk, (size_t)((capacity + POOL_BLOCK - 1) / POOL_BLOCK + 1) * sizeof(long long)));
+    s->stage_bytes = (size_t)16 << 20;
+    CUDA_OK(cudaMallocHost((void **)&s->stage, s->stage_bytes));
+    return 0;
+}
+
+int vboc_pool_create(int device, int n_in, long long capacity, vboc_pool **out) {
+    if (!out || n_in < 2 || n_in > MLP_MAX_IN || capacity < 1) return fail(VBOC_ERR_ARG, "vboc_pool_create: bad argument");
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(VBOC_ERR_CUDA, "vboc_pool_create: no such CUDA device");
+    CUDA_OK(cudaSetDevice(device));
+    vboc_pool *s = new vboc_pool();
+    memset(s, 0, sizeof(*s));
+    int rc = pool_create_impl(s, device, n_in, capacity);
+    if (rc) {
+        const std::string keep = g_err;
+        vboc_pool_destroy(s);
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+void vboc_pool_destroy(vboc_pool *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    void *ptrs[] = {s->x[0], s->x[1], s->score, s->hist, s->sel, s->flags, s->counters, s->blk};
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    if (s->stage) cudaFreeHost(s->stage);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError();
+    delete s;
+}
+
+long long vboc_pool_size(vboc_pool *s) { return s ? s->size : 0; }
+
+int vboc_pool_upload(vboc_pool *s, long long count, const float *x) {
+    if (!s || !x || count < 0 || count > s->cap) return fail(VBOC_ERR_ARG, "vboc_pool_upload: bad argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    int rc = pool_copy(s, s->x[s->cur], x, (size_t)count * s->n_in * sizeof(float), true);
+    if (rc) return rc;
+    s->size = count, s->sel_count = 0;
+    return 0;
+}
+
+int vboc_pool_score(vboc_pool *s, vboc_mlp *m, double mean, double stdv) {
+    if (!s || !m || m->n_in != s->n_in) return fail(VBOC_ERR_ARG, "vboc_pool_score: bad argument");
+    if (m->device != s->device) return fail(VBOC_ERR_ARG, "vboc_pool_score: pool and network live on different devices");
+    if (s->size == 0) return 0;
+    CUDA_OK(cudaSetDevice(s->device));
+    int rc = mlp_launch(m, s->size, s->x[s->cur], 2, mean, stdv, 0.0, nullptr, s->score, nullptr, s->stream);
+    if (rc) return rc;
+    if ((rc = mlp_finish(m, s->stream))) return rc;
+    s->last_score_ms = m->last_ms;
+    return 0;
+}
+
+int vboc_pool_download_scores(vboc_pool *s, float *score) {
+    if (!s || !score) return fail(VBOC_ERR_ARG, "vboc_pool_download_scores: bad argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    return pool_copy(s, score, s->score, (size_t)s->size * sizeof(float), false);
+}
+
+int vboc_pool_select(vboc_pool *s, int k, long long *idx, float *x, float *score) {
+    if (!s || k < 0 || !idx) return fail(VBOC_ERR_ARG, "vboc_pool_select: bad argument");
+    if (k > s->size) return fail(VBOC_ERR_ARG, "vboc_pool_select: k exceeds the pool size");
+    s->sel_count = 0;
+    if (k == 0) return 0;
+    CUDA_OK(cudaSetDevice(s->device));
+    const long long P = s->size;
+    const unsigned grid = (unsigned)((P + POOL_BLOCK - 1) / POOL_BLOCK);
+    // radix select of the k-th largest score on the (order preserving) bit pattern: 11 + 11 + 10 bits
+    unsigned int prefix = 0, prefix_mask = 0, hist[2048];
+    long long need = k;  // how many of the elements matching the prefix are still to be taken from the top
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        CUDA_OK(cudaMemsetAsync(s->hist, 0, 2048 * sizeof(unsigned int), s->stream));
+        pool_hist_kernel<<<grid, POOL_THREADS, 0, s->stream>>>(s->score, P, prefix, prefix_mask, shifts[pass], bits[pass], s->hist);
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpyAsync(hist, s->hist, 2048 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        int b = (1 << bits[pass]) - 1;
+        for (; b > 0 && (long long)hist[b] < need; --b) need -= hist[b];
+        prefix |= (unsigned)b << shifts[pass];
+        prefix_mask |= (unsigned)((1 << bits[pass]) - 1) << shifts[pass];
+    }
+    // prefix = key of the k-th largest score; `need` of the elements with exactly that key are taken
+    const long long above = k - need;
+    CUDA_OK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned int), s->stream));
+    CUDA_OK(cudaMemsetAsync(s->flags, 0, (size_t)P * sizeof(int), s->stream));
+    pool_pick_kernel<<<grid, POOL_THREADS, 0, s->stream>>>(s->score, P, prefix, (unsigned)above, (unsigned)need, s->sel,
+                                                           s->flags, s->counters);
+    CUDA_OK(cudaGetLastError());
+    std::vector<long long> h(k);
+    CUDA_OK(cudaMemcpyAsync(h.data(), s->sel, (size_t)k * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    std::sort(h.begin(), h.end(), [](long long a, long long b) { return a > b; });  // largest index first (the drivers' order)
+    memcpy(idx, h.data(), (size_t)k * sizeof(long long));
+    s->sel_count = k;
+    if (x || score) {
+        // the selected rows / scores in that order: gathered on the device, one copy back
+        CUDA_OK(cudaMemcpyAsync(s->sel, h.data(), (size_t)k * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+        float *gx = s->x[s->cur ^ 1];  // the other buffer is scratch between compactions
+        pool_gather_kernel<<<(k + 127) / 128, 128, 0, s->stream>>>(s->x[s->cur], s->score, s->sel, k, s->n_in, gx,
+                                                                  gx + (size_t)k * s->n_in);
+        CUDA_OK(cudaGetLastError());
+        int rc;
+        if (x && (rc = pool_copy(s, x, gx, (size_t)k * s->n_in * sizeof(float), false))) return rc;
+        if (score && (rc = pool_copy(s, score, gx + (size_t)k * s->n_in, (size_t)k * sizeof(float), false))) return rc;
+    }
+    return 0;
+}
+
+int vboc_pool_remove_selected(vboc_pool *s) {
+    if (!s) return fail(VBOC_ERR_ARG, "vboc_pool_remove_selected: null handle");
+    if (s->sel_count == 0) return 0;
+    CUDA_OK(cudaSetDevice(s->device));
+    const long long P = s->size;
+    const unsigned grid = (unsigned)((P + POOL_BLOCK - 1) / POOL_BLOCK);
+    // stable compaction (np.delete keeps the order of the survivors): per-block kept counts, offsets on the host
+    pool_count_kernel<<<grid, POOL_THREADS, 0, s->stream>>>(s->flags, P, s->blk);
+    CUDA_OK(cudaGetLastError());
+    std::vector<long long> cnt(grid + 1);
+    CUDA_OK(cudaMemcpyAsync(cnt.data(), s->blk, grid * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    long long run = 0;
+    for (unsigned b = 0; b < grid; ++b) {
+        long long c = cnt[b];
+        cnt[b] = run;
+        run += c;
+    }
+    CUDA_OK(cudaMemcpyAsync(s->blk, cnt.data(), grid * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+    pool_compact_kernel<<<grid, POOL_THREADS, 0, s->stream>>>(s->x[s->cur], s->flags, P, s->n_in, s->blk, s->x[s->cur ^ 1]);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    if (run != P - s->sel_count) return fail(VBOC_ERR_CUDA, "vboc_pool_remove_selected: compaction count mismatch");
+    s->cur ^= 1, s->size = run, s->sel_count = 0;
+    return 0;
+}
+
+int vboc_pool_download(vboc_pool *s, float *x) {
+    if (!s || !x) return fail(VBOC_ERR_ARG, "vboc_pool_download: bad argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    return pool_copy(s, x, s->x[s->cur], (size_t)s->size * s->n_in * sizeof(float), false);
+}
+
+double vboc_pool_last_score_ms(vboc_pool *s) { return s ? s->last_score_ms : -1.0; }
 
 double vboc_mlp_last_kernel_ms(vboc_mlp *m) { return m ? m->last_ms : -1.0; }
 
@@ -922,7 +1242,7 @@ struct vboc_datagen {
     int *djs;
     double *dp, *dlb0, *dub0, *dretry, *drows, *dwork;
     DgCounters *dcnt;
-    unsigned int *dcounter;
+    unsigned int *dcounter;  // [0] problem counter, [2..3] kernel start time (64 bit)
     size_t work_doubles;
     char *stage;  // pinned staging
     size_t stage_bytes;
@@ -949,7 +1269,7 @@ static int datagen_create_impl(vboc_datagen *s, int n_dof, int capacity, int dev
     CUDA_OK(cudaMalloc((void **)&s->dretry, B * DG_RETRIES * (n_dof + 1) * sizeof(double)));
     CUDA_OK(cudaMalloc((void **)&s->drows, B * DG_ROWS_MAX * nx * sizeof(double)));
     CUDA_OK(cudaMalloc((void **)&s->dcnt, B * sizeof(DgCounters)));
-    CUDA_OK(cudaMalloc((void **)&s->dcounter, sizeof(unsigned int)));
+    CUDA_OK(cudaMalloc((void **)&s->dcounter, 4 * sizeof(unsigned int)));
     CUDA_OK(cudaMalloc((void **)&s->dwork, (size_t)s->grid * WARPS_PER_CTA * s->work_doubles * sizeof(double)));
     s->stage_bytes = (size_t)8 << 20;
     CUDA_OK(cudaMallocHost((void **)&s->stage, s->stage_bytes));
@@ -1043,16 +1363,17 @@ int vboc_datagen_run(vboc_datagen *s, int count, int N0, double dt, double tol, 
     P.N0 = N0, P.dt = dt, P.tol = tol;
     // limits of the reference models (VBOC/triplependulum_class_vboc.py:90-93, VBOC/doublependulum_class_vboc.py:114-117)
     P.q_min = M_PI - M_PI / 4, P.q_max = M_PI + M_PI / 4, P.v_max = 10.0, P.u_max = 10.0;
-    CUDA_OK(cudaMemsetAsync(s->dcounter, 0, sizeof(unsigned int), s->stream));
+    CUDA_OK(cudaMemsetAsync(s->dcounter, 0, 4 * sizeof(unsigned int), s->stream));
     CUDA_OK(cudaEventRecord(s->ev0, s->stream));
+    unsigned long long *t_start = reinterpret_cast<unsigned long long *>(s->dcounter + 2);
     if (n == 2) {
         DgIO<2> io{s->djs, s->dp, s->dlb0, s->dub0, s->dretry, s->drows, s->dcnt};
         datagen_kernel<2><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(io, count, P, s->opts, s->dwork, s->work_doubles,
-                                                                       s->dcounter);
+                                                                       s->dcounter, t_start);
     } else {
         DgIO<3> io{s->djs, s->dp, s->dlb0, s->dub0, s->dretry, s->drows, s->dcnt};
         datagen_kernel<3><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(io, count, P, s->opts, s->dwork, s->work_doubles,
-                                                                       s->dcounter);
+                                                                       s->dcounter, t_start);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("datagen_kernel launch: ") + cudaGetErrorString(e));

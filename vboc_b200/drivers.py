@@ -646,6 +646,36 @@ def al_query(net, pool, mean, std, B, sharded=False):
     return idx, etp, float(np.max(etp[idx])) if len(idx) else 0.0
 
 
+def al_query_resident(rp, net, mean, std, B, sharded=False):
+    """`al_query` on a pool that is RESIDENT on the device (`nn.ResidentPool`): entropy of every pool row
+    by the fused MLP kernel, top-B by the device radix select, removal of the queried rows by the device compaction --
+    only the B selected rows come back.  Returns (indices into the pool as it was before the removal, largest first;
+    the selected rows (float32); largest selected entropy).
+    sharded=True: every rank holds a different shard; each rank's candidates are its local top-B, the global top-B is
+    cut from the gathered candidate scores and each rank keeps (and removes) its part of it."""
+    rp.score(net, mean, std)
+    k = min(int(B), len(rp))
+    idx, x, sc = rp.select(k)
+    emax = float(sc.max()) if k else 0.0
+    if sharded:
+        from . import distributed as vd
+        allsc = vd.all_gather_rows(sc.astype(np.float64)[:, None])[:, 0]
+        kk = min(int(B), allsc.shape[0])
+        if kk:
+            cut = np.partition(allsc, -kk)[-kk]
+            emax = float(allsc.max())
+            # ties at the cut are shared out in rank order so that the ranks' parts add up to exactly B
+            above = int((sc > cut).sum())
+            ties_all = vd.all_gather_rows(np.array([[float((sc == cut).sum())]]))[:, 0].astype(int)
+            import torch.distributed as dist
+            want_ties = kk - int((allsc > cut).sum())
+            before = int(ties_all[:dist.get_rank()].sum())
+            mine = max(0, min(int(ties_all[dist.get_rank()]), want_ties - before))
+            idx, x, sc = rp.select(above + mine)
+    rp.remove_selected()
+    return idx, x, emax
+
+
 # ------------------------------------------------------------------------------------------------
 # on-disk formats read by the untouched *_comparison.py scripts (SURVEY 8(f)3): vboc_b200/io.py
 def save_testdata(n, X_test, directory="."):

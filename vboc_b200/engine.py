@@ -231,7 +231,7 @@ class StreamSolver:
         return [got[t] for t in tk]
 
 
-_DG_DTYPE = np.dtype([(f, "i4") for f in ("status", "n_rows", "solves", "converged", "sim_steps", "sqp_iter", "qp_iter", "pad_")])
+_DG_DTYPE = np.dtype([(f, "i4") for f in ("status", "n_rows", "solves", "converged", "sim_steps", "sqp_iter", "qp_iter", "t_done_us")])
 
 
 class DataGenerator:

@@ -79,3 +79,51 @@ def select_max_entropy(entropy, B):
     idx = np.argpartition(entropy, -B)[-B:].tolist()
     idx.sort(reverse=True)
     return idx
+
+
+class ResidentPool:
+    """The AL drivers' unlabeled pool kept in HBM across rounds (`vboc_pool_*`): `score(net, mean, std)` runs the fused
+    MLP + entropy kernel over the resident rows, `select(k)` is the device top-k (indices largest first, rows, scores),
+    `remove_selected()` the device `np.delete`.  Per round only the k selected rows cross the host link."""
+
+    def __init__(self, X, device=0, capacity=None):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        self.n_in = X.shape[1]
+        self._h = C.c_void_p()
+        check(_lib.lib().vboc_pool_create(int(device), self.n_in, int(capacity or max(len(X), 1)), C.byref(self._h)))
+        check(_lib.lib().vboc_pool_upload(self._h, len(X), _fp(X)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().vboc_pool_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __len__(self):
+        return int(_lib.lib().vboc_pool_size(self._h))
+
+    def score(self, net, mean, std):
+        check(_lib.lib().vboc_pool_score(self._h, net._h, float(mean), float(std)))
+        return _lib.lib().vboc_pool_last_score_ms(self._h)
+
+    def select(self, k):
+        k = int(k)
+        idx = np.empty(k, dtype=np.int64)
+        x = np.empty((k, self.n_in), dtype=np.float32)
+        sc = np.empty(k, dtype=np.float32)
+        check(_lib.lib().vboc_pool_select(self._h, k, idx.ctypes.data_as(C.POINTER(C.c_longlong)), _fp(x), _fp(sc)))
+        return idx, x, sc
+
+    def remove_selected(self):
+        check(_lib.lib().vboc_pool_remove_selected(self._h))
+
+    def scores(self):
+        sc = np.empty(len(self), dtype=np.float32)
+        check(_lib.lib().vboc_pool_download_scores(self._h, _fp(sc)))
+        return sc
+
+    def rows(self):
+        x = np.empty((len(self), self.n_in), dtype=np.float32)
+        check(_lib.lib().vboc_pool_download(self._h, _fp(x)))
+        return x

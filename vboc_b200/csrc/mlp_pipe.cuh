@@ -59,15 +59,19 @@ __device__ __forceinline__ void tp_wait(uint32_t bar, uint32_t parity) {
 }
 
 // W2img: [Hp / 8 chunks][hi | lo][b_bytes]: the shared-memory images of the B operand chunks
+// NIN / NOUT are compile-time (2n in {2, 4, 6}, 1 or 2 outputs: every network of the reference) so that the row's
+// inputs and outputs live in registers and the layer-1 / output-layer loops unroll.
+template <int NIN, int NOUT>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_pipe_kernel(const MlpParams P, int Hp, int tmem_cols,
                                                                  const unsigned char *__restrict__ W2img, long long batch) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const TpLayout lay(Hp, P.n_in, P.n_out);
-    float *sW1 = (float *)(smraw + lay.off_w()), *sb1 = sW1 + (size_t)Hp * P.n_in, *sb2 = sb1 + Hp, *sW3 = sb2 + Hp;
+    const TpLayout lay(Hp, NIN, NOUT);
+    float *sW1 = (float *)(smraw + lay.off_w()), *sb1 = sW1 + (size_t)Hp * NIN, *sb2 = sb1 + Hp, *sW3 = sb2 + Hp;
     unsigned long long *bars = (unsigned long long *)(smraw + lay.off_bar());
     // bars[0..3] B slot full, bars[4..5] MMA of the A slot done, bars[8] (as uint32) TMEM base
     uint32_t *tmem_slot = (uint32_t *)(bars + 8);
-    const int t = threadIdx.x, warp = t >> 5, n = P.n_in / 2;
+    const int t = threadIdx.x, warp = t >> 5;
+    constexpr int n = NIN / 2;
     const int NCH = Hp / TP_KC;
     const long long tiles = (batch + TC_ROWS - 1) / TC_ROWS;
     const uint32_t bfull0 = tc_smem(bars), mdone0 = tc_smem(bars + 4);
@@ -84,9 +88,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_pipe_kernel(const MlpParams
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // small weights into shared memory (zero padded copies: W1p, b1p, b2p, W3p)
-    for (int i = t; i < Hp * P.n_in; i += TC_THREADS) sW1[i] = P.W1[i];
+    for (int i = t; i < Hp * NIN; i += TC_THREADS) sW1[i] = P.W1[i];
     for (int i = t; i < Hp; i += TC_THREADS) sb1[i] = P.b1[i], sb2[i] = P.b2[i];
-    for (int i = t; i < P.n_out * Hp; i += TC_THREADS) sW3[i] = P.W3[i];
+    for (int i = t; i < NOUT * Hp; i += TC_THREADS) sW3[i] = P.W3[i];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -114,16 +118,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_pipe_kernel(const MlpParams
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long row = tile * TC_ROWS + t;
         // ---- input normalisation (thread = row)
-        float xin[MLP_MAX_IN], nv = 0.f;
-        for (int i = 0; i < P.n_in; ++i) xin[i] = row < batch ? P.x[(size_t)row * P.n_in + i] : 0.f;
+        float xin[NIN], nv = 0.f;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) xin[i] = row < batch ? P.x[(size_t)row * NIN + i] : 0.f;
         if (P.mode == 1) {
-            for (int i = n; i < P.n_in; ++i) nv += xin[i] * xin[i];
+#pragma unroll
+            for (int i = n; i < NIN; ++i) nv += xin[i] * xin[i];
             nv = sqrtf(nv);
+#pragma unroll
             for (int i = 0; i < n; ++i) xin[i] = (xin[i] - P.mean) / P.stdv;
-            if (nv != 0.f)
-                for (int i = n; i < P.n_in; ++i) xin[i] = xin[i] / nv;
+            if (nv != 0.f) {
+#pragma unroll
+                for (int i = n; i < NIN; ++i) xin[i] = xin[i] / nv;
+            }
         } else if (P.mode == 2) {
-            for (int i = 0; i < P.n_in; ++i) xin[i] = (xin[i] - P.mean) / P.stdv;
+#pragma unroll
+            for (int i = 0; i < NIN; ++i) xin[i] = (xin[i] - P.mean) / P.stdv;
         }
         for (int ch = 0; ch < NCH; ++ch, ++g) {
             const int as = (int)(g & (TP_ASLOTS - 1)), q = (int)(g & (TP_BSLOTS - 1));
@@ -139,7 +149,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_pipe_kernel(const MlpParams
                 for (int e = 0; e < 4; ++e) {
                     const int k = ch * TP_KC + 4 * c + e;
                     float a = sb1[k];
-                    for (int i = 0; i < P.n_in; ++i) a = fmaf(xin[i], sW1[k * P.n_in + i], a);
+#pragma unroll
+                    for (int i = 0; i < NIN; ++i) a = fmaf(xin[i], sW1[k * NIN + i], a);
                     tc_split(fmaxf(a, 0.f), hi[e], lo[e]);
                 }
                 *(float4 *)(sA_hi + c * lay.a_lbo + t * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -174,8 +185,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_pipe_kernel(const MlpParams
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
         // ---- epilogue: thread = row; accumulators from TMEM, bias + ReLU, output layer, final op
-        float o[MLP_MAX_OUT];
-        for (int k = 0; k < MLP_MAX_OUT; ++k) o[k] = 0.f;
+        float o[NOUT];
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) o[k] = 0.f;
         const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int c0 = 0; c0 < Hp; c0 += 16) {
             uint32_t r[16];
@@ -188,22 +200,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_pipe_kernel(const MlpParams
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float v = fmaxf(__uint_as_float(r[j]) + sb2[c0 + j], 0.f);
-                for (int k = 0; k < P.n_out; ++k) o[k] = fmaf(v, sW3[k * Hp + c0 + j], o[k]);
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) o[k] = fmaf(v, sW3[k * Hp + c0 + j], o[k]);
             }
         }
         if (row < batch) {
-            for (int k = 0; k < P.n_out; ++k) {
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) {
                 float a = o[k] + P.b3[k];
                 o[k] = P.final_relu ? fmaxf(a, 0.f) : a;
-                if (P.out) P.out[(size_t)row * P.n_out + k] = o[k];
+                if (P.out) P.out[(size_t)row * NOUT + k] = o[k];
             }
             if (P.mode == 1) {
                 if (P.label) P.label[row] = nv > o[0] ? 0 : 1;
                 if (P.aux) P.aux[row] = o[0] * P.margin_scale - nv;
             } else if (P.mode == 2 && P.aux) {
-                float pr[MLP_MAX_OUT], s = 0.f, e = 0.f;
-                for (int k = 0; k < P.n_out; ++k) pr[k] = 1.f / (1.f + expf(-o[k])), s += pr[k];
-                for (int k = 0; k < P.n_out; ++k) {
+                float pr[NOUT], s = 0.f, e = 0.f;
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) pr[k] = 1.f / (1.f + expf(-o[k])), s += pr[k];
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) {
                     float q = pr[k] / s;
                     if (q > 0.f) e -= q * logf(q);
                 }

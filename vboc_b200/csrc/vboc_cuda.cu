@@ -933,9 +933,23 @@ static int mlp_launch(vboc_mlp *m, long long batch, const float *dx, int mode, d
             mlp_tc_kernel<<<(unsigned)tiles, TC_THREADS, lay.total(), stream>>>(P, m->Hp, cols);
         } else {
             TpLayout lay(m->Hp, m->n_in, m->n_out);
-            CUDA_OK(cudaFuncSetAttribute(mlp_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total()));
             const unsigned grid = (unsigned)(tiles < m->num_sms ? tiles : m->num_sms);  // persistent: one CTA per SM
-            mlp_pipe_kernel<<<grid, TC_THREADS, lay.total(), stream>>>(P, m->Hp, cols, m->W2img, batch);
+            bool launched = false;
+#define GO(NIN, NOUT)                                                                                                  \
+    if (m->n_in == NIN && m->n_out == NOUT) {                                                                          \
+        CUDA_OK(cudaFuncSetAttribute(mlp_pipe_kernel<NIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                     (int)lay.total()));                                                               \
+        mlp_pipe_kernel<NIN, NOUT><<<grid, TC_THREADS, lay.total(), stream>>>(P, m->Hp, cols, m->W2img, batch);        \
+        launched = true;                                                                                               \
+    }
+            GO(2, 1) GO(2, 2) GO(4, 1) GO(4, 2) GO(6, 1) GO(6, 2)
+#undef GO
+            if (!launched) {  // a network shape the reference does not have: the serial kernel handles any n_in / n_out
+                if (!dout) return fail(VBOC_ERR_ARG, "mlp: this network shape needs an output array");
+                TcLayout lay1(m->Hp);
+                CUDA_OK(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay1.total()));
+                mlp_tc_kernel<<<(unsigned)tiles, TC_THREADS, lay1.total(), stream>>>(P, m->Hp, cols);
+            }
         }
     } else {
         if (!dout) return fail(VBOC_ERR_ARG, "mlp: the CUDA-core kernel needs an output array");

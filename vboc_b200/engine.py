@@ -48,7 +48,7 @@ class BatchSolver:
         self._batch = 0
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
             _lib.lib().vboc_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -159,7 +159,7 @@ class StreamSolver:
         self._N = {}
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
             _lib.lib().vboc_stream_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -247,7 +247,7 @@ class DataGenerator:
             check(_lib.lib().vboc_datagen_set_opts(self._h, C.byref(opts)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
             _lib.lib().vboc_datagen_destroy(self._h)
             self._h = C.c_void_p()
 

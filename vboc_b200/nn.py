@@ -36,7 +36,7 @@ class MLP:
                    g(lin[2].bias), final_relu, device)
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
             _lib.lib().vboc_mlp_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -94,7 +94,7 @@ class ResidentPool:
         check(_lib.lib().vboc_pool_upload(self._h, len(X), _fp(X)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
             _lib.lib().vboc_pool_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -39,6 +39,8 @@ extern "C" {
 
 #define VBOC_FAMILY_VBOC 0 /* VBOC/ *_class_vboc.py: linear cost, dt state, stage-0 direction constraint */
 #define VBOC_FAMILY_AL 1   /* AL/ *_class_al.py: LINEAR_LS cost on velocities, x0 fixed             */
+#define VBOC_FAMILY_MPC 2  /* VBOC/Safe MPC/ *_class_fixedveldir.py: LINEAR_LS tracking cost, x0 fixed, the learned
+                              viability margin h(x_N) >= 0 as a nonlinear terminal constraint (vboc_set_mpc) */
 
 #define VBOC_MODE_SQP 0 /* nlp_solver_type "SQP"     */
 #define VBOC_MODE_RTI 1 /* nlp_solver_type "SQP_RTI" */
@@ -140,6 +142,27 @@ int vboc_download(vboc_solver *s, double *x, double *u, vboc_stats *stats);
  */
 int vboc_export_multipliers(vboc_solver *s, int on);
 int vboc_download_multipliers(vboc_solver *s, double *pi, double *lam);
+/*
+ * MPC family (vboc_create(n, VBOC_FAMILY_MPC, ...), n = 2 or 3): the OCP of the reference's Safe-MPC classes with the
+ * learned viability margin INSIDE the optimisation (SURVEY 8(f)4;
+ * VBOC/Safe MPC/hard_terminal_constraints/doublependulum_class_fixedveldir.py:110-258,
+ * VBOC/Safe MPC/parallel/doublependulum_class_fixedveldir.py:240-264):
+ *   min  sum_k Ts/2 |y_k - y_ref|^2_W + 1/2 |x_N - y_ref_e|^2_W_e     y = [x; u], LINEAR_LS, Gauss-Newton + LM
+ *   s.t. x_{k+1} = Phi_Ts(x_k, u_k), x_0 = given (lbx0 == ubx0), box bounds, lh <= h(x_N) <= uh,
+ *        h(x) = out(x) (100 - safety_margin)/100 - max(|v|, 1e-3),  out = the 2n-H-H-1 MLP on [(q - mean)/std, v/|v|]
+ *        without its output ReLU (nn_decisionfunction).
+ * vboc_set_mpc: the network (PyTorch nn.Linear layout, float32, one output), its normalisation, the constraint's
+ * bounds and the diagonals of cost.W (3n, order [x; u]) and cost.W_e (2n); vboc_set_mpc_reference: y_ref [batch][3n]
+ * and y_ref_e [batch][2n] of the problems of the next vboc_upload / vboc_solve_batch (cost_set(i, 'y_ref', ...),
+ * :208-213).  vboc_solve_batch then takes x_guess [batch][N_max+1][2n], p = C0 = NULL, Tf = horizon in seconds,
+ * mode VBOC_MODE_RTI (the classes' default nlp_solver_type) or VBOC_MODE_SQP.  vboc_download_mpc_multipliers: the
+ * (lower, upper) multipliers of the terminal constraint at the returned iterate, lamg [batch][2].
+ */
+int vboc_set_mpc(vboc_solver *s, int hidden, const float *W1, const float *b1, const float *W2, const float *b2,
+                 const float *W3, const float *b3, double mean, double stdv, double safety_margin, double lh, double uh,
+                 const double *W, const double *W_e);
+int vboc_set_mpc_reference(vboc_solver *s, int batch, const double *yref, const double *yref_e);
+int vboc_download_mpc_multipliers(vboc_solver *s, double *lamg);
 /* Device time of the last vboc_solve_resident kernel in milliseconds (CUDA events on the solver's
  * stream); negative if none. */
 double vboc_last_kernel_ms(vboc_solver *s);

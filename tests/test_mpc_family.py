@@ -1,0 +1,88 @@
+"""SURVEY 8(f)4 on the CPU: the MPC family of the warp solver (tracking cost + the learned viability margin as a
+nonlinear terminal constraint, `nn_margin.h`) compiled for the host by tools/emu, certified WITHOUT an oracle
+(tools/certify.py, numpy): the step of one SQP_RTI iteration satisfies the dense KKT conditions of the QP linearised
+at the guess -- including the constraint row, whose gradient the kernel forms by reverse mode through the network and
+numpy by the complex step -- and a converged SQP run satisfies the NLP's KKT conditions."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from vboc_b200 import problems as pr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tools", "emu"))
+import certify  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu as e
+    e.build()
+    return e
+
+
+def make_net(n, H, seed, b3):
+    rng = np.random.default_rng(seed)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    return dict(W1=f32(rng.normal(size=(H, 2 * n)) / np.sqrt(2 * n)), b1=f32(rng.normal(size=H) * 0.1),
+                W2=f32(rng.normal(size=(H, H)) / np.sqrt(H)), b2=f32(rng.normal(size=H) * 0.1),
+                W3=f32(rng.normal(size=H) / np.sqrt(H)), b3=b3, mean=np.pi, std=0.45, scale=1.0)
+
+
+def mpc_opts(emu, qp_tol=1e-9, tol=1e-2):
+    o = emu.Opts()
+    o.tol_stat = o.tol_eq = o.tol_ineq = o.tol_comp = tol
+    o.max_iter, o.levenberg_marquardt = 1000, 1.0
+    o.alpha_min, o.alpha_reduction, o.globalization = 1e-2, 0.3, 1
+    o.qp_tol_stat = o.qp_tol_eq = o.qp_tol_ineq = o.qp_tol_comp = qp_tol
+    o.qp_iter_max, o.qp_mu0, o.qp_alpha_min, o.qp_reg_prim = 100, 1e1, 1e-12, 1e-15
+    o.qp_lam_min = o.qp_t_min = o.qp_tau_min = 1e-16
+    return o
+
+
+@pytest.mark.parametrize("n,H", [(2, 64), (3, 96)])
+def test_rti_step_satisfies_dense_kkt_with_the_margin_row(emu, n, H):
+    net = make_net(n, H, n, 4.0)
+    bp = pr.sample_mpc(n, 24, seed=3)
+    out = emu.solve_mpc(n, 1, bp, net, mpc_opts(emu), multipliers=True)
+    assert set(np.unique(out["status"]).tolist()) == {0, 4}
+    active = 0
+    for b in range(24):
+        if out["status"][b] != 0:
+            continue   # infeasible QP: a margin too negative to repair within 10 ms, or a state about to leave the box
+        r = certify.mpc_kkt(n, bp, net, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["lamg"][b], 1.0,
+                            first_qp_at_guess=True)
+        assert max(r["res_stat"], r["res_eq"], r["res_ineq"]) < 1e-8 and r["res_comp"] < 1e-8 and r["lam_min"] >= 0.0, (b, r)
+        active += out["lamg"][b, 0] > 1e-3
+    assert active >= 2                   # the terminal constraint binds on some problems (row and multiplier exercised)
+
+
+def test_sqp_run_satisfies_nlp_kkt(emu):
+    n = 2
+    net = make_net(n, 64, 0, 4.0)
+    bp = pr.sample_mpc(n, 12, seed=3)
+    out = emu.solve_mpc(n, 0, bp, net, mpc_opts(emu, tol=1e-2), multipliers=True)
+    ok = out["status"] == 0
+    assert ok.sum() >= 6 and ((out["status"] == 4) | ok).all()
+    for b in np.where(ok)[0]:
+        r = certify.mpc_kkt(n, bp, net, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["lamg"][b], 1.0)
+        assert r["res_stat"] < 1e-2 and r["res_eq"] < 1e-2 and r["res_ineq"] < 1e-2 and r["res_comp"] < 1e-2
+        # the engine's own residuals are the recomputed ones
+        assert abs(r["res_stat"] - out["res"][b, 0]) < 1e-9 and abs(r["res_ineq"] - out["res"][b, 2]) < 1e-9
+        assert r["h"] >= -1e-2            # the returned terminal state is inside the learned set (to tolerance)
+
+
+def test_margin_function_matches_the_reference_expression():
+    """certify.nn_margin restates nn_decisionfunction; the shim's numeric twin is an independent transcription."""
+    sys.path.insert(0, os.path.join(ROOT, "vboc_b200", "shim", "SafeMPC"))
+    from vboc_b200.shim.SafeMPC.doublependulum_class_fixedveldir import OCPdoublependulumINIT
+    net = make_net(2, 32, 5, 3.0)
+    params = [net[k] if k != "W3" else net[k][None, :] for k in ("W1", "b1", "W2", "b2", "W3")] + [np.array([net["b3"]])]
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x = np.concatenate([rng.uniform(2.4, 3.9, 2), rng.uniform(-8, 8, 2)])
+        want = OCPdoublependulumINIT.nn_decisionfunction(None, params, net["mean"], net["std"], 0.0, x)
+        assert abs(certify.nn_margin(net, x, 2) - want) < 1e-12

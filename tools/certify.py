@@ -258,6 +258,90 @@ def qp_kkt(n, bp, b, dx, du, pi_q, lam_q, lm=1e-5):
     return dict(res_g=np.abs(r).max(), res_b=res_b, res_d=res_d, res_m=res_m, lam_min=np.where(ineq, np.minimum(ll, lu), 0).min())
 
 
+# ------------------------------------------------------------------------------------------------ MPC family (8(f)4)
+def nn_margin(net, x, n):
+    """`nn_decisionfunction` of the reference's Safe-MPC classes
+    (VBOC/Safe MPC/hard_terminal_constraints/doublependulum_class_fixedveldir.py:232-258) in numpy, complex-step safe:
+    h(x) = scale * MLP([(q - mean) / std, v / vn]) - vn,  vn = max(|v|, 1e-3), no ReLU on the output."""
+    q, v = x[..., :n], x[..., n:]
+    vn = np.sqrt(np.sum(v * v, axis=-1))
+    vn = np.where(vn.real > 1e-3, vn, 1e-3)
+    a = np.concatenate([(q - net["mean"]) / net["std"], v / vn[..., None]], axis=-1)
+    a = a @ net["W1"].T + net["b1"]
+    a = np.where(a.real > 0, a, 0)
+    a = a @ net["W2"].T + net["b2"]
+    a = np.where(a.real > 0, a, 0)
+    out = a @ net["W3"] + net["b3"]
+    return out * net["scale"] - vn
+
+
+def nn_margin_grad(net, x, n):
+    eps = 1e-30
+    g = np.empty(x.shape)
+    for j in range(x.shape[-1]):
+        xc = x.astype(complex)
+        xc[..., j] += 1j * eps
+        g[..., j] = nn_margin(net, xc, n).imag / eps
+    return nn_margin(net, x, n).real, g
+
+
+def mpc_kkt(n, bp, net, b, x, u, pi, lam, lamg, lm, first_qp_at_guess=False):
+    """KKT residuals of MPC problem b of `bp` (problems.sample_mpc).
+
+    first_qp_at_guess=False: the NLP's four acados residuals at the iterate (x, u) with multipliers (pi, lam, lamg) --
+    the SQP exit test.  True: (x, u) = guess + the step of ONE SQP_RTI iteration; the residuals are then those of the
+    QP linearised at the guess (dynamics, constraint row and Gauss-Newton cost + Levenberg-Marquardt term), whose
+    strict convexity makes a KKT point THE solution.  Lagrangian: cost + pi'(Phi - x+) + lam_u (z - ub) + lam_l (lb - z)
+    + lamg_u (h - uh) + lamg_l (lh - h)."""
+    N = int(bp["N"][b])
+    nx, nz, h = 2 * n, 3 * n, bp["Tf"] / int(bp["N"][b])
+    X, U = x[:N + 1, :nx], u[:N]
+    Wz, WzN, yref, yrefN = bp["Wz"], bp["WzN"], bp["yref"][b], bp["yrefN"][b]
+    lb = np.concatenate([bp["lbu"][b], bp["lbx"][b]])
+    ub = np.concatenate([bp["ubu"][b], bp["ubx"][b]])
+    Z = np.concatenate([np.concatenate([U, np.zeros((1, n))]), X], axis=1)
+    exists = np.ones((N + 1, nz), dtype=bool)
+    exists[N, :n] = False
+    fixed = np.zeros((N + 1, nz), dtype=bool)
+    fixed[0, n:] = True                                                # x_0 = x0
+    ineq = exists & ~fixed
+    ll, lu = lam[:N + 1, :, 0], lam[:N + 1, :, 1]
+    if first_qp_at_guess:
+        Xg, Ug = bp["x_guess"][b, :N + 1], bp["u_guess"][b, :N]
+        Zg = np.concatenate([np.concatenate([Ug, np.zeros((1, n))]), Xg], axis=1)
+        xn, A, Bm = rk4_jac(n, Xg[:N], Ug, h)
+        DZ = Z - Zg
+        res_eq = np.abs(np.einsum("kij,kj->ki", A, DZ[:N, n:]) + np.einsum("kij,kj->ki", Bm, DZ[:N, :n]) + (xn - Xg[1:]) - DZ[1:, n:]).max()
+        hv, gc = nn_margin_grad(net, Xg[N], n)
+        hlin = hv + gc @ DZ[N, n:]                                     # the row of the QP
+        scale = np.concatenate([np.full(N, h), [1.0]])[:, None]
+        W = np.concatenate([np.tile(Wz, (N, 1)), np.concatenate([np.zeros(n), WzN])[None]])
+        ref = np.concatenate([np.tile(yref, (N, 1)), np.concatenate([np.zeros(n), yrefN])[None]])
+        grad = scale * W * (Zg - ref) + (scale * W + lm) * DZ          # Gauss-Newton + LM, at the QP solution
+        x0_err = np.abs(Z[0, n:] - bp["x0"][b]).max()
+    else:
+        xn, A, Bm = rk4_jac(n, X[:N], U, h)
+        res_eq = np.abs(xn - X[1:]).max()
+        hv, gc = nn_margin_grad(net, X[N], n)
+        hlin = hv
+        scale = np.concatenate([np.full(N, h), [1.0]])[:, None]
+        W = np.concatenate([np.tile(Wz, (N, 1)), np.concatenate([np.zeros(n), WzN])[None]])
+        ref = np.concatenate([np.tile(yref, (N, 1)), np.concatenate([np.zeros(n), yrefN])[None]])
+        grad = scale * W * (Z - ref)
+        x0_err = np.abs(Z[0, n:] - bp["x0"][b]).max()
+    fl, fu = lb - Z, Z - ub
+    res_ineq = max(np.where(ineq, np.maximum(np.maximum(fl, fu), 0), 0).max(), x0_err, bp["lh"] - hlin, hlin - bp["uh"], 0.0)
+    res_comp = max(np.where(ineq, np.maximum(np.abs(ll * fl), np.abs(lu * fu)), 0).max(),
+                   abs(lamg[0] * (bp["lh"] - hlin)), abs(lamg[1] * (hlin - bp["uh"])))
+    r = grad + np.where(ineq, lu - ll, 0.0)
+    r[:N] += np.einsum("kij,ki->kj", np.concatenate([Bm, A], axis=2), pi[:N])
+    r[1:, n:] -= pi[:N]
+    r[N, n:] += gc * (lamg[1] - lamg[0])
+    r = np.where(ineq, r, 0.0)
+    return dict(res_stat=np.abs(r).max(), res_eq=res_eq, res_ineq=res_ineq, res_comp=res_comp,
+                lam_min=min(np.where(ineq, np.minimum(ll, lu), 0).min(), lamg.min()), h=hlin)
+
+
 # ------------------------------------------------------------------------------------------------ report
 def _solve_with_multipliers(n, family, bp, mode, opts=None):
     from vboc_b200 import engine

@@ -173,3 +173,55 @@ extern "C" int emu_datagen_run(int n, int count, int N0, double dt, double tol, 
     else return -1;
     return 0;
 }
+
+// MPC family: tracking cost + the learned margin as a terminal constraint
+template <int NQ>
+static void run_mpc(int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug, const double *x0,
+                    const double *lbx, const double *ubx, const double *lbu, const double *ubu, const double *Wz,
+                    const double *WzN, const double *yref, const double *yrefN, double Tf, const NnNet &net, double lh,
+                    double uh, const vboc_opts *o, double *x, double *u, vboc_stats *st, double *lamg) {
+    const int nxr = 2 * NQ, nu = NQ, nz = 3 * NQ;
+#pragma omp parallel
+    {
+        std::vector<double> buf(Work<NQ>::doubles(Nmax));
+        Smem<NQ> *sm = new Smem<NQ>();
+        SmemMpc<NQ> *gm = new SmemMpc<NQ>();
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < batch; ++b) {
+            Work<NQ> w;
+            w.carve(buf.data(), Nmax);
+            Prob pb;
+            pb.N = N[b], pb.nxr = nxr, pb.h = Tf / N[b], pb.wt = 0.0, pb.p = nullptr;
+            pb.xg = xg + (size_t)b * (Nmax + 1) * nxr, pb.ug = ug + (size_t)b * Nmax * nu;
+            pb.lbx0 = x0 + (size_t)b * nxr, pb.ubx0 = x0 + (size_t)b * nxr;
+            pb.lbx = lbx, pb.ubx = ubx, pb.lbxN = lbx, pb.ubxN = ubx, pb.lbu = lbu, pb.ubu = ubu, pb.dir = nullptr;
+            pb.x = x + (size_t)b * (Nmax + 1) * nxr, pb.u = u + (size_t)b * Nmax * nu, pb.st = st + b;
+            pb.Wz = Wz, pb.WzN = WzN, pb.yref = yref + (size_t)b * nz, pb.yrefN = yrefN + (size_t)b * nxr;
+            pb.nn = &net, pb.lh = lh, pb.uh = uh, pb.lamg_out = lamg ? lamg + 2 * b : nullptr;
+            if (g_pi) pb.pi_out = g_pi + (size_t)b * Nmax * 2 * NQ, pb.lam_out = g_lam + (size_t)b * (Nmax + 1) * 6 * NQ;
+            WarpSolver<NQ, VBOC_FAMILY_MPC> sol(*sm, w, *o, gm);
+            sol.solve(pb, mode);
+        }
+        delete sm;
+        delete gm;
+    }
+}
+
+extern "C" int emu_solve_mpc(int n, int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug,
+                             const double *x0, const double *lbx, const double *ubx, const double *lbu, const double *ubu,
+                             const double *Wz, const double *WzN, const double *yref, const double *yrefN, double Tf,
+                             int hidden, const double *W1, const double *b1, const double *W2, const double *b2,
+                             const double *W3, double b3, double mean, double stdv, double scale, double lh, double uh,
+                             const vboc_opts *o, double *x, double *u, vboc_stats *st, double *lamg) {
+    std::vector<double> w2t((size_t)hidden * hidden);
+    for (int j = 0; j < hidden; ++j)
+        for (int k = 0; k < hidden; ++k) w2t[(size_t)k * hidden + j] = W2[(size_t)j * hidden + k];
+    NnNet net;
+    net.n_in = 2 * n, net.hidden = hidden, net.W1 = W1, net.b1 = b1, net.W2 = W2, net.W2T = w2t.data(), net.b2 = b2;
+    net.W3 = W3, net.b3 = b3, net.mean = mean, net.stdv = stdv, net.scale = scale;
+    if (hidden > NN_HMAX) return -1;
+    if (n == 2) run_mpc<2>(mode, batch, Nmax, N, xg, ug, x0, lbx, ubx, lbu, ubu, Wz, WzN, yref, yrefN, Tf, net, lh, uh, o, x, u, st, lamg);
+    else if (n == 3) run_mpc<3>(mode, batch, Nmax, N, xg, ug, x0, lbx, ubx, lbu, ubu, Wz, WzN, yref, yrefN, Tf, net, lh, uh, o, x, u, st, lamg);
+    else return -1;
+    return 0;
+}

@@ -92,3 +92,34 @@ def datagen_run(n, inp, opts, N0=100, dt=1e-2, tol=1e-3):
     assert rc == 0
     out = [rows[b, :st[b].n_rows].copy() if st[b].status != 1 else None for b in range(B)]
     return out, [dict((f, getattr(s_, f)) for f, _ in DgStats._fields_) for s_ in st]
+
+
+def solve_mpc(n, mode, bp, net, opts, multipliers=False):
+    """MPC family on the host emulation.  bp: problems.sample_mpc(...); net: dict(W1, b1, W2, b2, W3 (H,), b3, mean, std,
+    scale) in float64."""
+    lib = C.CDLL(os.path.join(_HERE, "libemu.so"))
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    xg, ug = c(bp["x_guess"]), c(bp["u_guess"])
+    B, Np1, nx = xg.shape
+    Nmax = Np1 - 1
+    Nv = np.ascontiguousarray(bp["N"], dtype=np.int32)
+    x, u = np.zeros_like(xg), np.zeros_like(ug)
+    st = (Stats * B)()
+    lamg = np.zeros((B, 2))
+    pi = lam = None
+    if multipliers:
+        pi, lam = np.zeros((B, Nmax, 2 * n)), np.zeros((B, Nmax + 1, 3 * n, 2))
+        lib.emu_set_multiplier_out(_p(pi), _p(lam))
+    keep = [c(bp["x0"])] + [c(bp[k][0]) for k in ("lbx", "ubx", "lbu", "ubu")] + [c(bp[k]) for k in ("Wz", "WzN", "yref", "yrefN")]
+    w = [c(net[k]) for k in ("W1", "b1", "W2", "b2", "W3")]
+    rc = lib.emu_solve_mpc(n, mode, B, Nmax, Nv.ctypes.data_as(C.POINTER(C.c_int)), _p(xg), _p(ug), *[_p(a) for a in keep],
+                           C.c_double(bp["Tf"]), int(w[0].shape[0]), *[_p(a) for a in w], C.c_double(float(net["b3"])),
+                           C.c_double(net["mean"]), C.c_double(net["std"]), C.c_double(net["scale"]), C.c_double(bp["lh"]),
+                           C.c_double(bp["uh"]), C.byref(opts), _p(x), _p(u), st, _p(lamg))
+    assert rc == 0
+    if multipliers:
+        lib.emu_set_multiplier_out(None, None)
+    f = lambda name: np.array([getattr(s_, name) for s_ in st])
+    return dict(pi=pi, lam=lam, lamg=lamg, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"),
+                qp_iter=f("qp_iter"), qp_status=f("qp_status"),
+                res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # VBOC_LIB: kernel-tuning experiments load a differently compiled build of the same library (tools/build_variant.sh)
 LIB_PATH = os.environ.get("VBOC_LIB") or os.path.join(_HERE, "libvboc_b200.so")
 
-FAMILY_VBOC, FAMILY_AL = 0, 1
+FAMILY_VBOC, FAMILY_AL, FAMILY_MPC = 0, 1, 2
 MODE_SQP, MODE_RTI = 0, 1
 ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA = -1, -2, -3
 
@@ -19,6 +19,7 @@ EXPORTS = (
     "vboc_default_opts", "vboc_create", "vboc_destroy", "vboc_set_opts", "vboc_set_stream",
     "vboc_solve_batch", "vboc_upload", "vboc_solve_resident", "vboc_solve_resident_async", "vboc_sync",
     "vboc_download", "vboc_last_kernel_ms", "vboc_export_multipliers", "vboc_download_multipliers",
+    "vboc_set_mpc", "vboc_set_mpc_reference", "vboc_download_mpc_multipliers",
     "vboc_stream_create", "vboc_stream_destroy", "vboc_stream_set_opts", "vboc_stream_free_slots",
     "vboc_stream_pending", "vboc_stream_submit", "vboc_stream_poll", "vboc_stream_fetch", "vboc_stream_sim_step",
     "vboc_datagen_create", "vboc_datagen_destroy", "vboc_datagen_set_opts", "vboc_datagen_run", "vboc_datagen_last_kernel_ms",
@@ -91,6 +92,10 @@ def lib():
         L.vboc_solve_resident_async.argtypes = [vp, C.c_int]
         L.vboc_sync.argtypes = [vp]
         L.vboc_download.argtypes = [vp, dp, dp, C.POINTER(Stats)]
+        fp_ = C.POINTER(C.c_float)
+        L.vboc_set_mpc.argtypes = [vp, C.c_int] + [fp_] * 6 + [C.c_double] * 5 + [dp, dp]
+        L.vboc_set_mpc_reference.argtypes = [vp, C.c_int, dp, dp]
+        L.vboc_download_mpc_multipliers.argtypes = [vp, dp]
         L.vboc_export_multipliers.argtypes = [vp, C.c_int]
         L.vboc_download_multipliers.argtypes = [vp, dp, dp]
         L.vboc_last_kernel_ms.argtypes = [vp]

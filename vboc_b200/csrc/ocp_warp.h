@@ -24,6 +24,7 @@
 
 #include "../../include/vboc_b200.h"
 #include "dynamics.h"
+#include "nn_margin.h"
 #include "warp_spmd.h"
 
 namespace vboc {
@@ -42,6 +43,13 @@ struct Prob {
     // optional export of the KKT multipliers at the returned iterate (vboc_download_multipliers):
     // pi [N][2n] of the shooting equalities, lam [N+1][3n][2] of the (lower, upper) bounds on z = [u; q; v]
     double *pi_out = nullptr, *lam_out = nullptr;
+    // MPC family (VBOC/Safe MPC/hard_terminal_constraints/doublependulum_class_fixedveldir.py:123-212): diagonal
+    // LINEAR_LS weights in z = [u; x] ordering (stage: W = blkdiag(Q, R), terminal: W_e = Q), the reference y_ref of this
+    // problem, and the terminal constraint lh <= h(x_N) <= uh with h the learned margin (nn_margin.h)
+    const double *Wz = nullptr, *WzN = nullptr, *yref = nullptr, *yrefN = nullptr;
+    const NnNet *nn = nullptr;
+    double lh = 0.0, uh = 0.0;
+    double *lamg_out = nullptr;  // [2] multipliers of the terminal constraint at the returned iterate (optional)
 };
 
 template <int NQ>
@@ -177,6 +185,7 @@ struct Work {
     double *RG, *RD, *RM, *RMB;      // IPM residuals (RMB = lam*t, RM = dt_aff*dlam_aff)
     double *PP, *MF;                 // value functions; last-stage record
     double *WDYN, *WB, *ZT;          // merit weights, trial point
+    double *NNA;                     // MPC family: activations of the margin network (2 x NN_HMAX)
     // The workspace is carved with the compile-time stride SMAX so that every array is the slot base
     // plus a constant (no pointer table in registers, immediate offsets in the load/store
     // instructions); N_max <= SMAX - 1 is checked by vboc_create.
@@ -189,7 +198,8 @@ struct Work {
     static constexpr size_t O_RD = O_RG + SMAX * D::NZ, O_RM = O_RD + SMAX * D::NC, O_RMB = O_RM + SMAX * D::NC;
     static constexpr size_t O_PP = O_RMB + SMAX * D::NC, O_WDYN = O_PP + SMAX * PPS, O_WB = O_WDYN + SMAX * D::NX;
     static constexpr size_t O_ZT = O_WB + SMAX * D::NC, O_MF = O_ZT + SMAX * D::NZ;
-    static constexpr size_t TOTAL = (O_MF + D::MFS + 1) & ~(size_t)1;
+    static constexpr size_t O_NNA = (O_MF + D::MFS + 1) & ~(size_t)1;
+    static constexpr size_t TOTAL = O_NNA + 2 * NN_HMAX;
     static_assert(O_PIQ % 2 == 0 && O_LAMQ % 2 == 0 && O_TQ % 2 == 0 && O_DLAM % 2 == 0 && O_DT % 2 == 0 && O_RD % 2 == 0 &&
                       O_RM % 2 == 0, "16-byte aligned arrays");
     static VB_HD size_t doubles(int) { return TOTAL; }
@@ -199,7 +209,7 @@ struct Work {
         DZ = b + O_DZ, PIQ = b + O_PIQ, LAMQ = b + O_LAMQ, TQ = b + O_TQ;
         DV = b + O_DV, DLAM = b + O_DLAM, DT = b + O_DT;
         RG = b + O_RG, RD = b + O_RD, RM = b + O_RM, RMB = b + O_RMB;
-        PP = b + O_PP, WDYN = b + O_WDYN, WB = b + O_WB, ZT = b + O_ZT, MF = b + O_MF;
+        PP = b + O_PP, WDYN = b + O_WDYN, WB = b + O_WB, ZT = b + O_ZT, MF = b + O_MF, NNA = b + O_NNA;
     }
 };
 
@@ -228,6 +238,19 @@ struct alignas(16) Smem {
     double w0[D::NX], wN[D::NX], nu0q[D::NX], nuNq[D::NX];
 };
 
+// Extra shared-memory block of one warp for the MPC family only (the other families' kernels do not carry it):
+// tracking cost and the terminal constraint row  lgd <= gc' dx_N <= ugd  of the QP.
+template <int NQ>
+struct alignas(16) SmemMpc {
+    using D = Dim<NQ>;
+    double Wz[D::NZ], WzN[D::NX], yref[D::NZ], yrefN[D::NX];
+    double gc[D::NX], gx[D::NX], nnio[2 * D::NX + 2];
+    double gh, lgd, ugd;            // h(x_N) at the NLP iterate, bounds of the step
+    double LAMG[2], lamg[2], tg[2], rdg[2], rmg[2], wGm[2];  // NLP / QP multipliers, slacks, residuals, merit weights
+    double wg, barg, q1g, q2g;      // barrier Hessian weight and gradient pieces of the row
+    double lh, uh;
+};
+
 template <int NQ, int FAM>
 struct WarpSolver {
     using D = Dim<NQ>;
@@ -240,10 +263,14 @@ struct WarpSolver {
     Work<NQ> w;
     const vboc_opts &o;
     VbRing ring;
+    SmemMpc<NQ> *g = nullptr;    // MPC family only
+    const NnNet *nn = nullptr;
 
-    VB_DEV WarpSolver(Smem<NQ> &s_, const Work<NQ> &w_, const vboc_opts &o_) : s(s_), w(w_), o(o_) {
+    VB_DEV WarpSolver(Smem<NQ> &s_, const Work<NQ> &w_, const vboc_opts &o_, SmemMpc<NQ> *g_ = nullptr)
+        : s(s_), w(w_), o(o_), g(g_) {
         RING_INIT(ring, s.bar, RING_DEPTH);
     }
+    static constexpr bool MPC = FAM == VBOC_FAMILY_MPC;
 
     // index of the (k, i, side) bound constraint in the constraint arrays (LAM, LAMQ, TQ, DLAM, DT, RD, RM, RMB, WB).
     // VB_PAIR_LAYOUT: the lower / upper entries of a component are adjacent, so both come with one 128-bit load.
@@ -269,11 +296,17 @@ struct WarpSolver {
     // velocities, AL/triplependulum_class_al.py:98-115, Gauss-Newton)
     VB_DEV double cost_g(int k, int i, double zval) const {
         if (FAM == VBOC_FAMILY_VBOC) return (k == 0 && i >= NU + NQ) ? s.w[i - NU - NQ] : 0.0;
+        if constexpr (MPC) {
+            // LINEAR_LS, Gauss-Newton: the stage costs are scaled by the time step, the terminal one is not
+            if (k < s.N) return s.h * g->Wz[i] * (zval - g->yref[i]);
+            return i >= NU ? g->WzN[i - NU] * (zval - g->yrefN[i - NU]) : 0.0;
+        }
         return (i >= NU + NQ) ? 2.0 * (k < s.N ? s.h : 1.0) * zval : 0.0;
     }
     VB_DEV double cost_h(int k, int i) const {
         double hd = o.levenberg_marquardt;
         if (FAM == VBOC_FAMILY_AL && i >= NU + NQ) hd += 2.0 * (k < s.N ? s.h : 1.0);
+        if constexpr (MPC) hd += k < s.N ? s.h * g->Wz[i] : (i >= NU ? g->WzN[i - NU] : 0.0);
         return hd;
     }
     // e = (I - Z0 Z0')(x - c0): violation of the stage-0 equalities; x, e in shared memory
@@ -346,7 +379,15 @@ struct WarpSolver {
             s.fixed0 = f0, s.fixedN = fN, s.termfix = nfN != 0;
             s.nact = (N + 1) * NZ - NU - nf0 - nfN;
             for (int i = 0; i < NQ; ++i) s.w[i] = (FAM == VBOC_FAMILY_VBOC) ? pb.p[i] : 0.0;
+            if constexpr (MPC) {
+                s.nact += 1;  // the terminal constraint row: one more two-sided constraint
+                for (int i = 0; i < NZ; ++i) g->Wz[i] = pb.Wz[i], g->yref[i] = pb.yref[i];
+                for (int i = 0; i < NX; ++i) g->WzN[i] = pb.WzN[i], g->yrefN[i] = pb.yrefN[i];
+                g->lh = pb.lh, g->uh = pb.uh;
+                g->LAMG[0] = g->LAMG[1] = 0.0, g->wGm[0] = g->wGm[1] = 0.0;
+            }
         }
+        if constexpr (MPC) nn = pb.nn;
         static_assert(TRI <= 64 && NZ <= 16, "triangle index table");
         for (int idx = lane; idx < TRI; idx += 32) {
             int a_ = 0;
@@ -384,6 +425,9 @@ struct WarpSolver {
             pb.u[idx] = w.Z[k * NZ + i];
         }
         if (lane == 0) *pb.st = st;
+        if constexpr (MPC) {
+            if (pb.lamg_out && lane < 2) pb.lamg_out[lane] = g->LAMG[lane];
+        }
         if (pb.pi_out) {
             for (int idx = lane; idx < N * NX; idx += 32) pb.pi_out[idx] = w.PI[idx];
             for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
@@ -428,6 +472,28 @@ struct WarpSolver {
         END_LANES
     }
 
+    // MPC family: h(x_N) and its gradient at the NLP iterate -> the row  lh - h <= gc' dx_N <= uh - h  of the QP
+    VB_DEV void linearize_terminal_constraint() {
+        if constexpr (MPC) {
+            const int N = s.N;
+            FOR_LANES
+            if (lane < NX) g->gx[lane] = w.Z[N * NZ + NU + lane];
+            END_LANES
+            const double h = nn_margin<NQ>(*nn, g->gx, g->gc, w.NNA, w.NNA + NN_HMAX, g->nnio);
+            FOR_LANES
+            if (lane == 0) g->gh = h, g->lgd = g->lh - h, g->ugd = g->uh - h;
+            END_LANES
+        }
+    }
+    // h at the terminal state of a trial point (merit function)
+    VB_DEV double terminal_constraint_value(const double *Zs) {
+        const int N = s.N;
+        FOR_LANES
+        if (lane < NX) g->gx[lane] = Zs[N * NZ + NU + lane];
+        END_LANES
+        return nn_margin<NQ>(*nn, g->gx, nullptr, w.NNA, w.NNA + NN_HMAX, g->nnio);
+    }
+
     // ---------------------------------------------------------------- NLP residuals
     // inf-norms of the Lagrangian gradient, shooting gaps, constraint violation, complementarity
     VB_DEV bool nlp_residuals(double &rs, double &re, double &ri, double &rc) {
@@ -452,6 +518,9 @@ struct WarpSolver {
                     for (int m = 0; m < NX; ++m) r += col[m] * pi[m];
                 }
                 if (k > 0 && i >= NU) r -= w.PI[(k - 1) * NX + i - NU];
+                if constexpr (MPC) {
+                    if (k == N && i >= NU) r += g->gc[i - NU] * (g->LAMG[1] - g->LAMG[0]);
+                }
                 if (active(k, i)) {
                     int sc = sclass(k);
                     double ll = w.LAM[CI(k, i, 0)], lu = w.LAM[CI(k, i, 1)];
@@ -475,6 +544,13 @@ struct WarpSolver {
             double v = w.BD[idx];
             nb |= (v != v);
             ve = fmax(ve, fabs(v));
+        }
+        if constexpr (MPC) {
+            if (lane == 0) {  // the terminal constraint row lh <= h(x_N) <= uh
+                const double fl = g->lh - g->gh, fu = g->gh - g->uh;
+                vi = fmax(vi, fmax(fl, fu));
+                vc = fmax(vc, fmax(fabs(g->LAMG[0] * fl), fabs(g->LAMG[1] * fu)));
+            }
         }
         L(a_s) = vs, L(a_e) = ve, L(a_i) = vi, L(a_c) = vc, L(bad) = nb;
         END_LANES
@@ -539,6 +615,19 @@ struct WarpSolver {
         FOR_LANES
         if (lane < NX) w.DZ[NU + lane] -= s.vc[lane];
         END_LANES
+        if constexpr (MPC) {
+            // HPIPM cold start of a general constraint: slack = distance to the bound at the initial step, not below thr0
+            double g0 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) g0 += g->gc[i] * w.DZ[N * NZ + NU + i];
+            UNIFORM_SYNC();
+            FOR_LANES
+            if (lane < 2) {
+                const double t = fmax(lane == 0 ? g0 - g->lgd : g->ugd - g0, thr0);
+                g->tg[lane] = t, g->lamg[lane] = o.qp_mu0 / t;
+            }
+            END_LANES
+        }
     }
 
     // ---------------------------------------------------------------- QP: residuals
@@ -556,9 +645,47 @@ struct WarpSolver {
         LV(double, a_m);
         LV(double, a_mu);
         LV(int, bad);
+        if constexpr (MPC) {
+            // the terminal constraint row first (uniform): its updated multipliers enter the stationarity residual of
+            // x_N in the flat loop below, its barrier terms the terminal value function of the backward sweep
+            double gq = 0.0, dvg = 0.0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                const double dv = upd ? w.DV[N * NZ + NU + i] : 0.0;
+                gq += g->gc[i] * (w.DZ[N * NZ + NU + i] + as * dv);
+                dvg += g->gc[i] * dv;
+            }
+            double ll = g->lamg[0], lu = g->lamg[1], tl = g->tg[0], tu = g->tg[1];
+            if (upd) {
+                double rml = ll * tl, rmu = lu * tu;
+                if (umode == 1) rml += g->rmg[0] - usm, rmu += g->rmg[1] - usm;
+                if (umode == 2) rml -= usm, rmu -= usm;
+                const double dtl = dvg - g->rdg[0], dtu = -dvg - g->rdg[1];
+                const double dll = -(rml + ll * dtl) * VB_RCP(tl), dlu = -(rmu + lu * dtu) * VB_RCP(tu);
+                ll = fmax(ll + as * dll, o.qp_lam_min), lu = fmax(lu + as * dlu, o.qp_lam_min);
+                tl = fmax(tl + as * dtl, o.qp_t_min), tu = fmax(tu + as * dtu, o.qp_t_min);
+            }
+            const double dl = g->lgd - gq + tl, du = gq - g->ugd + tu, ml = ll * tl, mu_ = lu * tu;
+            const double itl = VB_RCP(tl), itu = VB_RCP(tu);
+            const double wg = ll * itl + lu * itu, barg = (ml - ll * dl) * itl - (mu_ - lu * du) * itu;
+            UNIFORM_SYNC();
+            FOR_LANES
+            if (lane == 0) {
+                g->lamg[0] = ll, g->lamg[1] = lu, g->tg[0] = tl, g->tg[1] = tu;
+                g->rdg[0] = dl, g->rdg[1] = du, g->wg = wg, g->barg = barg;
+            }
+            END_LANES
+        }
         FOR_LANES
         double vg = 0, vd = 0, vm = 0, mu = 0;
         int nb = 0;
+        if constexpr (MPC) {
+            if (lane == 0) {
+                const double dl = g->rdg[0], du = g->rdg[1], ml = g->lamg[0] * g->tg[0], mu_ = g->lamg[1] * g->tg[1];
+                nb |= (dl != dl) | (du != du) | (ml != ml) | (mu_ != mu_);
+                vd = fmax(fabs(dl), fabs(du)), vm = fmax(fabs(ml), fabs(mu_)), mu = ml + mu_;
+            }
+        }
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             {
@@ -602,6 +729,9 @@ struct WarpSolver {
 #endif
             }
             if (k > 0 && i >= NU) r -= w.PIQ[(k - 1) * NX + i - NU];
+            if constexpr (MPC) {
+                if (k == N && i >= NU) r += g->gc[i - NU] * (g->lamg[1] - g->lamg[0]);
+            }
             const int c = CI(k, i, 0), cu = CI(k, i, 1);
             if (active(k, i)) {
                 int sc = sclass(k);
@@ -670,6 +800,9 @@ struct WarpSolver {
                 if (k == N) r = 0.0;
             }
             if (VB_RG_ALL || k == 0) w.RG[idx] = r;  // only the stage-0 state part is read back (projection)
+            if constexpr (MPC) {
+                if (k == N && i >= NU) bar += g->barg * g->gc[i - NU];
+            }
             rk[R::HH + i] = hh;
             rk[R::RR + i] = r + bar;
             if (!(k == 0 && i >= NU)) {
@@ -753,7 +886,11 @@ struct WarpSolver {
                 s.pvec[lane] = fx ? 0.0 : rr;
                 if (factor) {
 #pragma unroll
-                    for (int j = 0; j < NX; ++j) s.P[lane][j] = (j == lane && !fx) ? hh : 0.0;
+                    for (int j = 0; j < NX; ++j) {
+                        double pv = (j == lane && !fx) ? hh : 0.0;
+                        if constexpr (MPC) pv += g->wg * g->gc[lane] * g->gc[j];  // barrier Hessian of the constraint row
+                        s.P[lane][j] = pv;
+                    }
                 }
             }
             END_LANES
@@ -1196,6 +1333,32 @@ struct WarpSolver {
         LV(double, a2);
         FOR_LANES
         double al = 1.0, s0 = 0, s1 = 0, s2 = 0;
+        if constexpr (MPC) {
+            if (lane == 0) {  // the terminal constraint row
+                double dvg = 0.0, q1g = 0.0, q2g = 0.0;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) dvg += g->gc[i] * w.DV[N * NZ + NU + i];
+#pragma unroll 1
+                for (int sd = 0; sd < 2; ++sd) {
+                    double lam = g->lamg[sd], t = g->tg[sd], rm = lam * t;
+                    if (mode == 1) rm += g->rmg[sd] - sm;
+                    if (mode == 2) rm -= sm;
+                    const double dtt = (sd ? -dvg : dvg) - g->rdg[sd];
+                    const double it = VB_RCP(t);
+                    const double dl = -(rm + lam * dtt) * it;
+                    if (dtt < 0.0 && t + al * dtt < 0.0) al = fmin(al, VB_RATIO(t, -dtt));
+                    if (dl < 0.0 && lam + al * dl < 0.0) al = fmin(al, VB_RATIO(lam, -dl));
+                    s0 += lam * t, s1 += lam * dtt + t * dl, s2 += dtt * dl;
+                    if (mode == 0) {
+                        const double pr = dtt * dl;
+                        g->rmg[sd] = pr;
+                        q1g += sd ? -pr * it : pr * it;
+                        q2g += sd ? -it : it;
+                    }
+                }
+                if (mode == 0) g->q1g = q1g, g->q2g = q2g;
+            }
+        }
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             double *rk = rec(k);
@@ -1268,6 +1431,16 @@ struct WarpSolver {
         END_LANES
         S0 = WARP_SUM(a0), S1 = WARP_SUM(a1), S2 = WARP_SUM(a2);
         double alpha = WARP_MIN(amin);
+        if constexpr (MPC) {
+            if (mode == 0) {  // the row's pieces of the corrector gradient act on x_N through its gradient
+                FOR_LANES
+                if (lane < NX) {
+                    rec(N)[R::Q1 + NU + lane] += g->gc[lane] * g->q1g;
+                    rec(N)[R::Q2 + NU + lane] += g->gc[lane] * g->q2g;
+                }
+                END_LANES
+            }
+        }
         if (mode == 0) PROXY_FENCE();
         return alpha;
     }
@@ -1338,6 +1511,12 @@ struct WarpSolver {
                     a = s.nuv[mI];
                 } else {
                     a = s.hhN[mI] * dxn[mI] + s.rN[mI];
+                    if constexpr (MPC) {
+                        double gd = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) gd += g->gc[j] * dxn[j];
+                        a += g->wg * g->gc[mI] * gd;
+                    }
                 }
                 w.PIQ[idx] += as * a;
             }
@@ -1384,8 +1563,26 @@ struct WarpSolver {
         double a = 0.0;
         for (int k = lane; k <= N; k += 32) {
             double q = 0.0;
+            if constexpr (MPC) {
+                // LINEAR_LS: 1/2 (y - y_ref)' W (y - y_ref), stage costs times the time step
+                if (k < N) {
 #pragma unroll
-            for (int i = 0; i < NQ; ++i) q += Zs[k * NZ + NU + NQ + i] * Zs[k * NZ + NU + NQ + i];
+                    for (int i = 0; i < NZ; ++i) {
+                        const double d = Zs[k * NZ + i] - g->yref[i];
+                        q += g->Wz[i] * d * d;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
+                        const double d = Zs[k * NZ + NU + i] - g->yrefN[i];
+                        q += g->WzN[i] * d * d;
+                    }
+                }
+                q *= 0.5;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) q += Zs[k * NZ + NU + NQ + i] * Zs[k * NZ + NU + NQ + i];
+            }
             a += (k < N ? s.h : 1.0) * q;
         }
         L(acc) = a;
@@ -1416,6 +1613,11 @@ struct WarpSolver {
         L(acc) = a;
         END_LANES
         double m = WARP_SUM(acc) + total_cost(Zs);
+        if constexpr (MPC) {
+            const double h = terminal_constraint_value(Zs);
+            if (g->lh - h > 0.0) m += g->wGm[0] * (g->lh - h);
+            if (h - g->uh > 0.0) m += g->wGm[1] * (h - g->uh);
+        }
         FOR_LANES
         if (lane < NX) s.vb[lane] = Zs[NU + lane];
         END_LANES
@@ -1444,6 +1646,12 @@ struct WarpSolver {
             double a = fabs(s.nu0q[lane]), b = fabs(s.nuNq[lane]);
             s.w0[lane] = sqp_iter == 0 ? a : fmax(a, 0.5 * (s.w0[lane] + a));
             s.wN[lane] = sqp_iter == 0 ? b : fmax(b, 0.5 * (s.wN[lane] + b));
+        }
+        if constexpr (MPC) {
+            if (lane < 2) {
+                const double a = fabs(g->lamg[lane]);
+                g->wGm[lane] = sqp_iter == 0 ? a : fmax(a, 0.5 * (g->wGm[lane] + a));
+            }
         }
         END_LANES
         // trial -1 evaluates the merit function at the current iterate (alpha = 0)
@@ -1477,6 +1685,7 @@ struct WarpSolver {
         const int maxit = mode == VBOC_MODE_RTI ? 1 : o.max_iter;
         for (int it = 0;; ++it) {
             linearize();
+            linearize_terminal_constraint();
             bool finite = nlp_residuals(st.res_stat, st.res_eq, st.res_ineq, st.res_comp);
             if (mode == VBOC_MODE_SQP || it > 0) {
                 if (!finite) {
@@ -1508,6 +1717,9 @@ struct WarpSolver {
                 w.PI[idx] = (1.0 - alpha) * w.PI[idx] + alpha * w.PIQ[idx];
             for (int idx = lane; idx < (N + 1) * NC; idx += 32)
                 w.LAM[idx] = (1.0 - alpha) * w.LAM[idx] + alpha * w.LAMQ[idx];
+            if constexpr (MPC) {
+                if (lane < 2) g->LAMG[lane] = (1.0 - alpha) * g->LAMG[lane] + alpha * g->lamg[lane];
+            }
             END_LANES
         }
         st.cost = total_cost(w.Z);

@@ -63,6 +63,12 @@ struct Batch {
     double *x, *u;
     vboc_stats *st;
     double *pi_out = nullptr, *lam_out = nullptr;  // optional multiplier export (vboc_download_multipliers)
+    // MPC family: tracking weights (shared by the batch), per-problem references, the margin network, the
+    // bounds of the terminal constraint and the export of its multipliers
+    const double *Wz = nullptr, *WzN = nullptr, *yref = nullptr, *yrefN = nullptr;
+    NnNet nn;
+    double lh = 0.0, uh = 0.0;
+    double *lamg_out = nullptr;
     double *work;  // slots * work_doubles
     size_t work_doubles;
     unsigned int *counter;
@@ -147,6 +153,47 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VB_LB_MINB(MINB)) solve_ke
     if constexpr (STREAM) {
         __syncthreads();
         if (threadIdx.x == 0) atomicAnd(ws_word, ~ws_bit);
+    }
+}
+
+// solve_mpc_kernel: solve_kernel for the MPC family: the same warp-per-OCP solver with the tracking
+// cost and the learned margin as a terminal constraint; every warp carries the extra SmemMpc block.
+template <int NQ>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) solve_mpc_kernel(const Batch B) {
+    __shared__ Smem<NQ> smem[WARPS_PER_CTA];
+    __shared__ SmemMpc<NQ> mpc[WARPS_PER_CTA];
+    __shared__ NnNet net;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * WARPS_PER_CTA + warp;
+    if (threadIdx.x == 0) net = B.nn;
+    __syncthreads();
+    Work<NQ> w;
+    w.carve(B.work + (size_t)slot * B.work_doubles, B.Nmax);
+    WarpSolver<NQ, VBOC_FAMILY_MPC> sol(smem[warp], w, B.opts, &mpc[warp]);
+    const int nu = NQ, nz = 3 * NQ;
+    for (;;) {
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(B.counter, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned)B.batch) break;
+        Prob pb;
+        pb.N = B.N[b], pb.nxr = B.nxr, pb.h = B.h[b], pb.p = nullptr, pb.wt = 0.0, pb.dir = nullptr;
+        pb.xg = B.xg + (size_t)b * (B.Nmax + 1) * B.nxr, pb.ug = B.ug + (size_t)b * B.Nmax * nu;
+        pb.lbx0 = B.lbx0 + (size_t)b * B.nxr, pb.ubx0 = B.ubx0 + (size_t)b * B.nxr;
+        pb.lbx = B.lbx + (size_t)b * B.nxr, pb.ubx = B.ubx + (size_t)b * B.nxr;
+        pb.lbxN = B.lbxN + (size_t)b * B.nxr, pb.ubxN = B.ubxN + (size_t)b * B.nxr;
+        pb.lbu = B.lbu + (size_t)b * nu, pb.ubu = B.ubu + (size_t)b * nu;
+        pb.x = B.x + (size_t)b * (B.Nmax + 1) * B.nxr, pb.u = B.u + (size_t)b * B.Nmax * nu;
+        pb.st = B.st + b;
+        pb.Wz = B.Wz, pb.WzN = B.WzN, pb.yref = B.yref + (size_t)b * nz, pb.yrefN = B.yrefN + (size_t)b * B.nxr;
+        pb.nn = &net, pb.lh = B.lh, pb.uh = B.uh;
+        pb.lamg_out = B.lamg_out ? B.lamg_out + 2 * (size_t)b : nullptr;
+        if (B.pi_out) {
+            pb.pi_out = B.pi_out + (size_t)b * B.Nmax * 2 * NQ;
+            pb.lam_out = B.lam_out + (size_t)b * (B.Nmax + 1) * 6 * NQ;
+        }
+        sol.solve(pb, B.mode);
+        __syncwarp();
     }
 }
 
@@ -298,6 +345,11 @@ struct vboc_solver {
     double *dxg, *dug, *dp, *dlbx0, *dubx0, *dlbx, *dubx, *dlbxN, *dubxN, *dlbu, *dubu, *ddir, *dh;
     double *dx, *du, *dwork;
     double *dpi, *dlam;  // multiplier export, allocated by vboc_export_multipliers
+    // MPC family (vboc_set_mpc / vboc_set_mpc_reference)
+    double *dnn, *dWz, *dWzN, *dyref, *dyrefN, *dlamg;
+    NnNet nn;
+    double mpc_lh, mpc_uh;
+    int mpc_set, mpc_ref_batch;
     vboc_stats *dst;
     unsigned int *dcounter;
     size_t work_doubles;
@@ -400,6 +452,15 @@ void vboc_default_opts(int family, vboc_opts *o) {
         o->qp_iter_max = 100, o->max_iter = 1000;
         o->globalization = 1, o->alpha_reduction = 0.3, o->alpha_min = 1e-2;
         o->levenberg_marquardt = 1e-5;
+    } else if (family == VBOC_FAMILY_MPC) {
+        // VBOC/Safe MPC/hard_terminal_constraints/doublependulum_class_fixedveldir.py:183-190: `tol = 1e-2` sets the four
+        // NLP tolerances and the QP solver's [acados_template: the `tol` setter], iter limits 1000 / 100, merit
+        // back-tracking 0.3 / 1e-2, Levenberg-Marquardt 1
+        o->tol_stat = o->tol_eq = o->tol_ineq = o->tol_comp = 1e-2;
+        o->qp_tol_stat = o->qp_tol_eq = o->qp_tol_ineq = o->qp_tol_comp = 1e-2;
+        o->qp_iter_max = 100, o->max_iter = 1000;
+        o->globalization = 1, o->alpha_reduction = 0.3, o->alpha_min = 1e-2;
+        o->levenberg_marquardt = 1.0;
     } else {
         // AL classes: SQP_RTI with acados defaults (AL/pendulum_class_al.py:124)
         o->tol_stat = 1e-6;
@@ -416,8 +477,9 @@ static size_t work_doubles_for(int n, int Nmax) {
 }
 
 int vboc_create(int n_dof, int family, int batch_capacity, int N_max, int device, vboc_solver **out) {
-    if (!out || n_dof < 1 || n_dof > 3 || (family != VBOC_FAMILY_VBOC && family != VBOC_FAMILY_AL) ||
-        batch_capacity < 1 || N_max < 1 || N_max > VBOC_N_MAX)
+    if (!out || n_dof < 1 || n_dof > 3 ||
+        (family != VBOC_FAMILY_VBOC && family != VBOC_FAMILY_AL && family != VBOC_FAMILY_MPC) || batch_capacity < 1 ||
+        N_max < 1 || N_max > VBOC_N_MAX || (family == VBOC_FAMILY_MPC && n_dof < 2))
         return fail(VBOC_ERR_ARG, "vboc_create: bad argument");
     int ndev = 0;
     CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -459,7 +521,7 @@ static int solver_create_impl(vboc_solver *s, int n_dof, int family, int batch_c
     s->work_doubles = work_doubles_for(n_dof, N_max);
     // kernel mapping: VBOC_KERNEL=lane selects one lane per OCP (ocp_lane.h), default one warp per OCP
     s->lane_kernel = 0;
-    if (const char *e = getenv("VBOC_KERNEL")) s->lane_kernel = strcmp(e, "lane") == 0;
+    if (const char *e = getenv("VBOC_KERNEL")) s->lane_kernel = strcmp(e, "lane") == 0 && family != VBOC_FAMILY_MPC;
     if (s->lane_kernel) {
         size_t per_lane = n_dof == 1 ? LaneLayout<1>::TOTAL : (n_dof == 2 ? LaneLayout<2>::TOTAL : LaneLayout<3>::TOTAL);
         int warps_per_cta = LANE_THREADS / 32;
@@ -503,7 +565,8 @@ void vboc_destroy(vboc_solver *s) {
     cudaSetDevice(s->device);
     void *ptrs[] = {s->dN,    s->dxg,   s->dug,  s->dp,   s->dlbx0, s->dubx0, s->dlbx,
                     s->dubx,  s->dlbxN, s->dubxN, s->dlbu, s->dubu,  s->ddir,  s->dh,
-                    s->dx,    s->du,    s->dst,  s->dcounter, s->dwork, s->dpi, s->dlam};
+                    s->dx,    s->du,    s->dst,  s->dcounter, s->dwork, s->dpi, s->dlam,
+                    s->dnn,   s->dWz,   s->dWzN, s->dyref, s->dyrefN, s->dlamg};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (s->dwork_free_dt) cudaFree(s->dwork_free_dt);
@@ -697,7 +760,20 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
     CUDA_OK(cudaMemsetAsync(s->dcounter, 0, sizeof(unsigned int), s->stream));
     CUDA_OK(cudaEventRecord(s->ev0, s->stream));
     cudaError_t e = cudaErrorInvalidValue;
-    if (s->free_dt) {
+    if (s->family == VBOC_FAMILY_MPC) {
+#ifndef VB_TUNE_BUILD
+        if (!s->mpc_set) return fail(VBOC_ERR_ARG, "vboc_solve_resident: call vboc_set_mpc first (MPC family)");
+        if (s->mpc_ref_batch < s->batch)
+            return fail(VBOC_ERR_ARG, "vboc_solve_resident: call vboc_set_mpc_reference for this batch (MPC family)");
+        B.Wz = s->dWz, B.WzN = s->dWzN, B.yref = s->dyref, B.yrefN = s->dyrefN, B.nn = s->nn;
+        B.lh = s->mpc_lh, B.uh = s->mpc_uh, B.lamg_out = s->dlamg;
+        const int g4 = (s->batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        const int grid = g4 < s->grid ? g4 : s->grid;
+        if (s->n == 2) solve_mpc_kernel<2><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+        else solve_mpc_kernel<3><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+        e = cudaGetLastError();
+#endif
+    } else if (s->free_dt) {
 #ifndef VB_TUNE_BUILD
         B.work = s->dwork_free_dt;
         const int smem = LaneSolver<1, VBOC_FAMILY_VBOC, 32, 1>::SM_TOTAL * LANE_THREADS * (int)sizeof(double);
@@ -744,6 +820,71 @@ int vboc_download(vboc_solver *s, double *x, double *u, vboc_stats *stats) {
     if (u && (rc = d2h(s, u, s->du, B * s->Nmax * s->nu * sizeof(double)))) return rc;
     if (stats && (rc = d2h(s, stats, s->dst, B * sizeof(vboc_stats)))) return rc;
     return 0;
+}
+
+int vboc_set_mpc(vboc_solver *s, int hidden, const float *W1, const float *b1, const float *W2, const float *b2,
+                 const float *W3, const float *b3, double mean, double stdv, double safety_margin, double lh, double uh,
+                 const double *W, const double *W_e) {
+    if (!s || s->family != VBOC_FAMILY_MPC) return fail(VBOC_ERR_ARG, "vboc_set_mpc: not an MPC-family solver");
+    if (hidden < 1 || hidden > NN_HMAX || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !W || !W_e || !(stdv > 0.0))
+        return fail(VBOC_ERR_ARG, "vboc_set_mpc: bad argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    const int n = s->n, nx = 2 * n, nz = 3 * n, H = hidden;
+    // FP64 copies of the FP32-trained weights (CasADi evaluates the network in double on float-valued parameters);
+    // W2 in both layouts so that the forward and the reverse pass read coalesced
+    const size_t o_b1 = (size_t)H * nx, o_W2 = o_b1 + H, o_W2T = o_W2 + (size_t)H * H, o_b2 = o_W2T + (size_t)H * H,
+                 o_W3 = o_b2 + H, total = o_W3 + H;
+    std::vector<double> h(total);
+    for (size_t i = 0; i < (size_t)H * nx; ++i) h[i] = W1[i];
+    for (int i = 0; i < H; ++i) h[o_b1 + i] = b1[i], h[o_b2 + i] = b2[i], h[o_W3 + i] = W3[i];
+    for (int j = 0; j < H; ++j)
+        for (int k = 0; k < H; ++k) h[o_W2 + (size_t)j * H + k] = W2[(size_t)j * H + k], h[o_W2T + (size_t)k * H + j] = W2[(size_t)j * H + k];
+    if (s->dnn) cudaFree(s->dnn);
+    s->dnn = nullptr;
+    CUDA_OK(cudaMalloc((void **)&s->dnn, total * sizeof(double)));
+    CUDA_OK(cudaMemcpy(s->dnn, h.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    s->nn.n_in = nx, s->nn.hidden = H, s->nn.W1 = s->dnn, s->nn.b1 = s->dnn + o_b1, s->nn.W2 = s->dnn + o_W2;
+    s->nn.W2T = s->dnn + o_W2T, s->nn.b2 = s->dnn + o_b2, s->nn.W3 = s->dnn + o_W3, s->nn.b3 = b3[0];
+    s->nn.mean = mean, s->nn.stdv = stdv, s->nn.scale = (100.0 - safety_margin) / 100.0;
+    s->mpc_lh = lh, s->mpc_uh = uh;
+    // weights arrive in acados' y = [x; u] order (cost.W = blkdiag(Q, R)); the engine orders z = [u; x]
+    std::vector<double> wz(nz), wzN(nx);
+    for (int i = 0; i < nx; ++i) wz[n + i] = W[i], wzN[i] = W_e[i];
+    for (int i = 0; i < n; ++i) wz[i] = W[nx + i];
+    if (!s->dWz) {
+        CUDA_OK(cudaMalloc((void **)&s->dWz, nz * sizeof(double)));
+        CUDA_OK(cudaMalloc((void **)&s->dWzN, nx * sizeof(double)));
+        CUDA_OK(cudaMalloc((void **)&s->dyref, (size_t)s->cap * nz * sizeof(double)));
+        CUDA_OK(cudaMalloc((void **)&s->dyrefN, (size_t)s->cap * nx * sizeof(double)));
+        CUDA_OK(cudaMalloc((void **)&s->dlamg, (size_t)s->cap * 2 * sizeof(double)));
+    }
+    CUDA_OK(cudaMemcpy(s->dWz, wz.data(), nz * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(s->dWzN, wzN.data(), nx * sizeof(double), cudaMemcpyHostToDevice));
+    s->mpc_set = 1;
+    return 0;
+}
+
+int vboc_set_mpc_reference(vboc_solver *s, int batch, const double *yref, const double *yref_e) {
+    if (!s || s->family != VBOC_FAMILY_MPC || !s->mpc_set) return fail(VBOC_ERR_ARG, "vboc_set_mpc_reference: call vboc_set_mpc first");
+    if (batch < 1 || batch > s->cap || !yref || !yref_e) return fail(VBOC_ERR_ARG, "vboc_set_mpc_reference: bad argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    const int n = s->n, nx = 2 * n, nz = 3 * n;
+    std::vector<double> yz((size_t)batch * nz);
+    for (int b = 0; b < batch; ++b) {
+        for (int i = 0; i < nx; ++i) yz[(size_t)b * nz + n + i] = yref[(size_t)b * nz + i];
+        for (int i = 0; i < n; ++i) yz[(size_t)b * nz + i] = yref[(size_t)b * nz + nx + i];
+    }
+    int rc;
+    if ((rc = h2d(s, s->dyref, yz.data(), yz.size() * sizeof(double)))) return rc;
+    if ((rc = h2d(s, s->dyrefN, yref_e, (size_t)batch * nx * sizeof(double)))) return rc;
+    s->mpc_ref_batch = batch;
+    return 0;
+}
+
+int vboc_download_mpc_multipliers(vboc_solver *s, double *lamg) {
+    if (!s || !s->batch || s->family != VBOC_FAMILY_MPC || !lamg) return fail(VBOC_ERR_ARG, "vboc_download_mpc_multipliers: bad argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    return d2h(s, lamg, s->dlamg, (size_t)s->batch * 2 * sizeof(double));
 }
 
 int vboc_export_multipliers(vboc_solver *s, int on) {

@@ -10,9 +10,9 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import FAMILY_AL, FAMILY_VBOC, MODE_RTI, MODE_SQP, Opts, Stats, check
+from ._lib import FAMILY_AL, FAMILY_MPC, FAMILY_VBOC, MODE_RTI, MODE_SQP, Opts, Stats, check
 
-_FAM = {"vboc": FAMILY_VBOC, "al": FAMILY_AL}
+_FAM = {"vboc": FAMILY_VBOC, "al": FAMILY_AL, "mpc": FAMILY_MPC}
 _STAT_FIELDS = ("status", "sqp_iter", "qp_iter", "ls_evals", "qp_status", "cost",
                 "res_stat", "res_eq", "res_ineq", "res_comp")
 _STATS_DTYPE = np.dtype([("status", "i4"), ("sqp_iter", "i4"), ("qp_iter", "i4"), ("ls_evals", "i4"),
@@ -102,6 +102,33 @@ class BatchSolver:
         st = np.empty(B, dtype=_STATS_DTYPE)
         check(_lib.lib().vboc_download(self._h, _dp(x), _dp(u), st.ctypes.data_as(C.POINTER(Stats))))
         return self._result(x, u, st)
+
+    # -- MPC family ------------------------------------------------------------
+    def set_mpc(self, net, mean, std, safety_margin, W, W_e, lh=0.0, uh=1e6):
+        """The margin network (a torch module with `linear_relu_stack`, or a dict of W1, b1, W2, b2, W3, b3 arrays in
+        nn.Linear layout), its normalisation, the constraint's bounds and the diagonals of cost.W ([x; u] order) /
+        cost.W_e."""
+        if not isinstance(net, dict):
+            lin = [m for m in net.linear_relu_stack if hasattr(m, "weight")]
+            g = lambda t: t.detach().cpu().numpy()
+            net = dict(W1=g(lin[0].weight), b1=g(lin[0].bias), W2=g(lin[1].weight), b2=g(lin[1].bias),
+                       W3=g(lin[2].weight), b3=g(lin[2].bias))
+        f = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32).ravel())
+        w = [f(net[k]) for k in ("W1", "b1", "W2", "b2", "W3", "b3")]
+        H = w[1].shape[0]
+        assert w[0].shape[0] == H * 2 * self.n and w[2].shape[0] == H * H and w[4].shape[0] == H and w[5].shape[0] == 1
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        check(_lib.lib().vboc_set_mpc(self._h, H, *[fp(a) for a in w], float(mean), float(std), float(safety_margin),
+                                      float(lh), float(uh), _dp(_c(W)), _dp(_c(W_e))))
+
+    def set_mpc_reference(self, yref, yref_e):
+        yref, yref_e = _c(np.atleast_2d(yref)), _c(np.atleast_2d(yref_e))
+        check(_lib.lib().vboc_set_mpc_reference(self._h, yref.shape[0], _dp(yref), _dp(yref_e)))
+
+    def mpc_multipliers(self):
+        lamg = np.zeros((self._batch, 2))
+        check(_lib.lib().vboc_download_mpc_multipliers(self._h, _dp(lamg)))
+        return lamg
 
     def export_multipliers(self, on=True):
         """Have the next solves keep the KKT multipliers of the returned iterates (`multipliers()`)."""

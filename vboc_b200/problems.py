@@ -303,3 +303,39 @@ def pendulum_free_dt_problems(batch, seed, N=50):
     return dict(n=1, family="vboc", N=np.full(batch, N, dtype=np.int32), x_guess=xg, u_guess=np.zeros((batch, N, 1)),
                 p=p, lbx0=lbx0, ubx0=ubx0, lbx=lbx, ubx=ubx, lbxN=lbxN, ubxN=ubxN,
                 lbu=np.full((batch, 1), -mdl.umax), ubu=np.full((batch, 1), mdl.umax), C0=None)
+
+
+# ------------------------------------------------------------------------------------------------
+# MPC family: the Safe-MPC OCP with the learned viability margin as a terminal constraint
+def mpc_weights(n):
+    """Diagonal LINEAR_LS weights of VBOC/Safe MPC/hard_terminal_constraints/doublependulum_class_fixedveldir.py:123-137
+    (Q = diag(1e4 on positions, 1e-4 on velocities), R = 1e-4) in the engine's z = [u; x] ordering; terminal W_e = Q."""
+    Q = np.array([1e4] * n + [1e-4] * n)
+    R = np.full(n, 1e-4)
+    return np.concatenate([R, Q]), Q.copy()
+
+
+def sample_mpc(n, batch, seed, N=10, Tf=0.01, v_scale=6.0):
+    """Initial states and guesses of the Safe-MPC simulation (VBOC/Safe MPC/parallel/2dof_sym.py:17-28): x0 inside the
+    box, reference q_ref = pi (hanging), guess = x0 at every stage with gravity-compensation torques."""
+    mdl = Model(n)
+    rng = _rng(seed)
+    q0 = mdl.thetamin + rng.random((batch, n)) * (mdl.thetamax - mdl.thetamin)
+    d = rng.normal(size=(batch, n))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    v0 = d * (rng.random((batch, 1)) * v_scale)
+    x0 = np.concatenate([q0, v0], axis=1)
+    xg = np.repeat(x0[:, None, :], N + 1, axis=1)
+    ug = np.repeat(np.stack([mdl.gravity_comp(q) for q in q0])[:, None, :], N, axis=1)
+    Wz, WzN = mpc_weights(n)
+    yref = np.tile(np.concatenate([np.zeros(n), np.full(n, np.pi), np.zeros(n)]), (batch, 1))   # [u_ref; q_ref; v_ref]
+    yrefN = np.tile(np.concatenate([np.full(n, np.pi), np.zeros(n)]), (batch, 1))
+    lo = np.concatenate([np.full(n, mdl.thetamin), np.full(n, -mdl.dthetamax)])
+    hi = np.concatenate([np.full(n, mdl.thetamax), np.full(n, mdl.dthetamax)])
+    rep = lambda v: np.tile(np.asarray(v, dtype=float), (batch, 1))
+    W_acados = np.concatenate([WzN, Wz[:n]])      # cost.W diagonal in acados' y = [x; u] order
+    yref_acados = np.concatenate([yref[:, n:], yref[:, :n]], axis=1)
+    return dict(n=n, family="mpc", N=np.full(batch, N, dtype=np.int32), Tf=Tf, x_guess=xg, u_guess=ug, x0=x0, p=None, C0=None,
+                lbx0=x0.copy(), ubx0=x0.copy(), lbx=rep(lo), ubx=rep(hi), lbxN=rep(lo), ubxN=rep(hi),
+                lbu=rep([-mdl.umax] * n), ubu=rep([mdl.umax] * n), Wz=Wz, WzN=WzN, yref=yref, yrefN=yrefN,
+                W=W_acados, W_e=WzN.copy(), yref_acados=yref_acados, lh=0.0, uh=1e6)

@@ -163,6 +163,17 @@ int vboc_set_mpc(vboc_solver *s, int hidden, const float *W1, const float *b1, c
                  const double *W, const double *W_e);
 int vboc_set_mpc_reference(vboc_solver *s, int batch, const double *yref, const double *yref_e);
 int vboc_download_mpc_multipliers(vboc_solver *s, double *lamg);
+/*
+ * AL family: `compute_problem_nnguess` (AL/triplependulum_class_al.py:171-201) with the guess network evaluated INSIDE the
+ * solve kernel: a 2n-H-H-(N 2n) MLP (my_nn.py NeuralNetCLS, PyTorch nn.Linear layout, float32) predicts the state
+ * trajectory of stages 1..N from the initial state, out = model((x0 - mean) / std) * std + mean; stage 0 takes x0.  After
+ * vboc_set_guess_network the x_guess argument of vboc_solve_batch / vboc_upload is ignored (u_guess is still read);
+ * hidden = 0 switches back to host-supplied guesses.  vboc_download_guess: the guesses the kernel computed,
+ * [batch][N_max+1][2n] (FP64 arithmetic on the FP32 weights; PyTorch's FP32 forward differs by ~1e-6 relative).
+ */
+int vboc_set_guess_network(vboc_solver *s, int hidden, int n_out, const float *W1, const float *b1, const float *W2,
+                           const float *b2, const float *W3, const float *b3, double mean, double stdv);
+int vboc_download_guess(vboc_solver *s, double *x_guess);
 /* Device time of the last vboc_solve_resident kernel in milliseconds (CUDA events on the solver's
  * stream); negative if none. */
 double vboc_last_kernel_ms(vboc_solver *s);

@@ -59,3 +59,27 @@ def test_free_dt_lane_program_matches_oracle(oracle, emu):
     x = out["x"][ok]
     assert (x[:, 0, 2] > 1e-4).all() and (x[:, 0, 2] < 1e-2).all()
     assert np.abs(np.diff(x[:, :, 2], axis=1)).max() < 1e-9
+
+
+def test_guess_network_inside_the_solver(oracle, emu):
+    """`compute_problem_nnguess` with the guess network evaluated by the solver itself (vboc_set_guess_network): the
+    computed guess equals the float64 forward of the network, and the RTI result equals the oracle's from that guess."""
+    n, N, H = 2, 100, 48
+    nx = 2 * n
+    rng = np.random.default_rng(0)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    net = dict(W1=f32(rng.normal(size=(H, nx)) / 2), b1=f32(rng.normal(size=H) * 0.1), W2=f32(rng.normal(size=(H, H)) / 7),
+               b2=f32(rng.normal(size=H) * 0.1), W3=f32(rng.normal(size=(N * nx, H)) * 0.02), b3=f32(rng.normal(size=N * nx) * 0.02),
+               mean=3.0, std=2.5)
+    bp = pr.sample_al(n, 24, seed=6)
+    out = emu.solve_batch(n, 1, 1, bp, _opts(emu, oracle.default_opts(1)), guess_net=net)
+    x0 = bp["lbx0"][:, :nx]
+    a = np.maximum(((x0 - net["mean"]) / net["std"]) @ net["W1"].T + net["b1"], 0)
+    a = np.maximum(a @ net["W2"].T + net["b2"], 0)
+    want = (a @ net["W3"].T + net["b3"]) * net["std"] + net["mean"]
+    assert np.abs(out["x_guess"][:, 1:] - want.reshape(24, N, nx)).max() < 1e-12
+    assert np.array_equal(out["x_guess"][:, 0], x0)
+    ref = oracle.solve_batch(n, 1, 1, pr.al_problems(n, x0, x_guess=out["x_guess"]))
+    assert (ref["status"] == out["status"]).all() and (ref["qp_iter"] == out["qp_iter"]).all()
+    ok = out["status"] == 0
+    assert ok.any() and np.abs(ref["x"] - out["x"])[ok].max() < 1e-6

@@ -16,6 +16,17 @@ using namespace vboc;
 // optional multiplier export of the warp solver (set before emu_solve_batch, reset to null afterwards)
 static double *g_pi = nullptr, *g_lam = nullptr;
 extern "C" void emu_set_multiplier_out(double *pi, double *lam) { g_pi = pi, g_lam = lam; }
+// optional in-kernel guess network of the AL family (W2T / W3T already transposed by the caller) + guess export
+static GuessNet g_gnn;
+static bool g_gnn_on = false;
+static double *g_xg_out = nullptr;
+extern "C" void emu_set_guess_net(int on, int hidden, int n_out, const double *W1, const double *b1, const double *W2T,
+                                  const double *b2, const double *W3T, const double *b3, double mean, double stdv,
+                                  double *xg_out) {
+    g_gnn_on = on != 0, g_xg_out = xg_out;
+    g_gnn.hidden = hidden, g_gnn.n_out = n_out, g_gnn.W1 = W1, g_gnn.b1 = b1, g_gnn.W2T = W2T, g_gnn.b2 = b2;
+    g_gnn.W3T = W3T, g_gnn.b3 = b3, g_gnn.mean = mean, g_gnn.stdv = stdv;
+}
 
 template <int NQ, int FAM>
 static void run(int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug,
@@ -45,6 +56,10 @@ static void run(int mode, int batch, int Nmax, const int *N, const double *xg, c
             pb.x = x + (size_t)b * (Nmax + 1) * nxr, pb.u = u + (size_t)b * Nmax * nu;
             pb.st = st + b;
             if (g_pi) pb.pi_out = g_pi + (size_t)b * Nmax * 2 * NQ, pb.lam_out = g_lam + (size_t)b * (Nmax + 1) * 6 * NQ;
+            if (FAM == VBOC_FAMILY_AL && g_gnn_on) {
+                pb.gnn = &g_gnn;
+                pb.xg_out = g_xg_out ? g_xg_out + (size_t)b * (Nmax + 1) * nxr : nullptr;
+            }
             WarpSolver<NQ, FAM> sol(*sm, w, *o);
             sol.solve(pb, mode);
         }

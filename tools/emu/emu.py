@@ -39,7 +39,9 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False):
+def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False, guess_net=None):
+    """guess_net (AL family): dict(W1, b1, W2, b2, W3, b3, mean, std) -> the guess network is evaluated by the solver
+    itself (compute_problem_nnguess); the result then carries the computed guesses as `x_guess`."""
     lib = C.CDLL(build() if not os.path.exists(os.path.join(_HERE, "libemu.so")) else os.path.join(_HERE, "libemu.so"))
     c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
     xg, ug = c(bp["x_guess"]), c(bp["u_guess"])
@@ -60,13 +62,23 @@ def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False):
         assert kernel == "warp"
         pi, lam = np.zeros((B, Nmax, 2 * n)), np.zeros((B, Nmax + 1, 3 * n, 2))
         lib.emu_set_multiplier_out(_p(pi), _p(lam))
+    xg_out = None
+    if guess_net is not None:
+        assert kernel == "warp" and family == 1
+        gw = [c(guess_net["W1"]), c(guess_net["b1"]), c(np.asarray(guess_net["W2"]).T), c(guess_net["b2"]),
+              c(np.asarray(guess_net["W3"]).T), c(guess_net["b3"])]
+        xg_out = np.zeros_like(xg)
+        lib.emu_set_guess_net(1, gw[1].shape[0], gw[5].shape[0], *[_p(a) for a in gw], C.c_double(guess_net["mean"]),
+                              C.c_double(guess_net["std"]), _p(xg_out))
     fn = {"warp": lib.emu_solve_batch, "lane": lib.emu_lane_solve_batch, "lane_dts": lib.emu_lane_dts_solve_batch}[kernel]
     fn(n, family, mode, B, Nmax, Nv.ctypes.data_as(C.POINTER(C.c_int)), _p(xg), _p(ug),
                         *[_p(a) for a in keep], _p(d), _p(h), C.byref(opts), _p(x), _p(u), st)
     if multipliers:
         lib.emu_set_multiplier_out(None, None)
+    if guess_net is not None:
+        lib.emu_set_guess_net(0, 0, 0, None, None, None, None, None, None, C.c_double(0.0), C.c_double(1.0), None)
     f = lambda name: np.array([getattr(s_, name) for s_ in st])
-    return dict(pi=pi, lam=lam, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),
+    return dict(x_guess=xg_out, pi=pi, lam=lam, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),
                 ls_evals=f("ls_evals"), qp_status=f("qp_status"),
                 res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))
 
@@ -119,7 +131,9 @@ def solve_mpc(n, mode, bp, net, opts, multipliers=False):
     assert rc == 0
     if multipliers:
         lib.emu_set_multiplier_out(None, None)
+    if guess_net is not None:
+        lib.emu_set_guess_net(0, 0, 0, None, None, None, None, None, None, C.c_double(0.0), C.c_double(1.0), None)
     f = lambda name: np.array([getattr(s_, name) for s_ in st])
-    return dict(pi=pi, lam=lam, lamg=lamg, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"),
+    return dict(x_guess=xg_out, pi=pi, lam=lam, lamg=lamg, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"),
                 qp_iter=f("qp_iter"), qp_status=f("qp_status"),
                 res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))

@@ -66,7 +66,7 @@ def _rows(X, labels, traj):
 
 def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, fit_guess, etp_stop=0.1,
                     max_rounds=100, N=100, Tf=1.0, device=0, label_fn=None, query_fn=None, history=None,
-                    sharded=False, resident=False):
+                    sharded=False, resident=False, guess_in_kernel=False):
     """Run the loop; returns (X_iter, X_traj, remaining pool).  `fit_cls(model, X_iter)` / `fit_guess(model_guess,
     X_traj)` retrain in place; `history` (list) receives one dict per round.
 
@@ -79,7 +79,10 @@ def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, 
     resident=True: after the initial labelling the pool is uploaded ONCE to the device (`nn.ResidentPool`) and stays
     there; every round's scoring, top-B and removal run on the device (`drivers.al_query_resident`) and only the
     queried rows travel.  The host keeps the float64 states (the OCPs are solved from those, not from the float32
-    copies the network sees) and the map from pool position to original row."""
+    copies the network sees) and the map from pool position to original row.
+
+    guess_in_kernel=True: `compute_problem_nnguess`'s guess network is evaluated inside the solve kernel
+    (`vboc_set_guess_network`) instead of by PyTorch + a (B, N+1, 2n) guess array through the host."""
     from . import distributed as vd
     from . import nn as vnn
     world = rank = 0
@@ -92,6 +95,7 @@ def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, 
             return it_rows, tr_rows
         return vd.all_gather_rows(it_rows), vd.all_gather_rows(tr_rows.reshape(-1, width_tr))
 
+    default_label = label_fn is None
     label_fn = label_fn or (lambda X, xg: drivers.al_label_batch(n, X, device=device, N=N, Tf=Tf, x_guess=xg))
     pool = np.asarray(pool, dtype=float)
     nx = 2 * n
@@ -147,8 +151,13 @@ def active_learning(n, pool, N_init, B, model, model_guess, mean, std, fit_cls, 
             k += 1
             elems = pool[idx]
             pool = np.delete(pool, idx, axis=0)
-        xg = predict_guess(model_guess, elems, mean, std, N, nx) if (model_guess is not None and len(X_traj) and len(elems)) else None
-        if len(elems):
+        use_guess = model_guess is not None and len(X_traj) and len(elems)
+        in_kernel = guess_in_kernel and default_label and use_guess
+        xg = predict_guess(model_guess, elems, mean, std, N, nx) if (use_guess and not in_kernel) else None
+        if in_kernel:   # the guess network is evaluated inside the solve kernel (vboc_set_guess_network)
+            labels, traj = drivers.al_label_batch(n, elems, device=device, N=N, Tf=Tf,
+                                                  guess_net=(model_guess, float(mean), float(std)))
+        elif len(elems):
             labels, traj = label_fn(elems, xg)
         else:
             labels, traj = np.zeros(0, dtype=np.int64), np.zeros((0, N + 1, nx))

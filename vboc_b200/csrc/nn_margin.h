@@ -31,6 +31,49 @@ struct NnNet {
     double mean, stdv, scale;  // scale = (100 - safety_margin) / 100
 };
 
+// Guess network of the AL drivers (AL/triplependulum_class_al.py:171-201, `compute_problem_nnguess`): a 2n-H-H-(N 2n)
+// MLP (my_nn.py NeuralNetCLS) that predicts the whole state trajectory from the initial state; forward only.
+struct GuessNet {
+    int hidden, n_out;
+    const double *W1;   // [H][n_in]
+    const double *b1;   // [H]
+    const double *W2T;  // [H_in][H_out]
+    const double *b2;   // [H]
+    const double *W3T;  // [H][n_out]
+    const double *b3;   // [n_out]
+    double mean, stdv;
+};
+
+// out[j] = (W3 relu(W2 relu(W1 (x0 - mean)/std + b1) + b2) + b3)[j] * std + mean, j < n_out, written through `put(j, v)`.
+// x0 in shared memory, a1 / a2 (H doubles each) in global memory.
+template <int NQ, class Put>
+VB_DEV void guess_forward(const GuessNet &net, const double *x0, double *a1, double *a2, Put put) {
+    constexpr int NX = 2 * NQ;
+    const int H = net.hidden;
+    FOR_LANES
+    for (int k = lane; k < H; k += 32) {
+        double a = net.b1[k];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) a += net.W1[k * NX + i] * ((x0[i] - net.mean) / net.stdv);
+        a1[k] = a > 0.0 ? a : 0.0;
+    }
+    END_LANES
+    FOR_LANES
+    for (int j = lane; j < H; j += 32) {
+        double a = net.b2[j];
+        for (int k = 0; k < H; ++k) a += net.W2T[(size_t)k * H + j] * a1[k];
+        a2[j] = a > 0.0 ? a : 0.0;
+    }
+    END_LANES
+    FOR_LANES
+    for (int j = lane; j < net.n_out; j += 32) {
+        double a = net.b3[j];
+        for (int k = 0; k < H; ++k) a += net.W3T[(size_t)k * net.n_out + j] * a2[k];
+        put(j, a * net.stdv + net.mean);
+    }
+    END_LANES
+}
+
 // h(x) and, if grad != nullptr, dh/dx (NX doubles).  x, grad and the scratch `io` (>= 2 NX + 2 doubles) are in shared
 // memory, a1 / a2 (H doubles each) in global memory.  Warp-uniform result.
 template <int NQ>

@@ -50,6 +50,10 @@ struct Prob {
     const NnNet *nn = nullptr;
     double lh = 0.0, uh = 0.0;
     double *lamg_out = nullptr;  // [2] multipliers of the terminal constraint at the returned iterate (optional)
+    // AL family: the guess network evaluated inside the kernel (compute_problem_nnguess); the state guess is then
+    // computed from the initial state instead of read from xg, and optionally exported (reference-shaped rows)
+    const GuessNet *gnn = nullptr;
+    double *xg_out = nullptr;
 };
 
 template <int NQ>
@@ -411,6 +415,28 @@ struct WarpSolver {
 #pragma unroll 1
         for (int idx = lane; idx < (N + 1) * NC; idx += 32) w.LAM[idx] = 0.0;
         END_LANES
+        if constexpr (FAM == VBOC_FAMILY_AL) {
+            if (pb.gnn) {
+                // compute_problem_nnguess (AL/triplependulum_class_al.py:171-201): stage 0 is the initial state itself,
+                // stages 1..N the de-normalised output of the guess network; controls stay at their (zero) guess
+                FOR_LANES
+                if (lane < NX) s.va[lane] = pb.lbx0[lane], w.Z[NU + lane] = pb.lbx0[lane];
+                END_LANES
+                double *Z = w.Z;
+                guess_forward<NQ>(*pb.gnn, s.va, w.NNA, w.NNA + NN_HMAX, [Z](int j, double v) {
+                    const int k = j / NX + 1, i = j - (k - 1) * NX;
+                    Z[k * NZ + NU + i] = v;
+                });
+                if (pb.xg_out) {
+                    FOR_LANES
+                    for (int idx = lane; idx < (N + 1) * NX; idx += 32) {
+                        const int k = idx / NX, i = idx - k * NX;
+                        pb.xg_out[(size_t)k * pb.nxr + i] = w.Z[k * NZ + NU + i];
+                    }
+                    END_LANES
+                }
+            }
+        }
     }
 
     VB_DEV void store_solution(const Prob &pb, const vboc_stats &st) {

@@ -69,6 +69,9 @@ struct Batch {
     NnNet nn;
     double lh = 0.0, uh = 0.0;
     double *lamg_out = nullptr;
+    // AL family: guess network evaluated in the kernel (vboc_set_guess_network) and the export of the computed guesses
+    const GuessNet *gnn = nullptr;
+    double *xg_out = nullptr;
     double *work;  // slots * work_doubles
     size_t work_doubles;
     unsigned int *counter;
@@ -140,6 +143,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VB_LB_MINB(MINB)) solve_ke
         if (B.pi_out) {
             pb.pi_out = B.pi_out + (size_t)b * B.Nmax * 2 * NQ;
             pb.lam_out = B.lam_out + (size_t)b * (B.Nmax + 1) * 6 * NQ;
+        }
+        if constexpr (FAM == VBOC_FAMILY_AL) {
+            pb.gnn = B.gnn;
+            pb.xg_out = B.xg_out ? B.xg_out + (size_t)b * (B.Nmax + 1) * B.nxr : nullptr;
         }
         sol.solve(pb, B.mode);
         __syncwarp();
@@ -350,6 +357,10 @@ struct vboc_solver {
     NnNet nn;
     double mpc_lh, mpc_uh;
     int mpc_set, mpc_ref_batch;
+    // AL family: guess network (vboc_set_guess_network)
+    double *dgn, *dxg_out;
+    GuessNet *dgnn;   // device copy of the descriptor
+    int gn_on, gn_out;
     vboc_stats *dst;
     unsigned int *dcounter;
     size_t work_doubles;
@@ -566,7 +577,7 @@ void vboc_destroy(vboc_solver *s) {
     void *ptrs[] = {s->dN,    s->dxg,   s->dug,  s->dp,   s->dlbx0, s->dubx0, s->dlbx,
                     s->dubx,  s->dlbxN, s->dubxN, s->dlbu, s->dubu,  s->ddir,  s->dh,
                     s->dx,    s->du,    s->dst,  s->dcounter, s->dwork, s->dpi, s->dlam,
-                    s->dnn,   s->dWz,   s->dWzN, s->dyref, s->dyrefN, s->dlamg};
+                    s->dnn,   s->dWz,   s->dWzN, s->dyref, s->dyrefN, s->dlamg, s->dgn,  s->dxg_out, s->dgnn};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (s->dwork_free_dt) cudaFree(s->dwork_free_dt);
@@ -710,6 +721,10 @@ int vboc_upload(vboc_solver *s, int batch, const int *N, const double *x_guess,
             return fail(VBOC_ERR_UNSUPPORTED, "vboc_upload: pinned and free dt mixed in one batch");
         }
     }
+    if (s->family == VBOC_FAMILY_AL && s->gn_on)
+        for (int b = 0; b < batch; ++b)
+            if (N[b] * 2 * n != s->gn_out)
+                return fail(VBOC_ERR_ARG, "vboc_upload: the guess network predicts N * 2n values for another horizon N");
     size_t B = batch;
     int rc = 0;
 #define UP(dst, src, count) \
@@ -755,6 +770,7 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
     B.dir = s->has_dir ? s->ddir : nullptr, B.h = s->dh;
     B.x = s->dx, B.u = s->du, B.st = s->dst;
     B.pi_out = s->dpi, B.lam_out = s->dpi ? s->dlam : nullptr;
+    if (s->family == VBOC_FAMILY_AL && s->gn_on) B.gnn = s->dgnn, B.xg_out = s->dxg_out;
     B.work = s->dwork, B.work_doubles = s->work_doubles, B.counter = s->dcounter;
     B.mode = mode, B.opts = s->opts;
     CUDA_OK(cudaMemsetAsync(s->dcounter, 0, sizeof(unsigned int), s->stream));
@@ -885,6 +901,50 @@ int vboc_download_mpc_multipliers(vboc_solver *s, double *lamg) {
     if (!s || !s->batch || s->family != VBOC_FAMILY_MPC || !lamg) return fail(VBOC_ERR_ARG, "vboc_download_mpc_multipliers: bad argument");
     CUDA_OK(cudaSetDevice(s->device));
     return d2h(s, lamg, s->dlamg, (size_t)s->batch * 2 * sizeof(double));
+}
+
+int vboc_set_guess_network(vboc_solver *s, int hidden, int n_out, const float *W1, const float *b1, const float *W2,
+                           const float *b2, const float *W3, const float *b3, double mean, double stdv) {
+    if (!s || s->family != VBOC_FAMILY_AL) return fail(VBOC_ERR_ARG, "vboc_set_guess_network: not an AL-family solver");
+    if (s->lane_kernel) return fail(VBOC_ERR_UNSUPPORTED, "vboc_set_guess_network: served by the warp kernel only");
+    CUDA_OK(cudaSetDevice(s->device));
+    if (hidden == 0) {  // switch it off
+        s->gn_on = 0;
+        return 0;
+    }
+    const int nx = 2 * s->n, H = hidden;
+    if (H < 1 || H > NN_HMAX || n_out < nx || n_out % nx || n_out / nx > s->Nmax || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 ||
+        !(stdv > 0.0))
+        return fail(VBOC_ERR_ARG, "vboc_set_guess_network: bad argument (n_out must be N * 2n with N <= N_max)");
+    const size_t o_b1 = (size_t)H * nx, o_W2T = o_b1 + H, o_b2 = o_W2T + (size_t)H * H, o_W3T = o_b2 + H,
+                 o_b3 = o_W3T + (size_t)H * n_out, total = o_b3 + n_out;
+    std::vector<double> h(total);
+    for (size_t i = 0; i < (size_t)H * nx; ++i) h[i] = W1[i];
+    for (int i = 0; i < H; ++i) h[o_b1 + i] = b1[i], h[o_b2 + i] = b2[i];
+    for (int j = 0; j < H; ++j)
+        for (int k = 0; k < H; ++k) h[o_W2T + (size_t)k * H + j] = W2[(size_t)j * H + k];
+    for (int j = 0; j < n_out; ++j) {
+        h[o_b3 + j] = b3[j];
+        for (int k = 0; k < H; ++k) h[o_W3T + (size_t)k * n_out + j] = W3[(size_t)j * H + k];
+    }
+    if (s->dgn) cudaFree(s->dgn);
+    s->dgn = nullptr;
+    CUDA_OK(cudaMalloc((void **)&s->dgn, total * sizeof(double)));
+    CUDA_OK(cudaMemcpy(s->dgn, h.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    GuessNet g;
+    g.hidden = H, g.n_out = n_out, g.W1 = s->dgn, g.b1 = s->dgn + o_b1, g.W2T = s->dgn + o_W2T, g.b2 = s->dgn + o_b2;
+    g.W3T = s->dgn + o_W3T, g.b3 = s->dgn + o_b3, g.mean = mean, g.stdv = stdv;
+    if (!s->dgnn) CUDA_OK(cudaMalloc((void **)&s->dgnn, sizeof(GuessNet)));
+    CUDA_OK(cudaMemcpy(s->dgnn, &g, sizeof(GuessNet), cudaMemcpyHostToDevice));
+    if (!s->dxg_out) CUDA_OK(cudaMalloc((void **)&s->dxg_out, (size_t)s->cap * (s->Nmax + 1) * s->nxr * sizeof(double)));
+    s->gn_on = 1, s->gn_out = n_out;
+    return 0;
+}
+
+int vboc_download_guess(vboc_solver *s, double *x_guess) {
+    if (!s || !s->batch || !s->gn_on || !x_guess) return fail(VBOC_ERR_ARG, "vboc_download_guess: no guess network active");
+    CUDA_OK(cudaSetDevice(s->device));
+    return d2h(s, x_guess, s->dxg_out, (size_t)s->batch * (s->Nmax + 1) * s->nxr * sizeof(double));
 }
 
 int vboc_export_multipliers(vboc_solver *s, int on) {

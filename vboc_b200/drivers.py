@@ -596,13 +596,14 @@ def data_generation_device(n, num_prob, seed, device=0, dgen=None, stats=None, f
 
 # ------------------------------------------------------------------------------------------------
 # AL: feasibility labels and the active-learning query
-def al_label_batch(n, X, device=0, solver=None, N=100, Tf=1.0, x_guess=None):
+def al_label_batch(n, X, device=0, solver=None, N=100, Tf=1.0, x_guess=None, guess_net=None):
     """Batched `testing(s0)` / `testing_guess(s0)` of the AL drivers (AL/triplependulum_al.py:24-62):
     states outside the position / velocity box are labelled unviable without solving (:27-28), the others
     get one SQP_RTI solve (`compute_problem`, AL/triplependulum_class_al.py:148-169): label 1 if status 0,
     0 if status 4 (QP failure), 2 otherwise.  `x_guess` (B, N+1, 2n) replaces the constant guess
-    (`compute_problem_nnguess`, :171-201).  Returns labels (B,) and the (N+1) x 2n trajectories (NaN rows
-    where no viable trajectory exists)."""
+    (`compute_problem_nnguess`, :171-201); `guess_net = (model, mean, std)` evaluates the guess network INSIDE the
+    solve kernel instead (`vboc_set_guess_network`): no guess array is built or copied.  Returns labels (B,) and the
+    (N+1) x 2n trajectories (NaN rows where no viable trajectory exists)."""
     from . import engine
     from ._lib import MODE_RTI
     mdl = pr.Model(n)
@@ -617,7 +618,11 @@ def al_label_batch(n, X, device=0, solver=None, N=100, Tf=1.0, x_guess=None):
         bp = pr.al_problems(n, X[idx], N=N, Tf=Tf, x_guess=None if x_guess is None else np.asarray(x_guess)[idx])
         own = solver is None
         sol = solver or engine.BatchSolver(n, "al", idx.size, N, device=device)
+        if guess_net is not None:
+            sol.set_guess_network(*guess_net)
         out = sol.solve(bp, MODE_RTI)
+        if guess_net is not None and not own:
+            sol.set_guess_network(None, 0.0, 1.0)
         if own:
             sol.close()
         st = out["status"]

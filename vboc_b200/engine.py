@@ -130,6 +130,25 @@ class BatchSolver:
         check(_lib.lib().vboc_download_mpc_multipliers(self._h, _dp(lamg)))
         return lamg
 
+    # -- AL family: the guess network inside the kernel (compute_problem_nnguess) -----------------
+    def set_guess_network(self, model, mean, std):
+        """`model`: torch module with `linear_relu_stack` (2n-H-H-(N 2n)), or None to switch back to host guesses."""
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        if model is None:
+            z = np.zeros(1, dtype=np.float32)
+            check(_lib.lib().vboc_set_guess_network(self._h, 0, 0, fp(z), fp(z), fp(z), fp(z), fp(z), fp(z), 0.0, 1.0))
+            return
+        lin = [m for m in model.linear_relu_stack if hasattr(m, "weight")]
+        g = lambda t: np.ascontiguousarray(t.detach().cpu().numpy().astype(np.float32).ravel())
+        w = [g(lin[0].weight), g(lin[0].bias), g(lin[1].weight), g(lin[1].bias), g(lin[2].weight), g(lin[2].bias)]
+        check(_lib.lib().vboc_set_guess_network(self._h, w[1].shape[0], w[5].shape[0], *[fp(a) for a in w],
+                                                float(mean), float(std)))
+
+    def guess(self):
+        xg = np.zeros((self._batch, self.N_max + 1, self.nx))
+        check(_lib.lib().vboc_download_guess(self._h, _dp(xg)))
+        return xg
+
     def export_multipliers(self, on=True):
         """Have the next solves keep the KKT multipliers of the returned iterates (`multipliers()`)."""
         check(_lib.lib().vboc_export_multipliers(self._h, int(bool(on))))

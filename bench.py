@@ -23,6 +23,9 @@ of the boundary states afterwards, as the drivers do before the NN fit).
            chains, twin simulation (VBOC/triplependulum_vboc.py:19-370) -- as the per-problem state machine on the
            device (`vboc_datagen_run`): SURVEY 8(d)(ii), 8(f)1; at N = 1 with the same generators on the CPU arm
            beside it (`pipeline.cpu`).
+`other_configs`: (N = 1) C3 (2-DOF `data_generation` of 1 024 problems on the device state machine) and C5 (one AL round
+           of the 3-DOF system: 46 656 SQP_RTI labels + the entropy query over the 15^6-state resident pool on the
+           tcgen05 MLP kernel with device top-B and removal), so that they are on the driver's record too.
 `cpu_baseline`: the CPU arm on the host cores, on a bounded sample of the same workload.  kind "acados" when
            `acados_template` + the reference scripts are importable on the box (tools/acados_arm.py: the UNMODIFIED
            reference classes under Pool(os.cpu_count())); otherwise kind "port": the oracle restatement, compiled on
@@ -218,6 +221,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="problems per step of the CPU arm (0 = 64 per host core, shrunk to fit --cpu-budget)")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the whole CPU arm may take")
+    ap.add_argument("--extras", type=int, default=1, help="1: also measure the other BASELINE.json configs (N = 1 only)")
     ap.add_argument("--cpu-pipeline", type=int, default=256, help="problems of the CPU data_generation pipeline leg")
     ap.add_argument("--pipeline", type=int, default=1024,
                     help="problems PER GPU of the data_generation pipeline leg (0 = skip); the reference's round is 1000")
@@ -373,6 +377,48 @@ def main():
         k90 = max(1, int(0.9 * len(order)))
         t90 = float(dst["t_done_us"][order[k90 - 1]]) * 1e-6
         pipeline["converged_solves_per_s_first_90pct_rank0"] = float(dst["converged"][order[:k90]].sum()) / max(t90, 1e-9)
+    # ---- the other configs of BASELINE.json, measured in the same run so that they are on the driver's record
+    # (N = 1 only): C3 2-DOF data generation, C5 one AL round (labelling + pool query), A12 MLP
+    other = None
+    if world == 1 and args.extras:
+        from vboc_b200 import drivers, nn as vnn
+        from vboc_b200._lib import MODE_RTI
+        from vboc_b200.shim.my_nn import NeuralNetCLS
+        other = {}
+        t0 = time.perf_counter()
+        st3 = {}
+        rows3 = drivers.data_generation_device(2, 1024, seed=5, device=local, stats=st3)
+        other["C3_doublependulum_vboc_data_generation"] = {
+            "problems": 1024, "rows": int(rows3.shape[0]), "converged": st3["converged"], "wall_s": time.perf_counter() - t0,
+            "converged_solves_per_s": st3["converged"] / (time.perf_counter() - t0)}
+        nA, BA = 3, 6 ** 6
+        bpa = pr.sample_al(nA, BA, seed=3)
+        sa = engine.BatchSolver(nA, "al", BA, 100, device=local)
+        sa.solve(bpa, MODE_RTI)
+        t0 = time.perf_counter()
+        oa = sa.solve(bpa, MODE_RTI)
+        dta = time.perf_counter() - t0
+        sa.close()
+        torch.manual_seed(0)
+        net = vnn.MLP.from_torch(NeuralNetCLS(6, 500, 2), device=local)
+        Xp = np.random.default_rng(0).uniform(-1, 1, (15 ** 6, 6)).astype(np.float32) * np.array([0.8, 0.8, 0.8, 10.5, 10.5, 10.5], dtype=np.float32) \
+            + np.array([np.pi, np.pi, np.pi, 0, 0, 0], dtype=np.float32)
+        t0 = time.perf_counter()
+        rp = vnn.ResidentPool(Xp, device=local)
+        t_up = time.perf_counter() - t0
+        rp.score(net, 3.14, 5.0)
+        t0 = time.perf_counter()
+        ms_score = rp.score(net, 3.14, 5.0)
+        idxq, _, _ = rp.select(BA)
+        rp.remove_selected()
+        t_query = time.perf_counter() - t0
+        rp.close()
+        net.close()
+        other["C5_triplependulum_al_round"] = {
+            "labelled_states": BA, "labelling_wall_s": dta, "labels_per_s": BA / dta, "viable_fraction": float((oa["status"] == 0).mean()),
+            "pool_states": int(Xp.shape[0]), "pool_upload_once_s": t_up, "pool_score_kernel_ms": ms_score,
+            "pool_score_topB_remove_wall_s": t_query, "selected": int(len(idxq)),
+            "mlp_algorithmic_tflops": 2.0 * Xp.shape[0] * (6 * 500 + 500 * 500 + 500 * 2) / (ms_score * 1e-3) / 1e12}
     if rank == 0:
         cores = os.cpu_count() or 1
         c_n = args.cpu_sample if args.cpu_sample > 0 else 32 * cores   # ~10-30 s of CPU work
@@ -417,6 +463,8 @@ def main():
         }
         if pipeline is not None:
             line["pipeline"] = pipeline
+        if other is not None:
+            line["other_configs"] = other
         if world == 1:
             kind, _, how = cpu_backend()
             line["cpu_baseline"] = {"value": c_conv / c_dt, "unit": UNIT, "cores": cores, "kind": kind,

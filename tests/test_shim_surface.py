@@ -56,3 +56,32 @@ def test_pendulum_vboc_class_surface():
     ocp = m.OCPpendulum()
     assert ocp.N == 50 and ocp.Fmax == 3 and ocp.ocp.dims.nx == 3
     assert callable(ocp.OCP_solve) and callable(ocp.ocp_solver.solve)
+
+
+def test_safe_mpc_class_surface():
+    """VBOC/Safe MPC/hard_terminal_constraints/doublependulum_class_fixedveldir.py:110-276 and its driver 2dof_sym.py:
+    constructor arguments, dimensions, cost / constraint data the driver reads, callable surface."""
+    m = _load("SafeMPC", "doublependulum_class_fixedveldir")
+    rng = np.random.default_rng(0)
+    params = [rng.normal(size=s).astype(np.float32) for s in ((30, 4), (30,), (30, 30), (30,), (1, 30), (1,))]
+    ocp = m.OCPdoublependulumINIT(True, params, 3.14, 0.45, 2.0)
+    sim = m.SYMdoublependulumINIT(True)
+    assert ocp.N == 10 and ocp.Tf == 0.01 and (ocp.nx, ocp.nu) == (4, 2) and ocp.Cmax == 10.
+    assert ocp.ocp.dims.nx == 4 and ocp.ocp.dims.nu == 2 and ocp.ocp.solver_options.nlp_solver_type == "SQP_RTI"
+    assert np.allclose(ocp.ocp.cost.yref, [np.pi, np.pi, 0, 0, 0, 0])
+    for name in ("reset", "set", "cost_set", "constraints_set", "solve", "get"):
+        assert callable(getattr(ocp.ocp_solver, name))
+    assert callable(ocp.OCP_solve) and callable(sim.acados_integrator.solve) and sim.acados_integrator.T == 1e-3
+    # the numeric twin of the constraint function: at rest the margin is the network's output minus the 1e-3 floor
+    x = np.array([3.0, 3.2, 0.0, 0.0])
+    h = ocp.nn_decisionfunction(params, 3.14, 0.45, 2.0, x)
+    a = np.maximum(params[0].astype(float) @ np.array([(3.0 - 3.14) / 0.45, (3.2 - 3.14) / 0.45, 0, 0]) + params[1], 0)
+    a = np.maximum(params[2].astype(float) @ a + params[3], 0)
+    assert abs(h - (float((params[4].astype(float) @ a + params[5])[0]) - 1e-3)) < 1e-12
+
+
+def test_my_nn_mirror():
+    torch = pytest.importorskip("torch")
+    from vboc_b200.shim.my_nn import NeuralNetCLS, NeuralNetDIR
+    x = torch.randn(5, 6)
+    assert NeuralNetCLS(6, 500, 2)(x).shape == (5, 2) and (NeuralNetDIR(6, 500, 1)(x) >= 0).all()

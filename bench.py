@@ -183,8 +183,8 @@ def run_reference(args):
     # problems run all 1000 SQP iterations = seconds on one core) amortises, sized from a short calibration so that
     # the whole --steps/--warmup run stays within a few minutes
     nprob = args.cpu_sample if args.cpu_sample > 0 else 64 * cores
-    c0, dt0 = cpu_sample(4 * cores, 899, cores)
-    rate0 = max(4 * cores / dt0, 1e-9)
+    c0, dt0 = cpu_sample(16 * cores, 899, cores)
+    rate0 = max(16 * cores / dt0, 1e-9)
     budget = args.cpu_budget / max(args.steps + args.warmup, 1)
     if args.cpu_sample <= 0 and nprob / rate0 > budget:
         nprob = max(8 * cores, int(rate0 * budget))
@@ -220,7 +220,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="problems per step of the CPU arm (0 = 64 per host core, shrunk to fit --cpu-budget)")
-    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the whole CPU arm may take")
+    ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds the whole CPU arm may take")
     ap.add_argument("--extras", type=int, default=1, help="1: also measure the other BASELINE.json configs (N = 1 only)")
     ap.add_argument("--cpu-pipeline", type=int, default=256, help="problems of the CPU data_generation pipeline leg")
     ap.add_argument("--pipeline", type=int, default=1024,

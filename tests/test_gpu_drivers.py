@@ -143,10 +143,12 @@ def test_guess_network_in_kernel_matches_oracle_and_torch(oracle, n):
     # an UNTRAINED (random) guess network: trajectories far from feasible put more QPs at the edge of feasibility than a
     # fitted one does (test_al_labels_from_nn_guess_match_oracle: >= 99.9 %); measured 100 % (n = 2) / 99.89 % (n = 3)
     assert (ref["status"] == out["status"]).mean() >= 0.998
-    both = (ref["status"] == 0) & (out["status"] == 0)
+    # trajectories where both IPMs CONVERGED (a QP that runs out of its 50 iterations is tolerated as status 0 by
+    # acados' semantics, but its iterate is wherever the two IPMs happened to stop)
+    both = (ref["status"] == 0) & (out["status"] == 0) & (ref["qp_status"] == 0) & (out["qp_status"] == 0)
     assert both.sum() > 20
     ex = np.abs(ref["x"] - out["x"]).reshape(len(X), -1).max(axis=1)[both]
-    assert np.percentile(ex, 99) < 1e-6 and ex.max() < 1e-4
+    assert np.percentile(ex, 99) < 1e-6 and ex.max() < 1e-4, (np.percentile(ex, 99), ex.max())
     # the driver-level entry point gives the same labels
     labels, _ = drivers.al_label_batch(n, X, guess_net=(guess, mean, std))
     assert np.array_equal(labels, np.where(out["status"] == 0, 1, np.where(out["status"] == 4, 0, 2)))

@@ -74,8 +74,9 @@ for n in (3, 2):
         print("| problem | GPU status (sqp, ipm) | oracle status (sqp, ipm) | GPU res_stat | oracle res_stat | explanation |")
         print("|---|---|---|---|---|---|")
         for b in np.where(~same)[0]:
-            why = ("borderline: one side stops at the iteration limit while the other's stationarity residual just "
-                   "passes tol_stat (different Riccati factorisations round differently after hundreds of SQP iterations)")
+            why = ("the two SQP paths separate (the rounding difference of the two Riccati factorisations is amplified over "
+                   "tens of iterations of a merit line search); one path reaches the exit test, the other cycles until the "
+                   "iteration limit.  A certified KKT point exists for every such problem (profiles/r2_certify.md)")
             print(f"| {b} | {out['status'][b]} ({out['sqp_iter'][b]}, {out['qp_iter'][b]}) | {ref['status'][b]} "
                   f"({ref['sqp_iter'][b]}, {ref['qp_iter'][b]}) | {out['res'][b, 0]:.2e} | {ref['res'][b, 0]:.2e} | {why} |")
         print()

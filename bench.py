@@ -23,7 +23,8 @@ of the boundary states afterwards, as the drivers do before the NN fit).
            chains, twin simulation (VBOC/triplependulum_vboc.py:19-370) -- as the per-problem state machine on the
            device (`vboc_datagen_run`): SURVEY 8(d)(ii), 8(f)1; at N = 1 with the same generators on the CPU arm
            beside it (`pipeline.cpu`).
-`other_configs`: (N = 1) C3 (2-DOF `data_generation` of 1 024 problems on the device state machine) and C5 (one AL round
+`other_configs`: (N = 1) C2 (`doublependulum_testdata.py`: 1 024 test points on the device state machine), C3 (2-DOF
+           `data_generation` of 1 024 problems on the device state machine) and C5 (one AL round
            of the 3-DOF system: 46 656 SQP_RTI labels + the entropy query over the 15^6-state resident pool on the
            tcgen05 MLP kernel with device top-B and removal), so that they are on the driver's record too.
 `cpu_baseline`: the CPU arm on the host cores, on a bounded sample of the same workload.  kind "acados" when
@@ -391,6 +392,12 @@ def main():
         other["C3_doublependulum_vboc_data_generation"] = {
             "problems": 1024, "rows": int(rows3.shape[0]), "converged": st3["converged"], "wall_s": time.perf_counter() - t0,
             "converged_solves_per_s": st3["converged"] / (time.perf_counter() - t0)}
+        t0 = time.perf_counter()
+        st2 = {}
+        Xt2 = drivers.testing_device(2, 1024, seed=1, device=local, stats=st2)
+        other["C2_doublependulum_testdata"] = {
+            "problems": 1024, "test_points": int(Xt2.shape[0]), "solves": st2["solves"], "converged": st2["converged"],
+            "wall_s": time.perf_counter() - t0, "converged_solves_per_s": st2["converged"] / (time.perf_counter() - t0)}
         nA, BA = 3, 6 ** 6
         bpa = pr.sample_al(nA, BA, seed=3)
         sa = engine.BatchSolver(nA, "al", BA, 100, device=local)

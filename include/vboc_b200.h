@@ -234,6 +234,16 @@ int vboc_datagen_run(vboc_datagen *s, int count, int N0, double dt, double tol, 
                      const double *lb0, const double *ub0, const double *retry, double *rows, long long rows_capacity,
                      long long *total_rows, vboc_dg_stats *stats);
 double vboc_datagen_last_kernel_ms(vboc_datagen *s);
+/*
+ * The test-data worker on the device: `Pool.map(testing, range(count))` (triplependulum_testdata.py:9-125, :141-142;
+ * doublependulum_testdata.py:10-121) as one kernel on the same handle -- per problem the extension loop (horizon + 1
+ * while the rounded cost still decreases) with restarts after failed solves.  Inputs are the worker's random draws:
+ * ran [count][n] (un-normalised direction), q_init [count][n], retry [count][60][2n] (per restart the perturbations of
+ * ran and of q_init).  rows [count][2n]: the boundary state of problem b if stats[b].status == 0.  Deliberate deviation:
+ * at most max_solves (<= 60) solves per problem instead of the reference's `while True`.
+ */
+int vboc_testdata_run(vboc_datagen *s, int count, int N0, double dt, int max_solves, const double *ran,
+                      const double *q_init, const double *retry, double *rows, vboc_dg_stats *stats);
 
 /* One classical RK4 step of the unscaled 2n-state model: x_next = Phi_T(x, u).  HOST arrays
  * x [batch][2n], u [batch][n], x_next [batch][2n]. */

@@ -68,3 +68,20 @@ def test_inputs_follow_the_generator_stream():
         assert np.array_equal(req.q_init_ub, inp["ub0"][b])
         assert inp["lb0"][b, inp["joint_sel"][b]] == inp["ub0"][b, inp["joint_sel"][b]]
     assert np.abs(inp["retry"]).max() <= 0.01 and np.abs(inp["retry"]).min() > 0
+
+
+@pytest.mark.parametrize("n,num", [(2, 12), (3, 8)])
+def test_testdata_state_machine_equals_host_generators(oracle, emu, n, num):
+    """`testing(v)` on the device (DataGen::run_testing) against `drivers.testing_worker` over the same solver source."""
+    be = EmuBackend(emu, oracle, n)
+    workers = [drivers.testing_worker(n, drivers._rng(2, i)) for i in range(num)]
+    st = {}
+    ref = drivers.run_workers(n, workers, be, be.sim, st)
+    rows, cnt = emu.testdata_run(n, drivers.testing_inputs(n, num, 2), be.opts)
+    assert sum(c["solves"] for c in cnt) == st["solves"] and sum(c["converged"] for c in cnt) == st["converged"]
+    for b in range(num):
+        if ref[b] is None:
+            assert cnt[b]["status"] == 1
+        else:
+            assert cnt[b]["status"] == 0 and np.abs(rows[b] - ref[b]).max() < 1e-9, (b, np.abs(rows[b] - ref[b]).max())
+    assert any(c["solves"] > 1 for c in cnt)

@@ -55,3 +55,15 @@ def test_datagen_refusals():
     dg.close()
     with pytest.raises(VbocError):
         engine.DataGenerator(1, 4)   # the 1-DOF driver has its own (free-dt) flow
+
+
+@pytest.mark.parametrize("n,num", [(2, 64), (3, 32)])
+def test_device_testdata_state_machine_equals_host_generators(n, num):
+    """`vboc_testdata_run` (`testing(v)`, triplependulum_testdata.py:9-125, as a state machine on the device) against the
+    host generators served by the batched solver: same solve counts, same X_test."""
+    s1, s2 = {}, {}
+    ref = drivers.testing_batch(n, num, seed=2, stats=s1)
+    out = drivers.testing_device(n, num, seed=2, stats=s2)
+    assert s1["solves"] == s2["solves"] and s1["converged"] == s2["converged"]
+    assert ref.shape == out.shape and s2["problems_ok"] == ref.shape[0]
+    assert np.abs(ref - out).max() < 1e-6, np.abs(ref - out).max()

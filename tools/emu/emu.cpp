@@ -240,3 +240,39 @@ extern "C" int emu_solve_mpc(int n, int mode, int batch, int Nmax, const int *N,
     else return -1;
     return 0;
 }
+
+template <int NQ>
+static void run_testdata(int count, const DgParams &P, const vboc_opts *o, const TestIO<NQ> &io) {
+#pragma omp parallel
+    {
+        std::vector<double> buf(Work<NQ>::TOTAL + DgWork<NQ>::TOTAL);
+        Smem<NQ> *sm = new Smem<NQ>();
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < count; ++b) {
+            Work<NQ> w;
+            w.carve(buf.data(), DG_N_CAP);
+            DgWork<NQ> g;
+            g.carve(buf.data() + Work<NQ>::TOTAL);
+            WarpSolver<NQ, VBOC_FAMILY_VBOC> sol(*sm, w, *o);
+            DataGen<NQ> dg(sol, g, P);
+            dg.run_testing(io, b);
+            io.cnt[b] = dg.c;
+        }
+        delete sm;
+    }
+}
+
+extern "C" int emu_testdata_run(int n, int count, int N0, double dt, int max_solves, const double *ran, const double *q_init,
+                                const double *retry, const vboc_opts *o, double *rows, DgCounters *cnt) {
+    DgParams P;
+    P.N0 = N0, P.dt = dt, P.tol = 1e-3;
+    P.q_min = M_PI - M_PI / 4, P.q_max = M_PI + M_PI / 4, P.v_max = 10.0, P.u_max = 10.0;
+    if (n == 2) {
+        TestIO<2> io{ran, q_init, retry, rows, cnt, max_solves, 4, 1e-4};
+        run_testdata<2>(count, P, o, io);
+    } else if (n == 3) {
+        TestIO<3> io{ran, q_init, retry, rows, cnt, max_solves, 3, 1e-3};
+        run_testdata<3>(count, P, o, io);
+    } else return -1;
+    return 0;
+}

@@ -137,3 +137,16 @@ def solve_mpc(n, mode, bp, net, opts, multipliers=False):
     return dict(x_guess=xg_out, pi=pi, lam=lam, lamg=lamg, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"),
                 qp_iter=f("qp_iter"), qp_status=f("qp_status"),
                 res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))
+
+
+def testdata_run(n, inp, opts, N0=100, dt=1e-2, max_solves=60):
+    """The device test-data state machine (DataGen::run_testing) on the host.  Returns (rows (B, 2n), stats list)."""
+    lib = C.CDLL(os.path.join(_HERE, "libemu.so"))
+    B = len(inp["ran"])
+    rows = np.zeros((B, 2 * n))
+    st = (DgStats * B)()
+    rc = lib.emu_testdata_run(n, B, N0, C.c_double(dt), max_solves, _p(np.ascontiguousarray(inp["ran"])),
+                              _p(np.ascontiguousarray(inp["q_init"])), _p(np.ascontiguousarray(inp["retry"])), C.byref(opts),
+                              _p(rows), st)
+    assert rc == 0
+    return rows, [dict((f, getattr(s_, f)) for f, _ in DgStats._fields_) for s_ in st]

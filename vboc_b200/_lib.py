@@ -23,6 +23,7 @@ EXPORTS = (
     "vboc_stream_create", "vboc_stream_destroy", "vboc_stream_set_opts", "vboc_stream_free_slots",
     "vboc_stream_pending", "vboc_stream_submit", "vboc_stream_poll", "vboc_stream_fetch", "vboc_stream_sim_step",
     "vboc_datagen_create", "vboc_datagen_destroy", "vboc_datagen_set_opts", "vboc_datagen_run", "vboc_datagen_last_kernel_ms",
+    "vboc_testdata_run",
     "vboc_pool_create", "vboc_pool_destroy", "vboc_pool_upload", "vboc_pool_size", "vboc_pool_score", "vboc_pool_select",
     "vboc_pool_remove_selected", "vboc_pool_download", "vboc_pool_download_scores", "vboc_pool_last_score_ms",
     "vboc_sim_step", "vboc_mlp_create", "vboc_mlp_destroy", "vboc_mlp_forward", "vboc_mlp_last_kernel_ms", "vboc_fp64_peak", "vboc_last_error", "vboc_version",
@@ -119,6 +120,7 @@ def lib():
         L.vboc_datagen_set_opts.argtypes = [vp, C.POINTER(Opts)]
         L.vboc_datagen_run.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, ip, dp, dp, dp, dp, dp, C.c_longlong,
                                        C.POINTER(C.c_longlong), C.POINTER(DgStats)]
+        L.vboc_testdata_run.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, dp, dp, dp, dp, C.POINTER(DgStats)]
         L.vboc_datagen_last_kernel_ms.argtypes = [vp]
         L.vboc_datagen_last_kernel_ms.restype = C.c_double
         fp = C.POINTER(C.c_float)

@@ -47,6 +47,19 @@ struct DgIO {
     DgCounters *cnt;        // [count]
 };
 
+// inputs / outputs of the test-data state machine (`testing(v)`, triplependulum_testdata.py:9-125)
+constexpr int TG_MAX_SOLVES = 60;
+template <int NQ>
+struct TestIO {
+    const double *ran;     // [count][NQ]                   un-normalised cost direction
+    const double *q_init;  // [count][NQ]                   initial position
+    const double *retry;   // [count][TG_MAX_SOLVES][2 NQ]  per restart: perturbation of ran, then of q_init
+    double *rows;          // [count][2 NQ]                 the boundary state x_0 (status 0)
+    DgCounters *cnt;       // [count]
+    int max_solves, digits;
+    double cost_tol;
+};
+
 // scratch of one warp slot in global memory (reference-shaped solver inputs / outputs and the walk's trajectory)
 template <int NQ>
 struct DgWork {
@@ -187,6 +200,87 @@ struct DataGen {
         if (lane < NX) dst[lane] = x[lane];
         END_LANES
         ++c.n_rows;
+    }
+
+    // the whole of testing(v) for problem b (triplependulum_testdata.py:9-125, doublependulum_testdata.py:10-121):
+    // maximise the initial velocity along a random direction from a random position; horizon + 1 while the rounded
+    // cost still decreases by more than cost_tol; after a failed solve restart with direction and position perturbed.
+    // Deliberate deviation shared with the host generator: at most max_solves solves instead of `while True`.
+    VB_DEV void run_testing(const TestIO<NQ> &io, int b) {
+        c.status = 1, c.n_rows = 0, c.solves = 0, c.converged = 0, c.sim_steps = 0, c.sqp_iter = 0, c.qp_iter = 0, c.t_done_us = 0;
+        const double *retry = io.retry + (size_t)b * TG_MAX_SOLVES * 2 * NQ;
+        set_constants();
+        double ran[NQ], qi[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) ran[i] = io.ran[(size_t)b * NQ + i], qi[i] = io.q_init[(size_t)b * NQ + i];
+        double scale = 1.0;
+        for (int d = 0; d < io.digits; ++d) scale *= 10.0;
+        int N = P.N0, n_retry = 0;
+        double cost = 1e6;
+        bool fresh = true;
+#pragma unroll 1
+        for (int attempt = 0; attempt < io.max_solves; ++attempt) {
+            {
+                const double nr = vnorm(ran);
+                double d[NQ];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) d[i] = ran[i] / nr;
+                set_direction(d);
+            }
+            FOR_LANES
+            if (lane < NXR) {
+                const bool q = lane < NQ, v = lane >= NQ && lane < NX;
+                double qv = 0.0;
+#pragma unroll
+                for (int i = 0; i < NQ; ++i)
+                    if (i == lane) qv = qi[i];
+                g.lbx0[lane] = q ? qv : (v ? -P.v_max : P.dt);
+                g.ubx0[lane] = q ? qv : (v ? P.v_max : P.dt);
+            }
+            END_LANES
+            if (fresh) {
+                // constant guess at the initial position, gravity-compensation torques for the double pendulum
+                FOR_LANES
+                for (int k = lane; k <= N; k += 32) {
+                    double *x = g.xg + (size_t)k * NXR;
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i) x[i] = qi[i], x[NQ + i] = 0.0;
+                    x[NX] = P.dt;
+                    if (k < N) {
+                        double *u = g.ug + (size_t)k * NU;
+#pragma unroll
+                        for (int i = 0; i < NU; ++i)
+                            u[i] = NQ == 2 ? PendN::g * PendN::l * (PendN::m * (NQ - i)) * sin(qi[i]) : 0.0;
+                    }
+                }
+                END_LANES
+                fresh = false;
+            }
+            const int status = solve(N, g.lbx0, g.ubx0);
+            if (status == 0) {
+                const double cnew = g.st->cost;
+                // python round(cost, digits): nearest multiple of 10^-digits
+                if (cnew > nearbyint(cost * scale) / scale - io.cost_tol) {
+                    FOR_LANES
+                    if (lane < NX) io.rows[(size_t)b * NX + lane] = g.xs[lane];
+                    END_LANES
+                    c.status = 0, c.n_rows = 1;
+                    return;
+                }
+                if (N + 1 > DG_N_CAP) return;
+                cost = cnew;
+                extended_guess(N);
+                N += 1;
+            } else {
+                N = P.N0;
+                const double *rp = retry + (size_t)n_retry * 2 * NQ;
+                ++n_retry;
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) ran[i] += rp[i], qi[i] += rp[NQ + i];
+                fresh = true;
+                cost = 1e6;
+            }
+        }
     }
 
     // the whole of data_generation(v) for problem b

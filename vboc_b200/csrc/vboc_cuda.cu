@@ -329,6 +329,46 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) datagen_kernel(const Dg
     }
 }
 
+// testing_kernel: datagen_kernel for the test-data worker `testing(v)` (DataGen::run_testing)
+template <int NQ>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) testing_kernel(const TestIO<NQ> io, int count, const DgParams P,
+                                                                      const vboc_opts opts, double *work,
+                                                                      size_t work_doubles, unsigned int *counter,
+                                                                      unsigned long long *t_start) {
+    __shared__ Smem<NQ> smem[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * WARPS_PER_CTA + warp;
+    unsigned long long t0 = 0;
+    if (lane == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        const unsigned long long prev = atomicCAS(t_start, 0ull, now);
+        t0 = prev ? prev : now;
+    }
+    double *base = work + (size_t)slot * work_doubles;
+    Work<NQ> w;
+    w.carve(base, DG_N_CAP);
+    DgWork<NQ> g;
+    g.carve(base + Work<NQ>::TOTAL);
+    WarpSolver<NQ, VBOC_FAMILY_VBOC> sol(smem[warp], w, opts);
+    DataGen<NQ> dg(sol, g, P);
+    for (;;) {
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned)count) break;
+        dg.run_testing(io, (int)b);
+        __syncwarp();
+        if (lane == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            dg.c.t_done_us = (int)((now - t0) / 1000ull);
+            io.cnt[b] = dg.c;
+        }
+        __syncwarp();
+    }
+}
+
 // gathers the saved rows of all problems into one contiguous array (problem order)
 __global__ void dg_compact_kernel(const double *rows, const DgCounters *cnt, const long long *off, double *out, int nx) {
     const int b = blockIdx.x;
@@ -1481,7 +1521,11 @@ static int datagen_create_impl(vboc_datagen *s, int n_dof, int capacity, int dev
     CUDA_OK(cudaMalloc((void **)&s->dp, B * (n_dof + 1) * sizeof(double)));
     CUDA_OK(cudaMalloc((void **)&s->dlb0, B * nxr * sizeof(double)));
     CUDA_OK(cudaMalloc((void **)&s->dub0, B * nxr * sizeof(double)));
-    CUDA_OK(cudaMalloc((void **)&s->dretry, B * DG_RETRIES * (n_dof + 1) * sizeof(double)));
+    {   // one buffer serves both state machines' restart tables: 10 x (n + 1) (data generation), 60 x 2n (test data)
+        const size_t per = (size_t)DG_RETRIES * (n_dof + 1) > (size_t)TG_MAX_SOLVES * 2 * n_dof ? (size_t)DG_RETRIES * (n_dof + 1)
+                                                                                              : (size_t)TG_MAX_SOLVES * 2 * n_dof;
+        CUDA_OK(cudaMalloc((void **)&s->dretry, B * per * sizeof(double)));
+    }
     CUDA_OK(cudaMalloc((void **)&s->drows, B * DG_ROWS_MAX * nx * sizeof(double)));
     CUDA_OK(cudaMalloc((void **)&s->dcnt, B * sizeof(DgCounters)));
     CUDA_OK(cudaMalloc((void **)&s->dcounter, 4 * sizeof(unsigned int)));
@@ -1615,6 +1659,48 @@ int vboc_datagen_run(vboc_datagen *s, int count, int N0, double dt, double tol, 
         if ((rc = dg_copy(s, rows, dcompact, (size_t)off[B] * nx * sizeof(double), false))) return rc;
     }
     return 0;
+}
+
+int vboc_testdata_run(vboc_datagen *s, int count, int N0, double dt, int max_solves, const double *ran,
+                      const double *q_init, const double *retry, double *rows, vboc_dg_stats *stats) {
+    if (!s) return fail(VBOC_ERR_ARG, "vboc_testdata_run: null handle");
+    if (count < 1 || count > s->cap) return fail(VBOC_ERR_ARG, "vboc_testdata_run: count exceeds capacity");
+    if (!ran || !q_init || !retry || !rows || !stats) return fail(VBOC_ERR_ARG, "vboc_testdata_run: null array");
+    if (N0 < 2 || N0 > DG_N_CAP || !(dt > 0.0) || max_solves < 1 || max_solves > TG_MAX_SOLVES)
+        return fail(VBOC_ERR_ARG, "vboc_testdata_run: bad N0 / dt / max_solves");
+    const int n = s->n;
+    const size_t B = count, nx = 2 * n;
+    CUDA_OK(cudaSetDevice(s->device));
+    int rc;
+    // the data-generation input buffers are reused: dp holds ran, dlb0 holds q_init
+    if ((rc = dg_copy(s, s->dp, ran, B * n * sizeof(double), true))) return rc;
+    if ((rc = dg_copy(s, s->dlb0, q_init, B * n * sizeof(double), true))) return rc;
+    if ((rc = dg_copy(s, s->dretry, retry, B * TG_MAX_SOLVES * 2 * n * sizeof(double), true))) return rc;
+    DgParams P;
+    P.N0 = N0, P.dt = dt, P.tol = 1e-3;
+    P.q_min = M_PI - M_PI / 4, P.q_max = M_PI + M_PI / 4, P.v_max = 10.0, P.u_max = 10.0;
+    CUDA_OK(cudaMemsetAsync(s->dcounter, 0, 4 * sizeof(unsigned int), s->stream));
+    CUDA_OK(cudaEventRecord(s->ev0, s->stream));
+    unsigned long long *t_start = reinterpret_cast<unsigned long long *>(s->dcounter + 2);
+    // triplependulum_testdata.py:82 compares with the cost rounded to 3 decimals minus 1e-3, doublependulum_testdata.py:80
+    // with 4 decimals minus 1e-4
+    if (n == 2) {
+        TestIO<2> io{s->dp, s->dlb0, s->dretry, s->drows, s->dcnt, max_solves, 4, 1e-4};
+        testing_kernel<2><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(io, count, P, s->opts, s->dwork, s->work_doubles,
+                                                                       s->dcounter, t_start);
+    } else {
+        TestIO<3> io{s->dp, s->dlb0, s->dretry, s->drows, s->dcnt, max_solves, 3, 1e-3};
+        testing_kernel<3><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(io, count, P, s->opts, s->dwork, s->work_doubles,
+                                                                       s->dcounter, t_start);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(VBOC_ERR_CUDA, std::string("testing_kernel launch: ") + cudaGetErrorString(e));
+    CUDA_OK(cudaEventRecord(s->ev1, s->stream));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->last_ms = ms;
+    if ((rc = dg_copy(s, stats, s->dcnt, B * sizeof(DgCounters), false))) return rc;
+    return dg_copy(s, rows, s->drows, B * nx * sizeof(double), false);
 }
 
 // vboc_sim_step keeps one grow-on-demand set of device / pinned buffers and a non-blocking stream per device

@@ -214,6 +214,36 @@ def _extended_guess(ans, n):
     return np.vstack([ans.x, ans.x[-1:]]), np.vstack([ans.u, np.zeros((2, n))])[:ans.u.shape[0] + 1]
 
 
+TG_MAX_SOLVES = 60
+
+
+def _tg_initial(n, rng, mdl):
+    """The sampling block of `testing(v)` (triplependulum_testdata.py:15-24): direction and position."""
+    ran = np.array([_pm(rng) * rng.random() for _ in range(n)])
+    q_init = mdl.thetamin + rng.random(n) * (mdl.thetamax - mdl.thetamin)
+    return ran, q_init
+
+
+def _tg_retry(n, rng):
+    """Draws of one restart (triplependulum_testdata.py:100-121): perturbation of the direction, then of the position."""
+    dr = np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
+    dq = np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
+    return dr, dq
+
+
+def testing_inputs(n, num_prob, seed, first=0):
+    """Inputs of the device test-data state machine (`vboc_testdata_run`): what `testing_worker` draws, in its order."""
+    mdl = pr.Model(n)
+    out = dict(ran=np.zeros((num_prob, n)), q_init=np.zeros((num_prob, n)), retry=np.zeros((num_prob, TG_MAX_SOLVES, 2 * n)))
+    for b in range(num_prob):
+        rng = _rng(seed, first + b)
+        out["ran"][b], out["q_init"][b] = _tg_initial(n, rng, mdl)
+        for r in range(TG_MAX_SOLVES):
+            dr, dq = _tg_retry(n, rng)
+            out["retry"][b, r, :n], out["retry"][b, r, n:] = dr, dq
+    return out
+
+
 def testing_worker(n, rng, N0=100, dt_sym=1e-2, max_solves=60):
     """One test-set point: maximise the initial velocity along a random direction from a uniformly random
     position; extend the horizon while the (3-decimal rounded) cost still decreases by > cost_tol; on a
@@ -223,8 +253,7 @@ def testing_worker(n, rng, N0=100, dt_sym=1e-2, max_solves=60):
     # doublependulum_testdata.py:80 with 4 decimals minus 1e-4
     digits, cost_tol = (4, 1e-4) if n == 2 else (3, 1e-3)
     q_lb, q_ub, u_lb, u_ub, q_fin_lb, q_fin_ub = _limits(n, mdl, dt_sym)
-    ran = np.array([_pm(rng) * rng.random() for _ in range(n)])
-    q_init = mdl.thetamin + rng.random(n) * (mdl.thetamax - mdl.thetamin)
+    ran, q_init = _tg_initial(n, rng, mdl)
 
     def fresh(N):
         xg = np.tile(np.concatenate([q_init, np.zeros(n), [dt_sym]]), (N, 1))
@@ -248,8 +277,8 @@ def testing_worker(n, rng, N0=100, dt_sym=1e-2, max_solves=60):
             N += 1
         else:
             N = N0
-            ran = ran + np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
-            q_init = q_init + np.array([rng.random() * _pm(rng) * 0.01 for _ in range(n)])
+            dr, dq = _tg_retry(n, rng)
+            ran, q_init = ran + dr, q_init + dq
             xg, ug = fresh(N)
             cost = 1e6
     return None
@@ -558,6 +587,20 @@ def data_generation_stream(n, num_prob, seed, device=0, ssol=None, stats=None):
         stats["problems"] = num_prob
         stats["problems_ok"] = len(rows)
     return np.concatenate(rows).reshape(-1, 2 * n) if rows else np.empty((0, 2 * n))
+
+
+def testing_device(n, num_prob, seed, device=0, dgen=None, stats=None):
+    """`testing_batch` with the per-problem state machine on the device (`vboc_testdata_run`): same seed, same X_test."""
+    from . import engine
+    own = dgen is None
+    dgen = dgen or engine.DataGenerator(n, num_prob, device=device)
+    rows, st = dgen.run_testing(testing_inputs(n, num_prob, seed))
+    if stats is not None:
+        stats.update(problems=num_prob, problems_ok=int((st["status"] == 0).sum()), solves=int(st["solves"].sum()),
+                     converged=int(st["converged"].sum()), kernel_ms=dgen.last_kernel_ms)
+    if own:
+        dgen.close()
+    return rows
 
 
 def data_generation_device(n, num_prob, seed, device=0, dgen=None, stats=None, first=0, sharded=False):

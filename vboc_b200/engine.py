@@ -318,6 +318,19 @@ class DataGenerator:
         return rows[:total.value].copy(), st
 
 
+    def run_testing(self, inp, N0=100, dt=1e-2, max_solves=60):
+        """`vboc_testdata_run`: inp = drivers.testing_inputs(...); returns (X_test rows of the problems that produced one,
+        per-problem counters)."""
+        B, n = len(inp["ran"]), self.n
+        arrs = [_c(inp[k]) for k in ("ran", "q_init", "retry")]
+        assert arrs[0].shape == (B, n) and arrs[2].shape == (B, 60, 2 * n)
+        rows = np.zeros((B, 2 * n))
+        st = np.zeros(B, dtype=_DG_DTYPE)
+        check(_lib.lib().vboc_testdata_run(self._h, B, int(N0), float(dt), int(max_solves), *[_dp(a) for a in arrs],
+                                           _dp(rows), st.ctypes.data_as(C.POINTER(_lib.DgStats))))
+        return rows[st["status"] == 0], st
+
+
 def sim_step(n, x, u, T, device=0):
     """Batched RK4 step of the unscaled model (the reference's `sim.acados_integrator`)."""
     x, u = _c(np.atleast_2d(x)), _c(np.atleast_2d(u))

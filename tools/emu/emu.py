@@ -131,10 +131,8 @@ def solve_mpc(n, mode, bp, net, opts, multipliers=False):
     assert rc == 0
     if multipliers:
         lib.emu_set_multiplier_out(None, None)
-    if guess_net is not None:
-        lib.emu_set_guess_net(0, 0, 0, None, None, None, None, None, None, C.c_double(0.0), C.c_double(1.0), None)
     f = lambda name: np.array([getattr(s_, name) for s_ in st])
-    return dict(x_guess=xg_out, pi=pi, lam=lam, lamg=lamg, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"),
+    return dict(pi=pi, lam=lam, lamg=lamg, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"),
                 qp_iter=f("qp_iter"), qp_status=f("qp_status"),
                 res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))
 

@@ -164,6 +164,21 @@ int vboc_set_mpc(vboc_solver *s, int hidden, const float *W1, const float *b1, c
 int vboc_set_mpc_reference(vboc_solver *s, int batch, const double *yref, const double *yref_e);
 int vboc_download_mpc_multipliers(vboc_solver *s, double *lamg);
 /*
+ * Soft rows: the `parallel`, `receiding_hard_constraints` and `soft_traj_constraints` variants of the Safe-MPC classes
+ * (VBOC/Safe MPC/parallel/doublependulum_class_fixedveldir.py:175-199) impose the margin at EVERY stage and soften it,
+ *     con_h_expr = con_h_expr_e = h,  lh = 0, uh = 1e6,  idxsh = idxsh_e = [0]:
+ *     lh <= h(x_k) + sl_k,  h(x_k) - su_k <= uh,  sl_k, su_k >= 0,  cost += 1/2 Zl_k sl_k^2 + zl_k sl_k + 1/2 Zu_k su_k^2 + zu_k su_k,
+ * with the penalties set per stage at run time (cost_set(i, "Zl", ...), VBOC/Safe MPC/parallel/2dof_sym.py:44-50,
+ * receiding_hard_constraints/2dof_sym.py:53-57, soft_traj_constraints/2dof_sym.py:110-111).
+ * vboc_set_mpc_rows: Z [batch][N_max+1][4] = (Zl, Zu, zl, zu) per problem and stage (stage k of a problem with horizon
+ * N <= N_max uses rows 0..N) for the problems of the next vboc_upload / vboc_solve_batch; batch = 0 switches back to the
+ * single hard terminal row.  The slacks are variables of the NLP (zero at reset, stepped with the line search) and are
+ * eliminated from the Newton systems of the IPM, so a row costs a rank-one term in its stage's Riccati step.
+ * vboc_download_mpc_rows: rows [batch][N_max+1][6] = (lam_l, lam_u, lam_sl, lam_su, sl, su) at the returned iterate.
+ */
+int vboc_set_mpc_rows(vboc_solver *s, int batch, const double *Z);
+int vboc_download_mpc_rows(vboc_solver *s, double *rows);
+/*
  * AL family: `compute_problem_nnguess` (AL/triplependulum_class_al.py:171-201) with the guess network evaluated INSIDE the
  * solve kernel: a 2n-H-H-(N 2n) MLP (my_nn.py NeuralNetCLS, PyTorch nn.Linear layout, float32) predicts the state
  * trajectory of stages 1..N from the initial state, out = model((x0 - mean) / std) * std + mean; stage 0 takes x0.  After

@@ -86,3 +86,85 @@ def test_margin_function_matches_the_reference_expression():
         x = np.concatenate([rng.uniform(2.4, 3.9, 2), rng.uniform(-8, 8, 2)])
         want = OCPdoublependulumINIT.nn_decisionfunction(None, params, net["mean"], net["std"], 0.0, x)
         assert abs(certify.nn_margin(net, x, 2) - want) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# soft rows: the margin at every stage with slacks (parallel / receiding_hard_constraints / soft_traj_constraints)
+def _row_penalties(kind, B, N):
+    Z = np.zeros((B, N + 1, 4))
+    if kind == "soft_traj":          # VBOC/Safe MPC/soft_traj_constraints/2dof_sym.py:110-111
+        Z[:, :, 0] = 1e6
+    elif kind == "parallel":         # VBOC/Safe MPC/parallel/2dof_sym.py:44-50: 1e9 at one stage p, vacuous rows elsewhere
+        for b in range(B):
+            Z[b, N - b % 6, 0] = 1e9
+    elif kind == "receding":         # VBOC/Safe MPC/receiding_hard_constraints/2dof_sym.py:53-57
+        Z[:, :, 0] = 10 ** ((1 - 0.5) * 6)
+        for b in range(B):
+            Z[b, N - b % 6, 0] = 1e12
+    elif kind == "generic":          # every penalty field in use (the engine's interface is general)
+        Z[:, :, 0], Z[:, :, 1], Z[:, :, 2], Z[:, :, 3] = 1e2, 3.0, 0.5, 0.1
+    return Z
+
+
+def _rel(r, rowm):
+    """KKT residuals relative to the size of the numbers they are differences of (multipliers reach Zl * sl ~ 1e9)."""
+    s = max(1.0, float(np.abs(rowm[:, :4]).max()))
+    return max(r["res_stat"], r["res_comp"]) / s, max(r["res_eq"], r["res_ineq"])
+
+
+@pytest.mark.parametrize("kind", ["soft_traj", "parallel", "receding", "generic"])
+def test_soft_rows_rti_step_satisfies_dense_kkt(emu, kind):
+    n, B, N = 2, 24, 10
+    net = make_net(n, 64, n, 4.0)
+    bp = pr.sample_mpc(n, B, seed=3)
+    Z = _row_penalties(kind, B, N)
+    out = emu.solve_mpc(n, 1, bp, net, mpc_opts(emu), multipliers=True, rowZ=Z)
+    ok = np.where(out["status"] == 0)[0]
+    # with slacks the QP is feasible wherever the box constraints alone are: more problems solve than with the hard row
+    hard = emu.solve_mpc(n, 1, bp, net, mpc_opts(emu), multipliers=True)
+    assert len(ok) >= (hard["status"] == 0).sum() and len(ok) >= 20
+    slack_used = 0
+    for b in ok:
+        r = certify.mpc_rows_kkt(n, bp, net, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["rowm"][b], Z[b],
+                                 1.0, first_qp_at_guess=True)
+        rel, feas = _rel(r, out["rowm"][b])
+        assert rel < 1e-8 and feas < 1e-8 and r["lam_min"] >= 0.0, (b, r)
+        slack_used += r["sl"].max() > 1e-3
+    assert slack_used >= 3               # the margin is violated (and paid for) on some problems
+
+
+def test_soft_rows_sqp_run_satisfies_nlp_kkt(emu):
+    n, B, N = 2, 12, 10
+    net = make_net(n, 64, 0, 4.0)
+    bp = pr.sample_mpc(n, B, seed=3)
+    Z = _row_penalties("soft_traj", B, N)
+    out = emu.solve_mpc(n, 0, bp, net, mpc_opts(emu, tol=1e-2), multipliers=True, rowZ=Z)
+    ok = np.where(out["status"] == 0)[0]
+    assert len(ok) >= 8
+    for b in ok:
+        r = certify.mpc_rows_kkt(n, bp, net, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["rowm"][b], Z[b], 1.0)
+        assert max(r["res_stat"], r["res_eq"], r["res_ineq"], r["res_comp"]) < 1e-2, (b, r)
+        s = max(1.0, float(np.abs(out["rowm"][b, :, :4]).max()))
+        assert abs(r["res_stat"] - out["res"][b, 0]) < 1e-9 * s and abs(r["res_ineq"] - out["res"][b, 2]) < 1e-9
+
+
+def test_soft_rows_limits(emu):
+    """Zl = 0 everywhere: every row is vacuous, the solution is that of the problem without the margin constraint.
+    Zl = 1e9 at the terminal stage only: the solution approaches that of the hard terminal row."""
+    n, B, N = 2, 16, 10
+    net = make_net(n, 64, n, 4.0)
+    bp = pr.sample_mpc(n, B, seed=3)
+    free = dict(bp)
+    free["lh"] = -1e9                                    # hard row that can never bind
+    ref = emu.solve_mpc(n, 1, free, net, mpc_opts(emu))
+    out = emu.solve_mpc(n, 1, bp, net, mpc_opts(emu), rowZ=np.zeros((B, N + 1, 4)))
+    ok = (ref["status"] == 0) & (out["status"] == 0)
+    assert ok.sum() >= 14
+    assert np.abs(out["x"] - ref["x"])[ok].max() < 1e-6 and np.abs(out["u"] - ref["u"])[ok].max() < 1e-5
+    hard = emu.solve_mpc(n, 1, bp, net, mpc_opts(emu))
+    Z = np.zeros((B, N + 1, 4))
+    Z[:, N, 0] = 1e9
+    stiff = emu.solve_mpc(n, 1, bp, net, mpc_opts(emu), rowZ=Z)
+    ok = (hard["status"] == 0) & (stiff["status"] == 0)
+    assert ok.sum() >= 10
+    assert np.abs(stiff["x"] - hard["x"])[ok].max() < 1e-5 and np.abs(stiff["u"] - hard["u"])[ok].max() < 1e-3

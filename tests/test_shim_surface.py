@@ -80,6 +80,25 @@ def test_safe_mpc_class_surface():
     assert abs(h - (float((params[4].astype(float) @ a + params[5])[0]) - 1e-3)) < 1e-12
 
 
+@pytest.mark.parametrize("variant", ["parallel", "receiding_hard_constraints", "soft_traj_constraints"])
+def test_soft_row_safe_mpc_class_surface(variant):
+    """VBOC/Safe MPC/{parallel, receiding_hard_constraints, soft_traj_constraints}/doublependulum_class_fixedveldir.py:
+    the same surface plus cost_set(i, "Zl", ..) (2dof_sym.py of each variant) and the margin WITH the safety factor."""
+    m = importlib.import_module(f"vboc_b200.shim.SafeMPC.{variant}.doublependulum_class_fixedveldir")
+    rng = np.random.default_rng(0)
+    params = [rng.normal(size=s).astype(np.float32) for s in ((30, 4), (30,), (30, 30), (30,), (1, 30), (1,))]
+    ocp = m.OCPdoublependulumINIT(True, params, 3.14, 0.45, 2.0)
+    assert ocp.SOFT_ROWS and ocp.N == 10 and callable(ocp.OCP_solve) and callable(m.SYMdoublependulumINIT)
+    for i in range(ocp.N + 1):
+        ocp.ocp_solver.cost_set(i, "Zl", 1e9 * np.ones((1,)) if i == 7 else np.zeros((1,)))
+    assert ocp.ocp_solver.Zl[7] == 1e9 and ocp.ocp_solver.Zl.sum() == 1e9
+    x = np.array([3.0, 3.2, 0.0, 0.0])
+    a = np.maximum(params[0].astype(float) @ np.array([(3.0 - 3.14) / 0.45, (3.2 - 3.14) / 0.45, 0, 0]) + params[1], 0)
+    a = np.maximum(params[2].astype(float) @ a + params[3], 0)
+    want = float((params[4].astype(float) @ a + params[5])[0]) * 0.98 - 1e-3
+    assert abs(ocp.nn_decisionfunction(params, 3.14, 0.45, 2.0, x) - want) < 1e-12
+
+
 def test_my_nn_mirror():
     torch = pytest.importorskip("torch")
     from vboc_b200.shim.my_nn import NeuralNetCLS, NeuralNetDIR

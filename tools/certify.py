@@ -342,6 +342,63 @@ def mpc_kkt(n, bp, net, b, x, u, pi, lam, lamg, lm, first_qp_at_guess=False):
                 lam_min=min(np.where(ineq, np.minimum(ll, lu), 0).min(), lamg.min()), h=hlin)
 
 
+def mpc_rows_kkt(n, bp, net, b, x, u, pi, lam, rowm, rowZ, lm, first_qp_at_guess=False):
+    """mpc_kkt for the SOFT-ROW variants of the Safe-MPC classes (VBOC/Safe MPC/{parallel, receiding_hard_constraints,
+    soft_traj_constraints}/doublependulum_class_fixedveldir.py:175-199): the margin row at every stage k = 0..N,
+        lh <= h(x_k) + sl_k,   h(x_k) - su_k <= uh,   sl_k, su_k >= 0,   cost += 1/2 Zl sl^2 + zl sl + 1/2 Zu su^2 + zu su.
+    rowm [N+1][6] = (lam_l, lam_u, lam_sl, lam_su, sl, su) as the engine exports them, rowZ [N+1][4] = (Zl, Zu, zl, zu).
+    Lagrangian terms: lam_l (lh - h - sl) + lam_u (h - su - uh) - lam_sl sl - lam_su su."""
+    N = int(bp["N"][b])
+    nx, nz, h = 2 * n, 3 * n, bp["Tf"] / int(bp["N"][b])
+    X, U = x[:N + 1, :nx], u[:N]
+    Wz, WzN, yref, yrefN = bp["Wz"], bp["WzN"], bp["yref"][b], bp["yrefN"][b]
+    lb = np.concatenate([bp["lbu"][b], bp["lbx"][b]])
+    ub = np.concatenate([bp["ubu"][b], bp["ubx"][b]])
+    Z = np.concatenate([np.concatenate([U, np.zeros((1, n))]), X], axis=1)
+    exists = np.ones((N + 1, nz), dtype=bool)
+    exists[N, :n] = False
+    fixed = np.zeros((N + 1, nz), dtype=bool)
+    fixed[0, n:] = True
+    ineq = exists & ~fixed
+    ll, lu = lam[:N + 1, :, 0], lam[:N + 1, :, 1]
+    rowm, rowZ = rowm[:N + 1], rowZ[:N + 1]
+    l1, l2, l3, l4, sl, su = (rowm[:, j] for j in range(6))
+    scale = np.concatenate([np.full(N, h), [1.0]])[:, None]
+    W = np.concatenate([np.tile(Wz, (N, 1)), np.concatenate([np.zeros(n), WzN])[None]])
+    ref = np.concatenate([np.tile(yref, (N, 1)), np.concatenate([np.zeros(n), yrefN])[None]])
+    if first_qp_at_guess:
+        Xg, Ug = bp["x_guess"][b, :N + 1], bp["u_guess"][b, :N]
+        Zg = np.concatenate([np.concatenate([Ug, np.zeros((1, n))]), Xg], axis=1)
+        xn, A, Bm = rk4_jac(n, Xg[:N], Ug, h)
+        DZ = Z - Zg
+        res_eq = np.abs(np.einsum("kij,kj->ki", A, DZ[:N, n:]) + np.einsum("kij,kj->ki", Bm, DZ[:N, :n]) + (xn - Xg[1:]) - DZ[1:, n:]).max()
+        hg = [nn_margin_grad(net, Xg[k], n) for k in range(N + 1)]
+        gc = np.stack([g_[1] for g_ in hg])
+        hlin = np.array([g_[0] for g_ in hg]) + np.einsum("ki,ki->k", gc, DZ[:, n:])
+        grad = scale * W * (Zg - ref) + (scale * W + lm) * DZ
+    else:
+        xn, A, Bm = rk4_jac(n, X[:N], U, h)
+        res_eq = np.abs(xn - X[1:]).max()
+        hg = [nn_margin_grad(net, X[k], n) for k in range(N + 1)]
+        gc = np.stack([g_[1] for g_ in hg])
+        hlin = np.array([g_[0] for g_ in hg])
+        grad = scale * W * (Z - ref)
+    x0_err = np.abs(Z[0, n:] - bp["x0"][b]).max()
+    fl, fu = lb - Z, Z - ub
+    rl, ru = bp["lh"] - hlin - sl, hlin - su - bp["uh"]
+    res_ineq = max(np.where(ineq, np.maximum(np.maximum(fl, fu), 0), 0).max(), x0_err, rl.max(), ru.max(), (-sl).max(), (-su).max(), 0.0)
+    res_comp = max(np.where(ineq, np.maximum(np.abs(ll * fl), np.abs(lu * fu)), 0).max(), np.abs(l1 * rl).max(),
+                   np.abs(l2 * ru).max(), np.abs(l3 * sl).max(), np.abs(l4 * su).max())
+    r = grad + np.where(ineq, lu - ll, 0.0)
+    r[:N] += np.einsum("kij,ki->kj", np.concatenate([Bm, A], axis=2), pi[:N])
+    r[1:, n:] -= pi[:N]
+    r[:, n:] += gc * (l2 - l1)[:, None]
+    r = np.where(ineq, r, 0.0)
+    rs = np.stack([rowZ[:, 0] * sl + rowZ[:, 2] - l1 - l3, rowZ[:, 1] * su + rowZ[:, 3] - l2 - l4])
+    return dict(res_stat=max(np.abs(r).max(), np.abs(rs).max()), res_eq=res_eq, res_ineq=res_ineq, res_comp=res_comp,
+                lam_min=min(np.where(ineq, np.minimum(ll, lu), 0).min(), rowm[:, :4].min()), h=hlin, sl=sl)
+
+
 # ------------------------------------------------------------------------------------------------ report
 def _solve_with_multipliers(n, family, bp, mode, opts=None):
     from vboc_b200 import engine

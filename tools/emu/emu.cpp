@@ -194,11 +194,12 @@ template <int NQ>
 static void run_mpc(int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug, const double *x0,
                     const double *lbx, const double *ubx, const double *lbu, const double *ubu, const double *Wz,
                     const double *WzN, const double *yref, const double *yrefN, double Tf, const NnNet &net, double lh,
-                    double uh, const vboc_opts *o, double *x, double *u, vboc_stats *st, double *lamg) {
+                    double uh, const vboc_opts *o, double *x, double *u, vboc_stats *st, double *lamg, int rows_soft,
+                    const double *rowZ, double *rowm) {
     const int nxr = 2 * NQ, nu = NQ, nz = 3 * NQ;
 #pragma omp parallel
     {
-        std::vector<double> buf(Work<NQ>::doubles(Nmax));
+        std::vector<double> buf(Work<NQ>::doubles_rows(Nmax));
         Smem<NQ> *sm = new Smem<NQ>();
         SmemMpc<NQ> *gm = new SmemMpc<NQ>();
 #pragma omp for schedule(dynamic, 1)
@@ -213,6 +214,8 @@ static void run_mpc(int mode, int batch, int Nmax, const int *N, const double *x
             pb.x = x + (size_t)b * (Nmax + 1) * nxr, pb.u = u + (size_t)b * Nmax * nu, pb.st = st + b;
             pb.Wz = Wz, pb.WzN = WzN, pb.yref = yref + (size_t)b * nz, pb.yrefN = yrefN + (size_t)b * nxr;
             pb.nn = &net, pb.lh = lh, pb.uh = uh, pb.lamg_out = lamg ? lamg + 2 * b : nullptr;
+            pb.rows_soft = rows_soft, pb.rowZ = rowZ ? rowZ + (size_t)b * (Nmax + 1) * 4 : nullptr;
+            pb.rowm_out = rowm ? rowm + (size_t)b * (Nmax + 1) * 6 : nullptr;
             if (g_pi) pb.pi_out = g_pi + (size_t)b * Nmax * 2 * NQ, pb.lam_out = g_lam + (size_t)b * (Nmax + 1) * 6 * NQ;
             WarpSolver<NQ, VBOC_FAMILY_MPC> sol(*sm, w, *o, gm);
             sol.solve(pb, mode);
@@ -227,7 +230,8 @@ extern "C" int emu_solve_mpc(int n, int mode, int batch, int Nmax, const int *N,
                              const double *Wz, const double *WzN, const double *yref, const double *yrefN, double Tf,
                              int hidden, const double *W1, const double *b1, const double *W2, const double *b2,
                              const double *W3, double b3, double mean, double stdv, double scale, double lh, double uh,
-                             const vboc_opts *o, double *x, double *u, vboc_stats *st, double *lamg) {
+                             const vboc_opts *o, double *x, double *u, vboc_stats *st, double *lamg, int rows_soft,
+                             const double *rowZ, double *rowm) {
     std::vector<double> w2t((size_t)hidden * hidden);
     for (int j = 0; j < hidden; ++j)
         for (int k = 0; k < hidden; ++k) w2t[(size_t)k * hidden + j] = W2[(size_t)j * hidden + k];
@@ -235,8 +239,8 @@ extern "C" int emu_solve_mpc(int n, int mode, int batch, int Nmax, const int *N,
     net.n_in = 2 * n, net.hidden = hidden, net.W1 = W1, net.b1 = b1, net.W2 = W2, net.W2T = w2t.data(), net.b2 = b2;
     net.W3 = W3, net.b3 = b3, net.mean = mean, net.stdv = stdv, net.scale = scale;
     if (hidden > NN_HMAX) return -1;
-    if (n == 2) run_mpc<2>(mode, batch, Nmax, N, xg, ug, x0, lbx, ubx, lbu, ubu, Wz, WzN, yref, yrefN, Tf, net, lh, uh, o, x, u, st, lamg);
-    else if (n == 3) run_mpc<3>(mode, batch, Nmax, N, xg, ug, x0, lbx, ubx, lbu, ubu, Wz, WzN, yref, yrefN, Tf, net, lh, uh, o, x, u, st, lamg);
+    if (n == 2) run_mpc<2>(mode, batch, Nmax, N, xg, ug, x0, lbx, ubx, lbu, ubu, Wz, WzN, yref, yrefN, Tf, net, lh, uh, o, x, u, st, lamg, rows_soft, rowZ, rowm);
+    else if (n == 3) run_mpc<3>(mode, batch, Nmax, N, xg, ug, x0, lbx, ubx, lbu, ubu, Wz, WzN, yref, yrefN, Tf, net, lh, uh, o, x, u, st, lamg, rows_soft, rowZ, rowm);
     else return -1;
     return 0;
 }

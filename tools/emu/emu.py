@@ -106,9 +106,10 @@ def datagen_run(n, inp, opts, N0=100, dt=1e-2, tol=1e-3):
     return out, [dict((f, getattr(s_, f)) for f, _ in DgStats._fields_) for s_ in st]
 
 
-def solve_mpc(n, mode, bp, net, opts, multipliers=False):
+def solve_mpc(n, mode, bp, net, opts, multipliers=False, rowZ=None):
     """MPC family on the host emulation.  bp: problems.sample_mpc(...); net: dict(W1, b1, W2, b2, W3 (H,), b3, mean, std,
-    scale) in float64."""
+    scale) in float64.  rowZ (B, N+1, 4) = per-stage (Zl, Zu, zl, zu): the margin row at every stage, softened (the
+    parallel / receding / soft_traj variants); None: the hard terminal row."""
     lib = C.CDLL(os.path.join(_HERE, "libemu.so"))
     c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     xg, ug = c(bp["x_guess"]), c(bp["u_guess"])
@@ -118,6 +119,10 @@ def solve_mpc(n, mode, bp, net, opts, multipliers=False):
     x, u = np.zeros_like(xg), np.zeros_like(ug)
     st = (Stats * B)()
     lamg = np.zeros((B, 2))
+    rowm = np.zeros((B, Nmax + 1, 6))
+    if rowZ is not None:
+        rowZ = c(rowZ)
+        assert rowZ.shape == (B, Nmax + 1, 4)
     pi = lam = None
     if multipliers:
         pi, lam = np.zeros((B, Nmax, 2 * n)), np.zeros((B, Nmax + 1, 3 * n, 2))
@@ -127,12 +132,13 @@ def solve_mpc(n, mode, bp, net, opts, multipliers=False):
     rc = lib.emu_solve_mpc(n, mode, B, Nmax, Nv.ctypes.data_as(C.POINTER(C.c_int)), _p(xg), _p(ug), *[_p(a) for a in keep],
                            C.c_double(bp["Tf"]), int(w[0].shape[0]), *[_p(a) for a in w], C.c_double(float(net["b3"])),
                            C.c_double(net["mean"]), C.c_double(net["std"]), C.c_double(net["scale"]), C.c_double(bp["lh"]),
-                           C.c_double(bp["uh"]), C.byref(opts), _p(x), _p(u), st, _p(lamg))
+                           C.c_double(bp["uh"]), C.byref(opts), _p(x), _p(u), st, _p(lamg), int(rowZ is not None),
+                           _p(rowZ) if rowZ is not None else None, _p(rowm))
     assert rc == 0
     if multipliers:
         lib.emu_set_multiplier_out(None, None)
     f = lambda name: np.array([getattr(s_, name) for s_ in st])
-    return dict(pi=pi, lam=lam, lamg=lamg, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"),
+    return dict(pi=pi, lam=lam, lamg=lamg, rowm=rowm, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"),
                 qp_iter=f("qp_iter"), qp_status=f("qp_status"),
                 res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))
 

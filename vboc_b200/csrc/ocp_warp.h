@@ -50,6 +50,13 @@ struct Prob {
     const NnNet *nn = nullptr;
     double lh = 0.0, uh = 0.0;
     double *lamg_out = nullptr;  // [2] multipliers of the terminal constraint at the returned iterate (optional)
+    // soft rows (VBOC/Safe MPC/{parallel,receiding_hard_constraints,soft_traj_constraints}/doublependulum_class_fixedveldir.py:
+    // con_h_expr = con_h_expr_e, idxsh = idxsh_e = [0]): the margin row at EVERY stage 0..N, both sides softened by slacks
+    // sl, su >= 0 with the per-stage penalties of cost_set(i, "Zl", ...) -- rowZ [N+1][4] = (Zl, Zu, zl, zu), or nullptr
+    // for all zero.  rows_soft = 0: the hard terminal row only.
+    int rows_soft = 0;
+    const double *rowZ = nullptr;
+    double *rowm_out = nullptr;  // [N+1][6] (lam_l, lam_u, lam_sl, lam_su, sl, su) of the rows at the returned iterate
     // AL family: the guess network evaluated inside the kernel (compute_problem_nnguess); the state guess is then
     // computed from the initial state instead of read from xg, and optionally exported (reference-shaped rows)
     const GuessNet *gnn = nullptr;
@@ -61,6 +68,23 @@ struct Dim {
     static constexpr int NX = 2 * NQ, NU = NQ, NZ = 3 * NQ, NC = 2 * NZ;
     static constexpr int FS = NU * NU + NX * NU + NX * NX;  // Riccati factor record per stage
     static constexpr int MFS = NZ * NZ + NZ + NU;           // last-stage record
+};
+
+// Row record of the MPC family: one general two-sided constraint  lh <= h(x_k) + sl_k,  h(x_k) - su_k <= uh  per stage
+// (the learned margin), optionally softened; field offsets in doubles.  IPM order of its one-sided constraints:
+// 0 row lower, 1 row upper, 2 slack sl >= 0, 3 slack su >= 0.
+struct RowF {
+    static constexpr int GC = 0;     // [6] gradient of h at the NLP iterate
+    static constexpr int GH = 6, LGD = 7, UGD = 8;            // h, bounds of the linearised row (lh - h, uh - h)
+    static constexpr int WEFF = 9, BARG = 10, Q1G = 11, Q2G = 12;  // barrier Hessian weight / gradient pieces (slacks eliminated)
+    static constexpr int ZS = 13;    // [4] Zl, Zu, zl, zu
+    static constexpr int ON = 17;    // 1.0: the row exists at this stage
+    static constexpr int LAMG = 18, LAMS = 20, SL = 22;       // NLP: row multipliers, slack-bound multipliers, slacks
+    static constexpr int WGM = 24, WSM = 26;                  // merit weights
+    static constexpr int LQ = 28, TQ = 32;                    // [4] QP multipliers / slacks of the inequalities
+    static constexpr int SIG = 36, DSIG = 38;                 // [2] QP value of (sl, su) and its step
+    static constexpr int RD = 40, PR = 44;                    // [4] bound residuals, second-order products
+    static constexpr int SIZE = 48;
 };
 
 // Per-stage record: everything the serial Riccati sweeps read at stage k, contiguous so that one
@@ -190,6 +214,7 @@ struct Work {
     double *PP, *MF;                 // value functions; last-stage record
     double *WDYN, *WB, *ZT;          // merit weights, trial point
     double *NNA;                     // MPC family: activations of the margin network (2 x NN_HMAX)
+    double *ROW;                     // MPC family: row records (SMAX x RowF::SIZE), behind TOTAL (doubles_rows())
     // The workspace is carved with the compile-time stride SMAX so that every array is the slot base
     // plus a constant (no pointer table in registers, immediate offsets in the load/store
     // instructions); N_max <= SMAX - 1 is checked by vboc_create.
@@ -207,6 +232,7 @@ struct Work {
     static_assert(O_PIQ % 2 == 0 && O_LAMQ % 2 == 0 && O_TQ % 2 == 0 && O_DLAM % 2 == 0 && O_DT % 2 == 0 && O_RD % 2 == 0 &&
                       O_RM % 2 == 0, "16-byte aligned arrays");
     static VB_HD size_t doubles(int) { return TOTAL; }
+    static VB_HD size_t doubles_rows(int) { return TOTAL + SMAX * RowF::SIZE; }  // MPC family
     VB_HD void carve(double *b, int) {
         SR = b + O_SR;
         Z = b + O_Z, PI = b + O_PI, LAM = b + O_LAM, BD = b + O_BD;
@@ -214,6 +240,7 @@ struct Work {
         DV = b + O_DV, DLAM = b + O_DLAM, DT = b + O_DT;
         RG = b + O_RG, RD = b + O_RD, RM = b + O_RM, RMB = b + O_RMB;
         PP = b + O_PP, WDYN = b + O_WDYN, WB = b + O_WB, ZT = b + O_ZT, MF = b + O_MF, NNA = b + O_NNA;
+        ROW = b + TOTAL;
     }
 };
 
@@ -248,11 +275,9 @@ template <int NQ>
 struct alignas(16) SmemMpc {
     using D = Dim<NQ>;
     double Wz[D::NZ], WzN[D::NX], yref[D::NZ], yrefN[D::NX];
-    double gc[D::NX], gx[D::NX], nnio[2 * D::NX + 2];
-    double gh, lgd, ugd;            // h(x_N) at the NLP iterate, bounds of the step
-    double LAMG[2], lamg[2], tg[2], rdg[2], rmg[2], wGm[2];  // NLP / QP multipliers, slacks, residuals, merit weights
-    double wg, barg, q1g, q2g;      // barrier Hessian weight and gradient pieces of the row
+    double gc[D::NX], gx[D::NX], nnio[2 * D::NX + 2];  // scratch of the margin evaluation
     double lh, uh;
+    int soft;   // rows at every stage with slacks (Prob::rows_soft), else the hard terminal row
 };
 
 template <int NQ, int FAM>
@@ -275,6 +300,9 @@ struct WarpSolver {
         RING_INIT(ring, s.bar, RING_DEPTH);
     }
     static constexpr bool MPC = FAM == VBOC_FAMILY_MPC;
+    // row record of stage k (MPC family)
+    VB_DEV double *row(int k) const { return w.ROW + (size_t)k * RowF::SIZE; }
+    VB_DEV int row_first() const { return g->soft ? 0 : s.N; }  // first stage that carries a row
 
     // index of the (k, i, side) bound constraint in the constraint arrays (LAM, LAMQ, TQ, DLAM, DT, RD, RM, RMB, WB).
     // VB_PAIR_LAYOUT: the lower / upper entries of a component are adjacent, so both come with one 128-bit load.
@@ -384,14 +412,28 @@ struct WarpSolver {
             s.nact = (N + 1) * NZ - NU - nf0 - nfN;
             for (int i = 0; i < NQ; ++i) s.w[i] = (FAM == VBOC_FAMILY_VBOC) ? pb.p[i] : 0.0;
             if constexpr (MPC) {
-                s.nact += 1;  // the terminal constraint row: one more two-sided constraint
+                // hard terminal row: one more two-sided constraint; soft rows: per stage the row (two sides) and the two
+                // slack bounds, i.e. two two-sided constraints' worth
+                s.nact += pb.rows_soft ? 2 * (N + 1) : 1;
                 for (int i = 0; i < NZ; ++i) g->Wz[i] = pb.Wz[i], g->yref[i] = pb.yref[i];
                 for (int i = 0; i < NX; ++i) g->WzN[i] = pb.WzN[i], g->yrefN[i] = pb.yrefN[i];
-                g->lh = pb.lh, g->uh = pb.uh;
-                g->LAMG[0] = g->LAMG[1] = 0.0, g->wGm[0] = g->wGm[1] = 0.0;
+                g->lh = pb.lh, g->uh = pb.uh, g->soft = pb.rows_soft;
             }
         }
-        if constexpr (MPC) nn = pb.nn;
+        if constexpr (MPC) {
+            nn = pb.nn;
+            // acados reset(): zero row multipliers and slacks
+            for (int k = lane; k <= N; k += 32) {
+                double *rw = w.ROW + (size_t)k * RowF::SIZE;
+#pragma unroll 1
+                for (int j = 0; j < RowF::SIZE; ++j) rw[j] = 0.0;
+                rw[RowF::ON] = (pb.rows_soft || k == N) ? 1.0 : 0.0;
+                if (pb.rows_soft && pb.rowZ) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rw[RowF::ZS + j] = pb.rowZ[k * 4 + j];
+                }
+            }
+        }
         static_assert(TRI <= 64 && NZ <= 16, "triangle index table");
         for (int idx = lane; idx < TRI; idx += 32) {
             int a_ = 0;
@@ -452,7 +494,13 @@ struct WarpSolver {
         }
         if (lane == 0) *pb.st = st;
         if constexpr (MPC) {
-            if (pb.lamg_out && lane < 2) pb.lamg_out[lane] = g->LAMG[lane];
+            if (pb.lamg_out && lane < 2) pb.lamg_out[lane] = row(N)[RowF::LAMG + lane];
+            if (pb.rowm_out) {
+                for (int idx = lane; idx < (N + 1) * 6; idx += 32) {
+                    const int k = idx / 6, j = idx - k * 6;
+                    pb.rowm_out[idx] = row(k)[RowF::LAMG + j];  // LAMG[2], LAMS[2], SL[2] are adjacent
+                }
+            }
         }
         if (pb.pi_out) {
             for (int idx = lane; idx < N * NX; idx += 32) pb.pi_out[idx] = w.PI[idx];
@@ -498,26 +546,55 @@ struct WarpSolver {
         END_LANES
     }
 
-    // MPC family: h(x_N) and its gradient at the NLP iterate -> the row  lh - h <= gc' dx_N <= uh - h  of the QP
-    VB_DEV void linearize_terminal_constraint() {
+    // MPC family: h(x_k) and its gradient at the NLP iterate for every stage that carries a row -> the row
+    // lh - h <= gc' dx_k (+ sl) ,  gc' dx_k (- su) <= uh - h  of the QP
+    VB_DEV void linearize_rows() {
         if constexpr (MPC) {
             const int N = s.N;
-            FOR_LANES
-            if (lane < NX) g->gx[lane] = w.Z[N * NZ + NU + lane];
-            END_LANES
-            const double h = nn_margin<NQ>(*nn, g->gx, g->gc, w.NNA, w.NNA + NN_HMAX, g->nnio);
-            FOR_LANES
-            if (lane == 0) g->gh = h, g->lgd = g->lh - h, g->ugd = g->uh - h;
-            END_LANES
+#pragma unroll 1
+            for (int k = row_first(); k <= N; ++k) {
+                FOR_LANES
+                if (lane < NX) g->gx[lane] = w.Z[k * NZ + NU + lane];
+                END_LANES
+                const double h = nn_margin<NQ>(*nn, g->gx, g->gc, w.NNA, w.NNA + NN_HMAX, g->nnio);
+                FOR_LANES
+                double *rw = row(k);
+                if (lane < NX) rw[RowF::GC + lane] = g->gc[lane];
+                if (lane == 0) rw[RowF::GH] = h, rw[RowF::LGD] = g->lh - h, rw[RowF::UGD] = g->uh - h;
+                END_LANES
+            }
         }
     }
-    // h at the terminal state of a trial point (merit function)
-    VB_DEV double terminal_constraint_value(const double *Zs) {
-        const int N = s.N;
+    // h at stage k of a trial point (merit function)
+    VB_DEV double row_value(const double *Zs, int k) {
         FOR_LANES
-        if (lane < NX) g->gx[lane] = Zs[N * NZ + NU + lane];
+        if (lane < NX) g->gx[lane] = Zs[k * NZ + NU + lane];
         END_LANES
         return nn_margin<NQ>(*nn, g->gx, nullptr, w.NNA, w.NNA + NN_HMAX, g->nnio);
+    }
+    // cost of the slacks  sum_k 1/2 Z s^2 + z s ; trial: at the trial slacks of the line search (RowF::RD), else at SL
+    VB_DEV double slack_cost(bool trial) {
+        double c = 0.0;
+        if constexpr (MPC) {
+            if (g->soft) {
+                const int N = s.N;
+                LV(double, acc);
+                FOR_LANES
+                double a = 0.0;
+                for (int k = lane; k <= N; k += 32) {
+                    const double *rw = row(k);
+#pragma unroll
+                    for (int sd = 0; sd < 2; ++sd) {
+                        const double sv = trial ? rw[RowF::RD + sd] : rw[RowF::SL + sd];
+                        a += (0.5 * rw[RowF::ZS + sd] * sv + rw[RowF::ZS + 2 + sd]) * sv;
+                    }
+                }
+                L(acc) = a;
+                END_LANES
+                c = WARP_SUM(acc);
+            }
+        }
+        return c;
     }
 
     // ---------------------------------------------------------------- NLP residuals
@@ -545,7 +622,10 @@ struct WarpSolver {
                 }
                 if (k > 0 && i >= NU) r -= w.PI[(k - 1) * NX + i - NU];
                 if constexpr (MPC) {
-                    if (k == N && i >= NU) r += g->gc[i - NU] * (g->LAMG[1] - g->LAMG[0]);
+                    if (i >= NU) {
+                        const double *rw = row(k);
+                        if (rw[RowF::ON] != 0.0) r += rw[RowF::GC + i - NU] * (rw[RowF::LAMG + 1] - rw[RowF::LAMG]);
+                    }
                 }
                 if (active(k, i)) {
                     int sc = sclass(k);
@@ -572,10 +652,22 @@ struct WarpSolver {
             ve = fmax(ve, fabs(v));
         }
         if constexpr (MPC) {
-            if (lane == 0) {  // the terminal constraint row lh <= h(x_N) <= uh
-                const double fl = g->lh - g->gh, fu = g->gh - g->uh;
+            // the rows  lh <= h(x_k) + sl ,  h(x_k) - su <= uh ,  sl, su >= 0  and the stationarity of the slacks
+            for (int k = lane; k <= N; k += 32) {
+                const double *rw = row(k);
+                if (rw[RowF::ON] == 0.0) continue;
+                const double sl = rw[RowF::SL], su = rw[RowF::SL + 1];  // zero for hard rows
+                const double fl = g->lh - rw[RowF::GH] - sl, fu = rw[RowF::GH] - su - g->uh;
                 vi = fmax(vi, fmax(fl, fu));
-                vc = fmax(vc, fmax(fabs(g->LAMG[0] * fl), fabs(g->LAMG[1] * fu)));
+                vc = fmax(vc, fmax(fabs(rw[RowF::LAMG] * fl), fabs(rw[RowF::LAMG + 1] * fu)));
+                if (g->soft) {
+                    vi = fmax(vi, fmax(-sl, -su));
+                    vc = fmax(vc, fmax(fabs(rw[RowF::LAMS] * sl), fabs(rw[RowF::LAMS + 1] * su)));
+                    const double rsl = rw[RowF::ZS] * sl + rw[RowF::ZS + 2] - rw[RowF::LAMG] - rw[RowF::LAMS];
+                    const double rsu = rw[RowF::ZS + 1] * su + rw[RowF::ZS + 3] - rw[RowF::LAMG + 1] - rw[RowF::LAMS + 1];
+                    nb |= (rsl != rsl) | (rsu != rsu);
+                    vs = fmax(vs, fmax(fabs(rsl), fabs(rsu)));
+                }
             }
         }
         L(a_s) = vs, L(a_e) = ve, L(a_i) = vi, L(a_c) = vc, L(bad) = nb;
@@ -642,15 +734,26 @@ struct WarpSolver {
         if (lane < NX) w.DZ[NU + lane] -= s.vc[lane];
         END_LANES
         if constexpr (MPC) {
-            // HPIPM cold start of a general constraint: slack = distance to the bound at the initial step, not below thr0
-            double g0 = 0.0;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) g0 += g->gc[i] * w.DZ[N * NZ + NU + i];
-            UNIFORM_SYNC();
+            // HPIPM cold start of a general constraint: slack = distance to the bound at the initial step, not below
+            // thr0; a softening slack starts at its bound and is pushed inside by thr0 like a box-bounded variable
             FOR_LANES
-            if (lane < 2) {
-                const double t = fmax(lane == 0 ? g0 - g->lgd : g->ugd - g0, thr0);
-                g->tg[lane] = t, g->lamg[lane] = o.qp_mu0 / t;
+            for (int k = lane; k <= N; k += 32) {
+                double *rw = row(k);
+                if (rw[RowF::ON] == 0.0) continue;
+                double g0 = 0.0;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) g0 += rw[RowF::GC + i] * w.DZ[k * NZ + NU + i];
+                double sg = 0.0;
+                if (g->soft) {
+                    sg = thr0;
+                    rw[RowF::TQ + 2] = rw[RowF::TQ + 3] = thr0;
+                    rw[RowF::LQ + 2] = rw[RowF::LQ + 3] = o.qp_mu0 / thr0;
+                }
+                rw[RowF::SIG] = rw[RowF::SIG + 1] = sg;
+                rw[RowF::DSIG] = rw[RowF::DSIG + 1] = 0.0;
+                const double tl = fmax(g0 + sg - rw[RowF::LGD], thr0), tu = fmax(rw[RowF::UGD] - g0 + sg, thr0);
+                rw[RowF::TQ] = tl, rw[RowF::TQ + 1] = tu;
+                rw[RowF::LQ] = o.qp_mu0 / tl, rw[RowF::LQ + 1] = o.qp_mu0 / tu;
             }
             END_LANES
         }
@@ -672,46 +775,78 @@ struct WarpSolver {
         LV(double, a_mu);
         LV(int, bad);
         if constexpr (MPC) {
-            // the terminal constraint row first (uniform): its updated multipliers enter the stationarity residual of
-            // x_N in the flat loop below, its barrier terms the terminal value function of the backward sweep
-            double gq = 0.0, dvg = 0.0;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                const double dv = upd ? w.DV[N * NZ + NU + i] : 0.0;
-                gq += g->gc[i] * (w.DZ[N * NZ + NU + i] + as * dv);
-                dvg += g->gc[i] * dv;
-            }
-            double ll = g->lamg[0], lu = g->lamg[1], tl = g->tg[0], tu = g->tg[1];
-            if (upd) {
-                double rml = ll * tl, rmu = lu * tu;
-                if (umode == 1) rml += g->rmg[0] - usm, rmu += g->rmg[1] - usm;
-                if (umode == 2) rml -= usm, rmu -= usm;
-                const double dtl = dvg - g->rdg[0], dtu = -dvg - g->rdg[1];
-                const double dll = -(rml + ll * dtl) * VB_RCP(tl), dlu = -(rmu + lu * dtu) * VB_RCP(tu);
-                ll = fmax(ll + as * dll, o.qp_lam_min), lu = fmax(lu + as * dlu, o.qp_lam_min);
-                tl = fmax(tl + as * dtl, o.qp_t_min), tu = fmax(tu + as * dtu, o.qp_t_min);
-            }
-            const double dl = g->lgd - gq + tl, du = gq - g->ugd + tu, ml = ll * tl, mu_ = lu * tu;
-            const double itl = VB_RCP(tl), itu = VB_RCP(tu);
-            const double wg = ll * itl + lu * itu, barg = (ml - ll * dl) * itl - (mu_ - lu * du) * itu;
-            UNIFORM_SYNC();
+            // the rows first (lanes over the stages): their updated multipliers enter the stationarity residual of x_k in
+            // the flat loop below, their barrier terms (slacks eliminated) the stage Hessian of the
+            // backward sweep.  One-sided constraints of a row: 0 lower, 1 upper, 2 sl >= 0, 3 su >= 0.
             FOR_LANES
-            if (lane == 0) {
-                g->lamg[0] = ll, g->lamg[1] = lu, g->tg[0] = tl, g->tg[1] = tu;
-                g->rdg[0] = dl, g->rdg[1] = du, g->wg = wg, g->barg = barg;
+            double vg = 0, vd = 0, vm = 0, mu = 0;
+            int nb = 0;
+            const int nsd = g->soft ? 4 : 2;
+            for (int k = N - lane; k >= 0; k -= 32) {  // lane 0 takes the terminal row (summation order of the hard-row kernel)
+                double *rw = row(k);
+                if (rw[RowF::ON] == 0.0) continue;
+                double gq = 0.0, dvg = 0.0;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) {
+                    const double dv = upd ? w.DV[k * NZ + NU + i] : 0.0;
+                    gq += rw[RowF::GC + i] * (w.DZ[k * NZ + NU + i] + as * dv);
+                    dvg += rw[RowF::GC + i] * dv;
+                }
+                double lam[4], t[4], sg[2] = {rw[RowF::SIG], rw[RowF::SIG + 1]};
+#pragma unroll
+                for (int sd = 0; sd < 4; ++sd) lam[sd] = rw[RowF::LQ + sd], t[sd] = rw[RowF::TQ + sd];
+                if (upd) {
+                    // the steps of the accepted solve, recomputed as con_pass formed them
+                    const double dsl = rw[RowF::DSIG], dsu = rw[RowF::DSIG + 1];
+                    const double dtt[4] = {dvg + dsl - rw[RowF::RD], -dvg + dsu - rw[RowF::RD + 1], dsl - rw[RowF::RD + 2],
+                                           dsu - rw[RowF::RD + 3]};
+#pragma unroll
+                    for (int sd = 0; sd < 4; ++sd) {
+                        if (sd < nsd) {
+                            double rm = lam[sd] * t[sd];
+                            if (umode == 1) rm += rw[RowF::PR + sd] - usm;
+                            if (umode == 2) rm -= usm;
+                            const double dl = -(rm + lam[sd] * dtt[sd]) * VB_RCP(t[sd]);
+                            lam[sd] = fmax(lam[sd] + as * dl, o.qp_lam_min);
+                            t[sd] = fmax(t[sd] + as * dtt[sd], o.qp_t_min);
+                        }
+                    }
+                    sg[0] += as * dsl, sg[1] += as * dsu;
+                }
+                const double rd[4] = {rw[RowF::LGD] - gq - sg[0] + t[0], gq - rw[RowF::UGD] - sg[1] + t[1], -sg[0] + t[2],
+                                      -sg[1] + t[3]};
+                double wv[4] = {0, 0, 0, 0}, beta[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int sd = 0; sd < 4; ++sd) {
+                    if (sd < nsd) {
+                        const double m_ = lam[sd] * t[sd], it = VB_RCP(t[sd]);
+                        wv[sd] = lam[sd] * it, beta[sd] = (m_ - lam[sd] * rd[sd]) * it;
+                        nb |= (rd[sd] != rd[sd]) | (m_ != m_);
+                        vd = fmax(vd, fabs(rd[sd])), vm = fmax(vm, fabs(m_)), mu += m_;
+                        rw[RowF::LQ + sd] = lam[sd], rw[RowF::TQ + sd] = t[sd], rw[RowF::RD + sd] = rd[sd];
+                    }
+                }
+                double a1 = 1.0, a2 = 1.0, c3 = 0.0, c4 = 0.0, rsl = 0.0, rsu = 0.0;
+                if (g->soft) {
+                    rw[RowF::SIG] = sg[0], rw[RowF::SIG + 1] = sg[1];
+                    rsl = rw[RowF::ZS] * sg[0] + rw[RowF::ZS + 2] - lam[0] - lam[2];
+                    rsu = rw[RowF::ZS + 1] * sg[1] + rw[RowF::ZS + 3] - lam[1] - lam[3];
+                    nb |= (rsl != rsl) | (rsu != rsu);
+                    vg = fmax(vg, fmax(fabs(rsl), fabs(rsu)));
+                    const double iDl = 1.0 / (rw[RowF::ZS] + wv[0] + wv[2]), iDu = 1.0 / (rw[RowF::ZS + 1] + wv[1] + wv[3]);
+                    a1 = (rw[RowF::ZS] + wv[2]) * iDl, c3 = wv[0] * iDl;
+                    a2 = (rw[RowF::ZS + 1] + wv[3]) * iDu, c4 = wv[1] * iDu;
+                }
+                rw[RowF::WEFF] = wv[0] * a1 + wv[1] * a2;
+                rw[RowF::BARG] = (a1 * beta[0] - c3 * (rsl + beta[2])) - (a2 * beta[1] - c4 * (rsu + beta[3]));
             }
+            L(a_g) = vg, L(a_d) = vd, L(a_m) = vm, L(a_mu) = mu, L(bad) = nb;
             END_LANES
         }
         FOR_LANES
         double vg = 0, vd = 0, vm = 0, mu = 0;
         int nb = 0;
-        if constexpr (MPC) {
-            if (lane == 0) {
-                const double dl = g->rdg[0], du = g->rdg[1], ml = g->lamg[0] * g->tg[0], mu_ = g->lamg[1] * g->tg[1];
-                nb |= (dl != dl) | (du != du) | (ml != ml) | (mu_ != mu_);
-                vd = fmax(fabs(dl), fabs(du)), vm = fmax(fabs(ml), fabs(mu_)), mu = ml + mu_;
-            }
-        }
+        if constexpr (MPC) vg = L(a_g), vd = L(a_d), vm = L(a_m), mu = L(a_mu), nb = L(bad);
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             {
@@ -755,8 +890,15 @@ struct WarpSolver {
 #endif
             }
             if (k > 0 && i >= NU) r -= w.PIQ[(k - 1) * NX + i - NU];
+            const double *rw_ = nullptr;
             if constexpr (MPC) {
-                if (k == N && i >= NU) r += g->gc[i - NU] * (g->lamg[1] - g->lamg[0]);
+                if (i >= NU) {
+                    const double *rw = row(k);
+                    if (rw[RowF::ON] != 0.0) {
+                        rw_ = rw;
+                        r += rw[RowF::GC + i - NU] * (rw[RowF::LQ + 1] - rw[RowF::LQ]);
+                    }
+                }
             }
             const int c = CI(k, i, 0), cu = CI(k, i, 1);
             if (active(k, i)) {
@@ -827,7 +969,7 @@ struct WarpSolver {
             }
             if (VB_RG_ALL || k == 0) w.RG[idx] = r;  // only the stage-0 state part is read back (projection)
             if constexpr (MPC) {
-                if (k == N && i >= NU) bar += g->barg * g->gc[i - NU];
+                if (rw_) bar += rw_[RowF::BARG] * rw_[RowF::GC + i - NU];
             }
             rk[R::HH + i] = hh;
             rk[R::RR + i] = r + bar;
@@ -914,7 +1056,10 @@ struct WarpSolver {
 #pragma unroll
                     for (int j = 0; j < NX; ++j) {
                         double pv = (j == lane && !fx) ? hh : 0.0;
-                        if constexpr (MPC) pv += g->wg * g->gc[lane] * g->gc[j];  // barrier Hessian of the constraint row
+                        if constexpr (MPC) {  // barrier Hessian of the terminal row
+                            const double *rw = row(N);
+                            if (rw[RowF::ON] != 0.0) pv += rw[RowF::WEFF] * rw[RowF::GC + lane] * rw[RowF::GC + j];
+                        }
                         s.P[lane][j] = pv;
                     }
                 }
@@ -952,6 +1097,12 @@ struct WarpSolver {
                     // (row, column) of the idx-th entry of the row-major lower triangle, from the table
                     const int ab = s.tri[idx], a_ = ab >> 4, b_ = ab & 15;
                     double a = dotv<NX>(r + R::BAT + a_ * NX, &s.PBAT[b_][0], (a_ == b_) ? r[R::HH + a_] : 0.0);
+                    if constexpr (MPC) {  // barrier Hessian of this stage's row (rank one in the states)
+                        if (b_ >= NU) {
+                            const double *rw = row(k);
+                            if (rw[RowF::ON] != 0.0) a += rw[RowF::WEFF] * rw[RowF::GC + a_ - NU] * rw[RowF::GC + b_ - NU];
+                        }
+                    }
                     s.M[a_][b_] = a, s.M[b_][a_] = a;
                 }
             } else if (last) {
@@ -1360,29 +1511,57 @@ struct WarpSolver {
         FOR_LANES
         double al = 1.0, s0 = 0, s1 = 0, s2 = 0;
         if constexpr (MPC) {
-            if (lane == 0) {  // the terminal constraint row
-                double dvg = 0.0, q1g = 0.0, q2g = 0.0;
+            // the rows (lanes over the stages): slack steps from the eliminated slack equations, then the steps of the
+            // four (two, if hard) one-sided constraints like those of a bound
+            const int nsd = g->soft ? 4 : 2;
+            for (int k = N - lane; k >= 0; k -= 32) {
+                double *rw = row(k);
+                if (rw[RowF::ON] == 0.0) continue;
+                double dvg = 0.0;
 #pragma unroll
-                for (int i = 0; i < NX; ++i) dvg += g->gc[i] * w.DV[N * NZ + NU + i];
-#pragma unroll 1
-                for (int sd = 0; sd < 2; ++sd) {
-                    double lam = g->lamg[sd], t = g->tg[sd], rm = lam * t;
-                    if (mode == 1) rm += g->rmg[sd] - sm;
-                    if (mode == 2) rm -= sm;
-                    const double dtt = (sd ? -dvg : dvg) - g->rdg[sd];
-                    const double it = VB_RCP(t);
-                    const double dl = -(rm + lam * dtt) * it;
-                    if (dtt < 0.0 && t + al * dtt < 0.0) al = fmin(al, VB_RATIO(t, -dtt));
-                    if (dl < 0.0 && lam + al * dl < 0.0) al = fmin(al, VB_RATIO(lam, -dl));
-                    s0 += lam * t, s1 += lam * dtt + t * dl, s2 += dtt * dl;
-                    if (mode == 0) {
-                        const double pr = dtt * dl;
-                        g->rmg[sd] = pr;
-                        q1g += sd ? -pr * it : pr * it;
-                        q2g += sd ? -it : it;
+                for (int i = 0; i < NX; ++i) dvg += rw[RowF::GC + i] * w.DV[k * NZ + NU + i];
+                double lam[4], t[4], it[4] = {0, 0, 0, 0}, rm[4] = {0, 0, 0, 0}, wv[4] = {0, 0, 0, 0}, beta[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int sd = 0; sd < 4; ++sd) {
+                    lam[sd] = rw[RowF::LQ + sd], t[sd] = rw[RowF::TQ + sd];
+                    if (sd < nsd) {
+                        rm[sd] = lam[sd] * t[sd];
+                        if (mode == 1) rm[sd] += rw[RowF::PR + sd] - sm;
+                        if (mode == 2) rm[sd] -= sm;
+                        it[sd] = VB_RCP(t[sd]);
+                        wv[sd] = lam[sd] * it[sd], beta[sd] = (rm[sd] - lam[sd] * rw[RowF::RD + sd]) * it[sd];
                     }
                 }
-                if (mode == 0) g->q1g = q1g, g->q2g = q2g;
+                double dsl = 0.0, dsu = 0.0, a1 = 1.0, a2 = 1.0, c3 = 0.0, c4 = 0.0;
+                if (g->soft) {
+                    const double rsl = rw[RowF::ZS] * rw[RowF::SIG] + rw[RowF::ZS + 2] - lam[0] - lam[2];
+                    const double rsu = rw[RowF::ZS + 1] * rw[RowF::SIG + 1] + rw[RowF::ZS + 3] - lam[1] - lam[3];
+                    const double iDl = 1.0 / (rw[RowF::ZS] + wv[0] + wv[2]), iDu = 1.0 / (rw[RowF::ZS + 1] + wv[1] + wv[3]);
+                    dsl = -(rsl + beta[0] + beta[2] + wv[0] * dvg) * iDl;
+                    dsu = -(rsu + beta[1] + beta[3] - wv[1] * dvg) * iDu;
+                    a1 = (rw[RowF::ZS] + wv[2]) * iDl, c3 = wv[0] * iDl;
+                    a2 = (rw[RowF::ZS + 1] + wv[3]) * iDu, c4 = wv[1] * iDu;
+                }
+                rw[RowF::DSIG] = dsl, rw[RowF::DSIG + 1] = dsu;
+                const double dtt[4] = {dvg + dsl - rw[RowF::RD], -dvg + dsu - rw[RowF::RD + 1], dsl - rw[RowF::RD + 2],
+                                       dsu - rw[RowF::RD + 3]};
+                const double cf[4] = {a1, -a2, -c3, c4};  // how the four second-order / centering terms enter the x gradient
+                double q1g = 0.0, q2g = 0.0;
+#pragma unroll
+                for (int sd = 0; sd < 4; ++sd) {
+                    if (sd < nsd) {
+                        const double dl = -(rm[sd] + lam[sd] * dtt[sd]) * it[sd];
+                        if (dtt[sd] < 0.0 && t[sd] + al * dtt[sd] < 0.0) al = fmin(al, VB_RATIO(t[sd], -dtt[sd]));
+                        if (dl < 0.0 && lam[sd] + al * dl < 0.0) al = fmin(al, VB_RATIO(lam[sd], -dl));
+                        s0 += lam[sd] * t[sd], s1 += lam[sd] * dtt[sd] + t[sd] * dl, s2 += dtt[sd] * dl;
+                        if (mode == 0) {
+                            const double pr = dtt[sd] * dl;
+                            rw[RowF::PR + sd] = pr;
+                            q1g += cf[sd] * pr * it[sd], q2g += cf[sd] * it[sd];
+                        }
+                    }
+                }
+                if (mode == 0) rw[RowF::Q1G] = q1g, rw[RowF::Q2G] = q2g;
             }
         }
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
@@ -1458,11 +1637,15 @@ struct WarpSolver {
         S0 = WARP_SUM(a0), S1 = WARP_SUM(a1), S2 = WARP_SUM(a2);
         double alpha = WARP_MIN(amin);
         if constexpr (MPC) {
-            if (mode == 0) {  // the row's pieces of the corrector gradient act on x_N through its gradient
+            if (mode == 0) {  // the rows' pieces of the corrector gradient act on x_k through the row gradient
                 FOR_LANES
-                if (lane < NX) {
-                    rec(N)[R::Q1 + NU + lane] += g->gc[lane] * g->q1g;
-                    rec(N)[R::Q2 + NU + lane] += g->gc[lane] * g->q2g;
+                for (int idx = lane; idx < (N + 1) * NX; idx += 32) {
+                    const int k = idx / NX, i = idx - k * NX;
+                    const double *rw = row(k);
+                    if (rw[RowF::ON] != 0.0) {
+                        rec(k)[R::Q1 + NU + i] += rw[RowF::GC + i] * rw[RowF::Q1G];
+                        rec(k)[R::Q2 + NU + i] += rw[RowF::GC + i] * rw[RowF::Q2G];
+                    }
                 }
                 END_LANES
             }
@@ -1538,10 +1721,13 @@ struct WarpSolver {
                 } else {
                     a = s.hhN[mI] * dxn[mI] + s.rN[mI];
                     if constexpr (MPC) {
-                        double gd = 0.0;
+                        const double *rw = row(N);
+                        if (rw[RowF::ON] != 0.0) {
+                            double gd = 0.0;
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) gd += g->gc[j] * dxn[j];
-                        a += g->wg * g->gc[mI] * gd;
+                            for (int j = 0; j < NX; ++j) gd += rw[RowF::GC + j] * dxn[j];
+                            a += rw[RowF::WEFF] * rw[RowF::GC + mI] * gd;
+                        }
                     }
                 }
                 w.PIQ[idx] += as * a;
@@ -1558,6 +1744,10 @@ struct WarpSolver {
 #pragma unroll
             for (int m = 0; m < NX; ++m) a += col[m] * w.PIQ[m];
             if (active(0, NU + i)) a += w.LAMQ[CI(0, NU + i, 1)] - w.LAMQ[CI(0, NU + i, 0)];
+            if constexpr (MPC) {
+                const double *rw = row(0);
+                if (rw[RowF::ON] != 0.0) a += rw[RowF::GC + i] * (rw[RowF::LQ + 1] - rw[RowF::LQ]);
+            }
             s.va[i] = s.vb[i] = a;
             s.nuNq[i] = ((s.fixedN >> i) & 1)
                             ? w.PIQ[(N - 1) * NX + i] - cost_g(N, NU + i, w.Z[N * NZ + NU + i]) -
@@ -1640,9 +1830,17 @@ struct WarpSolver {
         END_LANES
         double m = WARP_SUM(acc) + total_cost(Zs);
         if constexpr (MPC) {
-            const double h = terminal_constraint_value(Zs);
-            if (g->lh - h > 0.0) m += g->wGm[0] * (g->lh - h);
-            if (h - g->uh > 0.0) m += g->wGm[1] * (h - g->uh);
+            // rows at the trial point: violation against the trial slacks (RowF::RD, set by line_search) and the
+            // slacks' own cost; the trial slacks are convex combinations of non-negative values
+            m += slack_cost(true);
+#pragma unroll 1
+            for (int k = row_first(); k <= N; ++k) {
+                const double h = row_value(Zs, k);
+                const double *rw = row(k);
+                const double fl = g->lh - h - rw[RowF::RD], fu = h - rw[RowF::RD + 1] - g->uh;
+                if (fl > 0.0) m += rw[RowF::WGM] * fl;
+                if (fu > 0.0) m += rw[RowF::WGM + 1] * fu;
+            }
         }
         FOR_LANES
         if (lane < NX) s.vb[lane] = Zs[NU + lane];
@@ -1674,9 +1872,11 @@ struct WarpSolver {
             s.wN[lane] = sqp_iter == 0 ? b : fmax(b, 0.5 * (s.wN[lane] + b));
         }
         if constexpr (MPC) {
-            if (lane < 2) {
-                const double a = fabs(g->lamg[lane]);
-                g->wGm[lane] = sqp_iter == 0 ? a : fmax(a, 0.5 * (g->wGm[lane] + a));
+            for (int idx = lane; idx < (N + 1) * 4; idx += 32) {
+                double *rw = row(idx >> 2);
+                const int sd = idx & 3;  // WGM[2] and WSM[2] are adjacent, like LQ[0..3]
+                const double a = fabs(rw[RowF::LQ + sd]);
+                rw[RowF::WGM + sd] = sqp_iter == 0 ? a : fmax(a, 0.5 * (rw[RowF::WGM + sd] + a));
             }
         }
         END_LANES
@@ -1686,6 +1886,13 @@ struct WarpSolver {
         for (int trial = -1;; ++trial) {
             FOR_LANES
             for (int idx = lane; idx < (N + 1) * NZ; idx += 32) w.ZT[idx] = w.Z[idx] + alpha * w.DZ[idx];
+            if constexpr (MPC) {
+                for (int idx = lane; idx < (N + 1) * 2; idx += 32) {  // trial slacks (the QP's SIG is the new slack VALUE)
+                    double *rw = row(idx >> 1);
+                    const int sd = idx & 1;
+                    rw[RowF::RD + sd] = rw[RowF::SL + sd] + alpha * (rw[RowF::SIG + sd] - rw[RowF::SL + sd]);
+                }
+            }
             END_LANES
             double m1 = merit(w.ZT);
             if (trial < 0) {
@@ -1711,7 +1918,7 @@ struct WarpSolver {
         const int maxit = mode == VBOC_MODE_RTI ? 1 : o.max_iter;
         for (int it = 0;; ++it) {
             linearize();
-            linearize_terminal_constraint();
+            linearize_rows();
             bool finite = nlp_residuals(st.res_stat, st.res_eq, st.res_ineq, st.res_comp);
             if (mode == VBOC_MODE_SQP || it > 0) {
                 if (!finite) {
@@ -1744,11 +1951,16 @@ struct WarpSolver {
             for (int idx = lane; idx < (N + 1) * NC; idx += 32)
                 w.LAM[idx] = (1.0 - alpha) * w.LAM[idx] + alpha * w.LAMQ[idx];
             if constexpr (MPC) {
-                if (lane < 2) g->LAMG[lane] = (1.0 - alpha) * g->LAMG[lane] + alpha * g->lamg[lane];
+                for (int idx = lane; idx < (N + 1) * 6; idx += 32) {
+                    double *rw = row(idx / 6);
+                    const int j = idx - (idx / 6) * 6;  // LAMG[2], LAMS[2] <- LQ[4]; SL[2] <- SIG[2]
+                    const double qv = j < 4 ? rw[RowF::LQ + j] : rw[RowF::SIG + j - 4];
+                    rw[RowF::LAMG + j] = (1.0 - alpha) * rw[RowF::LAMG + j] + alpha * qv;
+                }
             }
             END_LANES
         }
-        st.cost = total_cost(w.Z);
+        st.cost = total_cost(w.Z) + slack_cost(false);
         store_solution(pb, st);
     }
 };

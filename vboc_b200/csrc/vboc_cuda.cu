@@ -69,6 +69,9 @@ struct Batch {
     NnNet nn;
     double lh = 0.0, uh = 0.0;
     double *lamg_out = nullptr;
+    int rows_soft = 0;               // vboc_set_mpc_rows: the margin row at every stage, softened
+    const double *rowZ = nullptr;    // [batch][Nmax + 1][4] penalties (Zl, Zu, zl, zu)
+    double *rowm_out = nullptr;      // [batch][Nmax + 1][6] row multipliers and slacks
     // AL family: guess network evaluated in the kernel (vboc_set_guess_network) and the export of the computed guesses
     const GuessNet *gnn = nullptr;
     double *xg_out = nullptr;
@@ -195,6 +198,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) solve_mpc_kernel(const 
         pb.Wz = B.Wz, pb.WzN = B.WzN, pb.yref = B.yref + (size_t)b * nz, pb.yrefN = B.yrefN + (size_t)b * B.nxr;
         pb.nn = &net, pb.lh = B.lh, pb.uh = B.uh;
         pb.lamg_out = B.lamg_out ? B.lamg_out + 2 * (size_t)b : nullptr;
+        pb.rows_soft = B.rows_soft;
+        pb.rowZ = B.rowZ ? B.rowZ + (size_t)b * (B.Nmax + 1) * 4 : nullptr;
+        pb.rowm_out = B.rowm_out ? B.rowm_out + (size_t)b * (B.Nmax + 1) * 6 : nullptr;
         if (B.pi_out) {
             pb.pi_out = B.pi_out + (size_t)b * B.Nmax * 2 * NQ;
             pb.lam_out = B.lam_out + (size_t)b * (B.Nmax + 1) * 6 * NQ;
@@ -394,6 +400,8 @@ struct vboc_solver {
     double *dpi, *dlam;  // multiplier export, allocated by vboc_export_multipliers
     // MPC family (vboc_set_mpc / vboc_set_mpc_reference)
     double *dnn, *dWz, *dWzN, *dyref, *dyrefN, *dlamg;
+    double *drowZ, *drowm;  // soft rows (vboc_set_mpc_rows)
+    int rows_soft, rows_batch;
     NnNet nn;
     double mpc_lh, mpc_uh;
     int mpc_set, mpc_ref_batch;
@@ -570,6 +578,8 @@ static int solver_create_impl(vboc_solver *s, int n_dof, int family, int batch_c
     s->grid = need < max_grid ? need : max_grid;
     s->slots = s->grid * WARPS_PER_CTA;
     s->work_doubles = work_doubles_for(n_dof, N_max);
+    if (family == VBOC_FAMILY_MPC)  // + the row records of the margin constraint
+        s->work_doubles = n_dof == 2 ? Work<2>::doubles_rows(N_max) : Work<3>::doubles_rows(N_max);
     // kernel mapping: VBOC_KERNEL=lane selects one lane per OCP (ocp_lane.h), default one warp per OCP
     s->lane_kernel = 0;
     if (const char *e = getenv("VBOC_KERNEL")) s->lane_kernel = strcmp(e, "lane") == 0 && family != VBOC_FAMILY_MPC;
@@ -617,7 +627,7 @@ void vboc_destroy(vboc_solver *s) {
     void *ptrs[] = {s->dN,    s->dxg,   s->dug,  s->dp,   s->dlbx0, s->dubx0, s->dlbx,
                     s->dubx,  s->dlbxN, s->dubxN, s->dlbu, s->dubu,  s->ddir,  s->dh,
                     s->dx,    s->du,    s->dst,  s->dcounter, s->dwork, s->dpi, s->dlam,
-                    s->dnn,   s->dWz,   s->dWzN, s->dyref, s->dyrefN, s->dlamg, s->dgn,  s->dxg_out, s->dgnn};
+                    s->dnn,   s->dWz,   s->dWzN, s->dyref, s->dyrefN, s->dlamg, s->drowZ, s->drowm, s->dgn,  s->dxg_out, s->dgnn};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (s->dwork_free_dt) cudaFree(s->dwork_free_dt);
@@ -823,6 +833,9 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
             return fail(VBOC_ERR_ARG, "vboc_solve_resident: call vboc_set_mpc_reference for this batch (MPC family)");
         B.Wz = s->dWz, B.WzN = s->dWzN, B.yref = s->dyref, B.yrefN = s->dyrefN, B.nn = s->nn;
         B.lh = s->mpc_lh, B.uh = s->mpc_uh, B.lamg_out = s->dlamg;
+        if (s->rows_soft && s->rows_batch < s->batch)
+            return fail(VBOC_ERR_ARG, "vboc_solve_resident: call vboc_set_mpc_rows for this batch (soft rows are on)");
+        B.rows_soft = s->rows_soft, B.rowZ = s->rows_soft ? s->drowZ : nullptr, B.rowm_out = s->drowm;
         const int g4 = (s->batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const int grid = g4 < s->grid ? g4 : s->grid;
         if (s->n == 2) solve_mpc_kernel<2><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
@@ -913,6 +926,7 @@ int vboc_set_mpc(vboc_solver *s, int hidden, const float *W1, const float *b1, c
         CUDA_OK(cudaMalloc((void **)&s->dyref, (size_t)s->cap * nz * sizeof(double)));
         CUDA_OK(cudaMalloc((void **)&s->dyrefN, (size_t)s->cap * nx * sizeof(double)));
         CUDA_OK(cudaMalloc((void **)&s->dlamg, (size_t)s->cap * 2 * sizeof(double)));
+        CUDA_OK(cudaMalloc((void **)&s->drowm, (size_t)s->cap * (s->Nmax + 1) * 6 * sizeof(double)));
     }
     CUDA_OK(cudaMemcpy(s->dWz, wz.data(), nz * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(s->dWzN, wzN.data(), nx * sizeof(double), cudaMemcpyHostToDevice));
@@ -935,6 +949,31 @@ int vboc_set_mpc_reference(vboc_solver *s, int batch, const double *yref, const 
     if ((rc = h2d(s, s->dyrefN, yref_e, (size_t)batch * nx * sizeof(double)))) return rc;
     s->mpc_ref_batch = batch;
     return 0;
+}
+
+int vboc_set_mpc_rows(vboc_solver *s, int batch, const double *Z) {
+    if (!s || s->family != VBOC_FAMILY_MPC || !s->mpc_set) return fail(VBOC_ERR_ARG, "vboc_set_mpc_rows: call vboc_set_mpc first");
+    if (batch == 0) {  // back to the hard terminal row
+        s->rows_soft = 0;
+        return 0;
+    }
+    if (batch < 1 || batch > s->cap || !Z) return fail(VBOC_ERR_ARG, "vboc_set_mpc_rows: bad argument");
+    const size_t cnt = (size_t)batch * (s->Nmax + 1) * 4;
+    for (size_t i = 0; i < cnt; ++i)
+        if ((i & 3) < 2 && !(Z[i] >= 0.0)) return fail(VBOC_ERR_ARG, "vboc_set_mpc_rows: Zl, Zu must be >= 0");
+    CUDA_OK(cudaSetDevice(s->device));
+    if (!s->drowZ) CUDA_OK(cudaMalloc((void **)&s->drowZ, (size_t)s->cap * (s->Nmax + 1) * 4 * sizeof(double)));
+    int rc;
+    if ((rc = h2d(s, s->drowZ, Z, cnt * sizeof(double)))) return rc;
+    s->rows_soft = 1, s->rows_batch = batch;
+    return 0;
+}
+
+int vboc_download_mpc_rows(vboc_solver *s, double *rows) {
+    if (!s || !s->batch || s->family != VBOC_FAMILY_MPC || !rows || !s->drowm)
+        return fail(VBOC_ERR_ARG, "vboc_download_mpc_rows: bad argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    return d2h(s, rows, s->drowm, (size_t)s->batch * (s->Nmax + 1) * 6 * sizeof(double));
 }
 
 int vboc_download_mpc_multipliers(vboc_solver *s, double *lamg) {

@@ -125,6 +125,26 @@ class BatchSolver:
         yref, yref_e = _c(np.atleast_2d(yref)), _c(np.atleast_2d(yref_e))
         check(_lib.lib().vboc_set_mpc_reference(self._h, yref.shape[0], _dp(yref), _dp(yref_e)))
 
+    def set_mpc_rows(self, Z):
+        """Soft margin rows at every stage (the parallel / receding / soft_traj Safe-MPC variants): Z (B, N_max+1, 4) =
+        per problem and stage (Zl, Zu, zl, zu), or (B, N_max+1) = Zl only (the reference sets nothing else,
+        VBOC/Safe MPC/parallel/2dof_sym.py:44-50).  None: back to the hard terminal row."""
+        if Z is None:
+            check(_lib.lib().vboc_set_mpc_rows(self._h, 0, None))
+            return
+        Z = np.asarray(Z, dtype=np.float64)
+        if Z.ndim == 2:
+            Z = np.concatenate([Z[:, :, None], np.zeros(Z.shape + (3,))], axis=2)
+        assert Z.shape[1:] == (self.N_max + 1, 4), Z.shape
+        Z = _c(Z)
+        check(_lib.lib().vboc_set_mpc_rows(self._h, Z.shape[0], _dp(Z)))
+
+    def mpc_rows(self):
+        """(lam_l, lam_u, lam_sl, lam_su, sl, su) of every stage's margin row at the returned iterate, (B, N_max+1, 6)."""
+        rows = np.zeros((self._batch, self.N_max + 1, 6))
+        check(_lib.lib().vboc_download_mpc_rows(self._h, _dp(rows)))
+        return rows
+
     def mpc_multipliers(self):
         lamg = np.zeros((self._batch, 2))
         check(_lib.lib().vboc_download_mpc_multipliers(self._h, _dp(lamg)))

@@ -46,7 +46,8 @@ class _MpcSolverShim:
         self.yref = np.tile(owner.ocp.cost.yref, (N, 1))
         self.yref_e = owner.ocp.cost.yref_e.copy()
         self.x0 = np.zeros(nx)
-        self._sol = self._out = None
+        self.Zl = np.zeros(N + 1)    # cost_set(i, "Zl", ...) of the soft-row variants (zl = zu = Zu = 0 in the reference)
+        self._sol = self._out = self._rows = None
 
     def reset(self):
         self.x[:] = 0.0
@@ -71,6 +72,8 @@ class _MpcSolverShim:
             else:
                 self.o._W = d.copy()
             self._sol_dirty = True
+        elif field == "Zl" and self.o.SOFT_ROWS:
+            self.Zl[stage] = float(np.ravel(v)[0])
         else:
             raise NotImplementedError(f"cost_set(.., {field!r}, ..) is not part of this path")
 
@@ -91,6 +94,8 @@ class _MpcSolverShim:
             self._sol_dirty = False
         self._sol.set_opts(o.opts)
         self._sol.set_mpc_reference(self.yref[0], self.yref_e)
+        if o.SOFT_ROWS:
+            self._sol.set_mpc_rows(self.Zl[None, :])
         one = lambda a: np.ascontiguousarray(np.asarray(a, dtype=float)[None])
         lo = np.concatenate([[o.thetamin] * 2, [-o.dthetamax] * 2])
         hi = np.concatenate([[o.thetamax] * 2, [o.dthetamax] * 2])
@@ -100,9 +105,12 @@ class _MpcSolverShim:
         self._out = self._sol.solve(bp, MODE_RTI if o.ocp.solver_options.nlp_solver_type == "SQP_RTI" else MODE_SQP)
         self.x[:] = self._out["x"][0, :o.N + 1]
         self.u[:] = self._out["u"][0, :o.N]
+        self._rows = self._sol.mpc_rows()[0] if o.SOFT_ROWS else None
         return int(self._out["status"][0])
 
     def get(self, stage, field):
+        if field in ("sl", "su"):      # slacks of the softened margin row
+            return self._rows[stage, 4 + (field == "su")].reshape(1).copy()
         return (self.x if field == "x" else self.u)[stage].copy()
 
     def get_cost(self):
@@ -110,6 +118,10 @@ class _MpcSolverShim:
 
 
 class OCPdoublependulumINIT(OCPdoublependulum):
+    # False: hard terminal row (this module).  True (the subclasses under parallel/, receiding_hard_constraints/,
+    # soft_traj_constraints/): the row at every stage with slacks, penalties by cost_set(i, "Zl", ..)
+    SOFT_ROWS = False
+
     def __init__(self, regenerate, nn_params, mean, std, safety_margin):
         super().__init__()
         self.Tf = 0.01
@@ -127,7 +139,7 @@ class OCPdoublependulumINIT(OCPdoublependulum):
         self._mean, self._std = float(mean), float(std)
         # the hard-terminal-constraint class passes safety_margin but its constraint function does not use it
         # (`return out - vel_norm`, :258); the parallel class applies it (`out*(100-safety_margin)/100 - vel_norm`)
-        self._margin_pct = 0.0
+        self._margin_pct = float(safety_margin) if self.SOFT_ROWS else 0.0
         self.safety_margin = safety_margin
         self.opts = engine.default_opts("mpc")
         self.ocp = NS(dims=NS(N=self.N, nx=self.nx, nu=self.nu),
@@ -157,6 +169,8 @@ class OCPdoublependulumINIT(OCPdoublependulum):
         out = np.maximum(W1 @ out + b1, 0.)
         out = np.maximum(W2 @ out + b2, 0.)
         out = W3 @ out + b3
+        if self is not None and getattr(self, "SOFT_ROWS", False):   # the soft-row classes apply the margin (:264)
+            return float(np.ravel(out)[0] * (100 - safety_margin) / 100 - vel_norm)
         return float(np.ravel(out)[0] - vel_norm)
 
 

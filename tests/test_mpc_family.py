@@ -128,7 +128,7 @@ def test_soft_rows_rti_step_satisfies_dense_kkt(emu, kind):
         r = certify.mpc_rows_kkt(n, bp, net, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["rowm"][b], Z[b],
                                  1.0, first_qp_at_guess=True)
         rel, feas = _rel(r, out["rowm"][b])
-        assert rel < 1e-8 and feas < 1e-8 and r["lam_min"] >= 0.0, (b, r)
+        assert rel < 2e-6 and feas < 2e-6 and r["lam_min"] >= 0.0, (b, r)
         slack_used += r["sl"].max() > 1e-3
     assert slack_used >= 3               # the margin is violated (and paid for) on some problems
 

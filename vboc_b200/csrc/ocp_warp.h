@@ -743,17 +743,27 @@ struct WarpSolver {
                 double g0 = 0.0;
 #pragma unroll
                 for (int i = 0; i < NX; ++i) g0 += rw[RowF::GC + i] * w.DZ[k * NZ + NU + i];
-                double sg = 0.0;
-                if (g->soft) {
-                    sg = thr0;
-                    rw[RowF::TQ + 2] = rw[RowF::TQ + 3] = thr0;
-                    rw[RowF::LQ + 2] = rw[RowF::LQ + 3] = o.qp_mu0 / thr0;
-                }
-                rw[RowF::SIG] = rw[RowF::SIG + 1] = sg;
                 rw[RowF::DSIG] = rw[RowF::DSIG + 1] = 0.0;
-                const double tl = fmax(g0 + sg - rw[RowF::LGD], thr0), tu = fmax(rw[RowF::UGD] - g0 + sg, thr0);
-                rw[RowF::TQ] = tl, rw[RowF::TQ + 1] = tu;
-                rw[RowF::LQ] = o.qp_mu0 / tl, rw[RowF::LQ + 1] = o.qp_mu0 / tu;
+                if (g->soft) {
+                    // A softened row can always start strictly feasible: the slack absorbs the violation (not below thr0,
+                    // like a box-bounded variable at its bound).  The row multiplier starts where the slack's own
+                    // stationarity Z s + z - lam_row - lam_slack = 0 holds, so that a large penalty does not enter the
+                    // first Newton systems as a residual of size Z s (with Z ~ 1e6 ... 1e12 the IPM otherwise spends its
+                    // iterations growing that multiplier by a factor per step).
+                    const double viol[2] = {rw[RowF::LGD] - g0, g0 - rw[RowF::UGD]};
+#pragma unroll
+                    for (int sd = 0; sd < 2; ++sd) {
+                        const double sg = fmax(viol[sd] + thr0, thr0), t = sg - viol[sd];
+                        const double ls = o.qp_mu0 / sg;
+                        rw[RowF::SIG + sd] = sg, rw[RowF::TQ + sd] = t, rw[RowF::TQ + 2 + sd] = sg, rw[RowF::LQ + 2 + sd] = ls;
+                        rw[RowF::LQ + sd] = fmax(o.qp_mu0 / t, rw[RowF::ZS + sd] * sg + rw[RowF::ZS + 2 + sd] - ls);
+                    }
+                } else {
+                    rw[RowF::SIG] = rw[RowF::SIG + 1] = 0.0;
+                    const double tl = fmax(g0 - rw[RowF::LGD], thr0), tu = fmax(rw[RowF::UGD] - g0, thr0);
+                    rw[RowF::TQ] = tl, rw[RowF::TQ + 1] = tu;
+                    rw[RowF::LQ] = o.qp_mu0 / tl, rw[RowF::LQ + 1] = o.qp_mu0 / tu;
+                }
             }
             END_LANES
         }

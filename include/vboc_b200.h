@@ -179,6 +179,17 @@ int vboc_download_mpc_multipliers(vboc_solver *s, double *lamg);
 int vboc_set_mpc_rows(vboc_solver *s, int batch, const double *Z);
 int vboc_download_mpc_rows(vboc_solver *s, double *rows);
 /*
+ * Cartesian path constraint (VBOC/Cartesian constraints/doublependulum_class_fixedveldir.py:147-160, driven by
+ * VBOC/Cartesian constraints/vboc_multiprocessing.py): the VBOC OCP of the double pendulum with the nonlinear constraint
+ *     lh <= h(q_k) <= uh,  h(q) = (l1 sin q1 + l2 sin q2 - xc)^2 + (l1 cos q1 + l2 cos q2 - yc)^2   (con_h_expr, k = 0..N-1)
+ * -- the end effector stays outside the circle of radius sqrt(lh) around (xc, yc); the reference uses xc = 0,
+ * yc = -l1 - l2/2, lh = (l2/4)^2, uh = 1e6.  vboc_set_cartesian(s, 1, ...) on a VBOC-family handle with n = 2 switches the
+ * handle's solves to the kernel that carries one hard general row per stage (linearised every SQP iteration, its barrier
+ * term a rank-one update of the stage Hessian in the Riccati step, its violation in the merit function);
+ * vboc_set_cartesian(s, 0, ...) switches back.  vboc_download_mpc_rows then returns the row multipliers in columns 0:2.
+ */
+int vboc_set_cartesian(vboc_solver *s, int on, double xc, double yc, double lh, double uh);
+/*
  * AL family: `compute_problem_nnguess` (AL/triplependulum_class_al.py:171-201) with the guess network evaluated INSIDE the
  * solve kernel: a 2n-H-H-(N 2n) MLP (my_nn.py NeuralNetCLS, PyTorch nn.Linear layout, float32) predicts the state
  * trajectory of stages 1..N from the initial state, out = model((x0 - mean) / std) * std + mean; stage 0 takes x0.  After

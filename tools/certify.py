@@ -81,7 +81,17 @@ def rk4_jac(n, x, u, h):
 
 
 # ------------------------------------------------------------------------------------------------ KKT exit test
-def kkt_residuals(n, bp, x, u, pi, lam):
+def cartesian_h(q, xc, yc, l1=0.8, l2=0.8):
+    """Squared distance of the double pendulum's end effector from (xc, yc) and its gradient wrt (q1, q2):
+    VBOC/Cartesian constraints/doublependulum_class_fixedveldir.py:154-156.  q (..., 2)."""
+    ex = l1 * np.sin(q[..., 0]) + l2 * np.sin(q[..., 1]) - xc
+    ey = l1 * np.cos(q[..., 0]) + l2 * np.cos(q[..., 1]) - yc
+    g = np.stack([2 * l1 * (ex * np.cos(q[..., 0]) - ey * np.sin(q[..., 0])),
+                  2 * l2 * (ex * np.cos(q[..., 1]) - ey * np.sin(q[..., 1]))], axis=-1)
+    return ex ** 2 + ey ** 2, g
+
+
+def kkt_residuals(n, bp, x, u, pi, lam, cart=None):
     """acados' four SQP residuals of the VBOC-family NLP at (x, u, pi, lam), per problem.
 
     bp: the batched problem dict (reference-shaped, vboc_b200.problems); x (B, Nmax+1, 2n+1), u (B, Nmax, n),
@@ -89,7 +99,9 @@ def kkt_residuals(n, bp, x, u, pi, lam):
     gradient).  Multipliers of the other equalities the reference writes as lb == ub pairs / projector rows
     (fixed initial positions, (I - d d') v_0 = 0, v_N = 0) are free in sign, so the stationarity residual is
     measured on the complement of their normals.  Returns dict of (B,) arrays res_stat, res_eq, res_ineq,
-    res_comp, lam_min."""
+    res_comp, lam_min.
+    cart = dict(xc, yc, lh, uh, rowm (B, Nmax+1, 6)): the Cartesian path constraint lh <= h(q_k) <= uh at stages 0..N-1
+    (n = 2) with its multipliers rowm[..., 0:2] = (lower, upper), Lagrangian terms lam_l (lh - h) + lam_u (h - uh)."""
     B = x.shape[0]
     nx, nz = 2 * n, 3 * n
     Nv = np.asarray(bp["N"])
@@ -97,13 +109,14 @@ def kkt_residuals(n, bp, x, u, pi, lam):
     for N in np.unique(Nv):
         sel = np.where(Nv == N)[0]
         r = _kkt_fixed_horizon(n, int(N), {k: (np.asarray(v)[sel] if isinstance(v, np.ndarray) and v.shape[:1] == (B,) else v)
-                                            for k, v in bp.items()}, x[sel], u[sel], pi[sel], lam[sel])
+                                            for k, v in bp.items()}, x[sel], u[sel], pi[sel], lam[sel],
+                               None if cart is None else dict(cart, rowm=cart["rowm"][sel]))
         for k in out:
             out[k][sel] = r[k]
     return out
 
 
-def _kkt_fixed_horizon(n, N, bp, x, u, pi, lam):
+def _kkt_fixed_horizon(n, N, bp, x, u, pi, lam, cart=None):
     nx, nz = 2 * n, 3 * n
     B = x.shape[0]
     h = np.asarray(bp["lbx0"])[:, 2 * n]                      # the pinned dt
@@ -138,6 +151,14 @@ def _kkt_fixed_horizon(n, N, bp, x, u, pi, lam):
     r = g + np.where(ineq, lu - ll, 0.0)
     r[:, :N] += np.einsum("bkij,bki->bkj", BA, PI)
     r[:, 1:, n:] -= PI
+    if cart is not None:
+        hv, hg = cartesian_h(X[:, :N, :n], cart["xc"], cart["yc"])                      # (B, N), (B, N, 2)
+        l1, l2 = cart["rowm"][:, :N, 0], cart["rowm"][:, :N, 1]
+        r[:, :N, n:2 * n] += hg * (l2 - l1)[..., None]
+        rl, ru = cart["lh"] - hv, hv - cart["uh"]
+        res_ineq = np.maximum(res_ineq, np.maximum(np.maximum(rl, ru), 0.0).max(axis=1))
+        res_comp = np.maximum(res_comp, np.maximum(np.abs(l1 * rl), np.abs(l2 * ru)).max(axis=1))
+        lam_min = np.minimum(lam_min, np.minimum(l1, l2).min(axis=1))
     r = np.where(exists & ~fixed, r, 0.0)      # fixed components: free multiplier; u_N does not exist
     # stage 0: v_0 = alpha d  ->  only the component of the velocity gradient along d counts
     if bp.get("C0") is not None:

@@ -28,17 +28,27 @@ extern "C" void emu_set_guess_net(int on, int hidden, int n_out, const double *W
     g_gnn.W3T = W3T, g_gnn.b3 = b3, g_gnn.mean = mean, g_gnn.stdv = stdv;
 }
 
+// optional Cartesian path constraint of the VBOC family (n = 2): WarpSolver<2, VBOC_FAMILY_CART>, row export
+static bool g_cart_on = false;
+static double g_cart[4] = {0, 0, 0, 0};  // xc, yc, lh, uh
+static double *g_rowm = nullptr;
+extern "C" void emu_set_cartesian(int on, double xc, double yc, double lh, double uh, double *rowm) {
+    g_cart_on = on != 0, g_cart[0] = xc, g_cart[1] = yc, g_cart[2] = lh, g_cart[3] = uh, g_rowm = rowm;
+}
+
 template <int NQ, int FAM>
 static void run(int mode, int batch, int Nmax, const int *N, const double *xg, const double *ug,
                 const double *p, const double *lbx0, const double *ubx0, const double *lbx,
                 const double *ubx, const double *lbxN, const double *ubxN, const double *lbu,
                 const double *ubu, const double *dir, const double *h, const vboc_opts *o, double *x,
                 double *u, vboc_stats *st) {
-    const int nxr = 2 * NQ + (FAM == VBOC_FAMILY_VBOC), nu = NQ;
+    constexpr bool VB = FAM == VBOC_FAMILY_VBOC || FAM == VBOC_FAMILY_CART;
+    const int nxr = 2 * NQ + VB, nu = NQ;
 #pragma omp parallel
     {
-        std::vector<double> buf(Work<NQ>::doubles(Nmax));
+        std::vector<double> buf(Work<NQ>::doubles_rows(Nmax));
         Smem<NQ> *sm = new Smem<NQ>();
+        SmemMpc<NQ> *gm = new SmemMpc<NQ>();
 #pragma omp for schedule(dynamic, 1)
         for (int b = 0; b < batch; ++b) {
             Work<NQ> w;
@@ -60,10 +70,15 @@ static void run(int mode, int batch, int Nmax, const int *N, const double *xg, c
                 pb.gnn = &g_gnn;
                 pb.xg_out = g_xg_out ? g_xg_out + (size_t)b * (Nmax + 1) * nxr : nullptr;
             }
-            WarpSolver<NQ, FAM> sol(*sm, w, *o);
+            if constexpr (FAM == VBOC_FAMILY_CART) {
+                pb.cart_xc = g_cart[0], pb.cart_yc = g_cart[1], pb.lh = g_cart[2], pb.uh = g_cart[3];
+                pb.rowm_out = g_rowm ? g_rowm + (size_t)b * (Nmax + 1) * 6 : nullptr;
+            }
+            WarpSolver<NQ, FAM> sol(*sm, w, *o, gm);
             sol.solve(pb, mode);
         }
         delete sm;
+        delete gm;
     }
 }
 
@@ -147,6 +162,11 @@ extern "C" int emu_solve_batch(int n, int family, int mode, int batch, int Nmax,
         run<NQ, FAM>(mode, batch, Nmax, N, xg, ug, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu, ubu, \
                      dir, h, o, x, u, st);                                                       \
         return 0;                                                                                \
+    }
+    if (g_cart_on) {
+        if (n != 2 || family != VBOC_FAMILY_VBOC) return -1;
+        run<2, VBOC_FAMILY_CART>(mode, batch, Nmax, N, xg, ug, p, lbx0, ubx0, lbx, ubx, lbxN, ubxN, lbu, ubu, dir, h, o, x, u, st);
+        return 0;
     }
     GO(1, 0) GO(2, 0) GO(3, 0) GO(1, 1) GO(2, 1) GO(3, 1)
 #undef GO

@@ -39,9 +39,11 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False, guess_net=None):
+def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False, guess_net=None, cartesian=None):
     """guess_net (AL family): dict(W1, b1, W2, b2, W3, b3, mean, std) -> the guess network is evaluated by the solver
-    itself (compute_problem_nnguess); the result then carries the computed guesses as `x_guess`."""
+    itself (compute_problem_nnguess); the result then carries the computed guesses as `x_guess`.
+    cartesian (VBOC family, n = 2): (xc, yc, lh, uh) -> the Cartesian path constraint at stages 0..N-1; the result then
+    carries `rowm` (B, Nmax+1, 6), the row multipliers in columns 0:2."""
     lib = C.CDLL(build() if not os.path.exists(os.path.join(_HERE, "libemu.so")) else os.path.join(_HERE, "libemu.so"))
     c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
     xg, ug = c(bp["x_guess"]), c(bp["u_guess"])
@@ -62,6 +64,11 @@ def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False, gue
         assert kernel == "warp"
         pi, lam = np.zeros((B, Nmax, 2 * n)), np.zeros((B, Nmax + 1, 3 * n, 2))
         lib.emu_set_multiplier_out(_p(pi), _p(lam))
+    rowm = None
+    if cartesian is not None:
+        assert kernel == "warp" and family == 0 and n == 2
+        rowm = np.zeros((B, Nmax + 1, 6))
+        lib.emu_set_cartesian(1, *[C.c_double(float(v)) for v in cartesian], _p(rowm))
     xg_out = None
     if guess_net is not None:
         assert kernel == "warp" and family == 1
@@ -75,10 +82,12 @@ def solve_batch(n, family, mode, bp, opts, kernel="warp", multipliers=False, gue
                         *[_p(a) for a in keep], _p(d), _p(h), C.byref(opts), _p(x), _p(u), st)
     if multipliers:
         lib.emu_set_multiplier_out(None, None)
+    if cartesian is not None:
+        lib.emu_set_cartesian(0, C.c_double(0.0), C.c_double(0.0), C.c_double(0.0), C.c_double(0.0), None)
     if guess_net is not None:
         lib.emu_set_guess_net(0, 0, 0, None, None, None, None, None, None, C.c_double(0.0), C.c_double(1.0), None)
     f = lambda name: np.array([getattr(s_, name) for s_ in st])
-    return dict(x_guess=xg_out, pi=pi, lam=lam, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),
+    return dict(rowm=rowm, x_guess=xg_out, pi=pi, lam=lam, status=f("status"), x=x, u=u, cost=f("cost"), sqp_iter=f("sqp_iter"), qp_iter=f("qp_iter"),
                 ls_evals=f("ls_evals"), qp_status=f("qp_status"),
                 res=np.stack([f("res_stat"), f("res_eq"), f("res_ineq"), f("res_comp")], axis=1))
 

@@ -29,6 +29,11 @@
 
 namespace vboc {
 
+// Kernel-internal family: the VBOC OCP with the Cartesian path constraint of
+// VBOC/Cartesian constraints/doublependulum_class_fixedveldir.py:154-160 as a hard row at stages 0..N-1
+// (vboc_set_cartesian on a VBOC-family handle; n = 2)
+constexpr int VBOC_FAMILY_CART = 3;
+
 // one problem, reference-shaped device arrays
 struct Prob {
     int N;
@@ -56,6 +61,7 @@ struct Prob {
     // for all zero.  rows_soft = 0: the hard terminal row only.
     int rows_soft = 0;
     const double *rowZ = nullptr;
+    double cart_xc = 0.0, cart_yc = 0.0;  // CART: centre of the circle the end effector must stay outside of
     double *rowm_out = nullptr;  // [N+1][6] (lam_l, lam_u, lam_sl, lam_su, sl, su) of the rows at the returned iterate
     // AL family: the guess network evaluated inside the kernel (compute_problem_nnguess); the state guess is then
     // computed from the initial state instead of read from xg, and optionally exported (reference-shaped rows)
@@ -277,6 +283,7 @@ struct alignas(16) SmemMpc {
     double Wz[D::NZ], WzN[D::NX], yref[D::NZ], yrefN[D::NX];
     double gc[D::NX], gx[D::NX], nnio[2 * D::NX + 2];  // scratch of the margin evaluation
     double lh, uh;
+    double xc, yc;  // CART: circle centre
     int soft;   // rows at every stage with slacks (Prob::rows_soft), else the hard terminal row
 };
 
@@ -300,9 +307,13 @@ struct WarpSolver {
         RING_INIT(ring, s.bar, RING_DEPTH);
     }
     static constexpr bool MPC = FAM == VBOC_FAMILY_MPC;
+    static constexpr bool CART = FAM == VBOC_FAMILY_CART;
+    static constexpr bool ROWS = MPC || CART;               // families that carry general rows (RowF records)
+    static constexpr bool VBOCLIKE = FAM == VBOC_FAMILY_VBOC || CART;  // linear cost on v_0, dt eliminated
     // row record of stage k (MPC family)
     VB_DEV double *row(int k) const { return w.ROW + (size_t)k * RowF::SIZE; }
-    VB_DEV int row_first() const { return g->soft ? 0 : s.N; }  // first stage that carries a row
+    VB_DEV int row_first() const { return (CART || g->soft) ? 0 : s.N; }  // first / last stage that carries a row
+    VB_DEV int row_last() const { return CART ? s.N - 1 : s.N; }
 
     // index of the (k, i, side) bound constraint in the constraint arrays (LAM, LAMQ, TQ, DLAM, DT, RD, RM, RMB, WB).
     // VB_PAIR_LAYOUT: the lower / upper entries of a component are adjacent, so both come with one 128-bit load.
@@ -327,7 +338,7 @@ struct WarpSolver {
     // VBOC/triplependulum_class_vboc.py:82-87 + levenberg_marquardt; AL: LINEAR_LS on the
     // velocities, AL/triplependulum_class_al.py:98-115, Gauss-Newton)
     VB_DEV double cost_g(int k, int i, double zval) const {
-        if (FAM == VBOC_FAMILY_VBOC) return (k == 0 && i >= NU + NQ) ? s.w[i - NU - NQ] : 0.0;
+        if (VBOCLIKE) return (k == 0 && i >= NU + NQ) ? s.w[i - NU - NQ] : 0.0;
         if constexpr (MPC) {
             // LINEAR_LS, Gauss-Newton: the stage costs are scaled by the time step, the terminal one is not
             if (k < s.N) return s.h * g->Wz[i] * (zval - g->yref[i]);
@@ -386,7 +397,7 @@ struct WarpSolver {
         FOR_LANES
         if (lane == 0) {
             s.N = N, s.h = pb.h;
-            s.wtdt = (FAM == VBOC_FAMILY_VBOC) ? pb.wt * pb.h * N : 0.0;
+            s.wtdt = VBOCLIKE ? pb.wt * pb.h * N : 0.0;
             int f0 = 0, fN = 0;
             for (int i = 0; i < NX; ++i) {
                 bool a = pb.lbx0[i] == pb.ubx0[i], b = pb.lbxN[i] == pb.ubxN[i];
@@ -410,7 +421,7 @@ struct WarpSolver {
             for (int i = 0; i < NX; ++i) nf0 += (f0 >> i) & 1, nfN += (fN >> i) & 1;
             s.fixed0 = f0, s.fixedN = fN, s.termfix = nfN != 0;
             s.nact = (N + 1) * NZ - NU - nf0 - nfN;
-            for (int i = 0; i < NQ; ++i) s.w[i] = (FAM == VBOC_FAMILY_VBOC) ? pb.p[i] : 0.0;
+            for (int i = 0; i < NQ; ++i) s.w[i] = VBOCLIKE ? pb.p[i] : 0.0;
             if constexpr (MPC) {
                 // hard terminal row: one more two-sided constraint; soft rows: per stage the row (two sides) and the two
                 // slack bounds, i.e. two two-sided constraints' worth
@@ -419,15 +430,19 @@ struct WarpSolver {
                 for (int i = 0; i < NX; ++i) g->WzN[i] = pb.WzN[i], g->yrefN[i] = pb.yrefN[i];
                 g->lh = pb.lh, g->uh = pb.uh, g->soft = pb.rows_soft;
             }
+            if constexpr (CART) {
+                s.nact += N;  // one hard two-sided row per stage 0..N-1
+                g->lh = pb.lh, g->uh = pb.uh, g->soft = 0, g->xc = pb.cart_xc, g->yc = pb.cart_yc;
+            }
         }
-        if constexpr (MPC) {
-            nn = pb.nn;
+        if constexpr (ROWS) {
+            if constexpr (MPC) nn = pb.nn;
             // acados reset(): zero row multipliers and slacks
             for (int k = lane; k <= N; k += 32) {
                 double *rw = w.ROW + (size_t)k * RowF::SIZE;
 #pragma unroll 1
                 for (int j = 0; j < RowF::SIZE; ++j) rw[j] = 0.0;
-                rw[RowF::ON] = (pb.rows_soft || k == N) ? 1.0 : 0.0;
+                rw[RowF::ON] = (CART ? k < N : (pb.rows_soft || k == N)) ? 1.0 : 0.0;
                 if (pb.rows_soft && pb.rowZ) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) rw[RowF::ZS + j] = pb.rowZ[k * 4 + j];
@@ -493,7 +508,7 @@ struct WarpSolver {
             pb.u[idx] = w.Z[k * NZ + i];
         }
         if (lane == 0) *pb.st = st;
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             if (pb.lamg_out && lane < 2) pb.lamg_out[lane] = row(N)[RowF::LAMG + lane];
             if (pb.rowm_out) {
                 for (int idx = lane; idx < (N + 1) * 6; idx += 32) {
@@ -548,15 +563,38 @@ struct WarpSolver {
 
     // MPC family: h(x_k) and its gradient at the NLP iterate for every stage that carries a row -> the row
     // lh - h <= gc' dx_k (+ sl) ,  gc' dx_k (- su) <= uh - h  of the QP
-    VB_DEV void linearize_rows() {
+    // the row function h(x) and (grad != nullptr) its gradient: MPC the learned margin, CART the squared distance of
+    // the end effector from the circle centre, (l1 sin q1 + l2 sin q2 - xc)^2 + (l1 cos q1 + l2 cos q2 - yc)^2
+    // (VBOC/Cartesian constraints/doublependulum_class_fixedveldir.py:154-156).  x, grad in shared memory; uniform result.
+    VB_DEV double row_eval(const double *x, double *grad) {
         if constexpr (MPC) {
+            return nn_margin<NQ>(*nn, x, grad, w.NNA, w.NNA + NN_HMAX, g->nnio);
+        } else {
+            static_assert(!CART || NQ == 2, "the Cartesian constraint is the double pendulum's");
+            const double l1 = PendN::l, l2 = PendN::l;  // both links 0.8 m
+            double s1, c1, s2, c2;
+            sincos(x[0], &s1, &c1);
+            sincos(x[1], &s2, &c2);
+            const double ex = l1 * s1 + l2 * s2 - g->xc, ey = l1 * c1 + l2 * c2 - g->yc;
+            UNIFORM_SYNC();
+            if (grad) {
+                FOR_LANES
+                if (lane < NX) grad[lane] = lane == 0 ? 2.0 * l1 * (ex * c1 - ey * s1) : (lane == 1 ? 2.0 * l2 * (ex * c2 - ey * s2) : 0.0);
+                END_LANES
+            }
+            return ex * ex + ey * ey;
+        }
+    }
+    VB_DEV void linearize_rows() {
+        if constexpr (ROWS) {
             const int N = s.N;
+            (void)N;
 #pragma unroll 1
-            for (int k = row_first(); k <= N; ++k) {
+            for (int k = row_first(); k <= row_last(); ++k) {
                 FOR_LANES
                 if (lane < NX) g->gx[lane] = w.Z[k * NZ + NU + lane];
                 END_LANES
-                const double h = nn_margin<NQ>(*nn, g->gx, g->gc, w.NNA, w.NNA + NN_HMAX, g->nnio);
+                const double h = row_eval(g->gx, g->gc);
                 FOR_LANES
                 double *rw = row(k);
                 if (lane < NX) rw[RowF::GC + lane] = g->gc[lane];
@@ -570,12 +608,12 @@ struct WarpSolver {
         FOR_LANES
         if (lane < NX) g->gx[lane] = Zs[k * NZ + NU + lane];
         END_LANES
-        return nn_margin<NQ>(*nn, g->gx, nullptr, w.NNA, w.NNA + NN_HMAX, g->nnio);
+        return row_eval(g->gx, nullptr);
     }
     // cost of the slacks  sum_k 1/2 Z s^2 + z s ; trial: at the trial slacks of the line search (RowF::RD), else at SL
     VB_DEV double slack_cost(bool trial) {
         double c = 0.0;
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             if (g->soft) {
                 const int N = s.N;
                 LV(double, acc);
@@ -621,7 +659,7 @@ struct WarpSolver {
                     for (int m = 0; m < NX; ++m) r += col[m] * pi[m];
                 }
                 if (k > 0 && i >= NU) r -= w.PI[(k - 1) * NX + i - NU];
-                if constexpr (MPC) {
+                if constexpr (ROWS) {
                     if (i >= NU) {
                         const double *rw = row(k);
                         if (rw[RowF::ON] != 0.0) r += rw[RowF::GC + i - NU] * (rw[RowF::LAMG + 1] - rw[RowF::LAMG]);
@@ -651,7 +689,7 @@ struct WarpSolver {
             nb |= (v != v);
             ve = fmax(ve, fabs(v));
         }
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             // the rows  lh <= h(x_k) + sl ,  h(x_k) - su <= uh ,  sl, su >= 0  and the stationarity of the slacks
             for (int k = lane; k <= N; k += 32) {
                 const double *rw = row(k);
@@ -733,7 +771,7 @@ struct WarpSolver {
         FOR_LANES
         if (lane < NX) w.DZ[NU + lane] -= s.vc[lane];
         END_LANES
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             // HPIPM cold start of a general constraint: slack = distance to the bound at the initial step, not below
             // thr0; a softening slack starts at its bound and is pushed inside by thr0 like a box-bounded variable
             FOR_LANES
@@ -784,7 +822,7 @@ struct WarpSolver {
         LV(double, a_m);
         LV(double, a_mu);
         LV(int, bad);
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             // the rows first (lanes over the stages): their updated multipliers enter the stationarity residual of x_k in
             // the flat loop below, their barrier terms (slacks eliminated) the stage Hessian of the
             // backward sweep.  One-sided constraints of a row: 0 lower, 1 upper, 2 sl >= 0, 3 su >= 0.
@@ -856,7 +894,7 @@ struct WarpSolver {
         FOR_LANES
         double vg = 0, vd = 0, vm = 0, mu = 0;
         int nb = 0;
-        if constexpr (MPC) vg = L(a_g), vd = L(a_d), vm = L(a_m), mu = L(a_mu), nb = L(bad);
+        if constexpr (ROWS) vg = L(a_g), vd = L(a_d), vm = L(a_m), mu = L(a_mu), nb = L(bad);
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             {
@@ -901,7 +939,7 @@ struct WarpSolver {
             }
             if (k > 0 && i >= NU) r -= w.PIQ[(k - 1) * NX + i - NU];
             const double *rw_ = nullptr;
-            if constexpr (MPC) {
+            if constexpr (ROWS) {
                 if (i >= NU) {
                     const double *rw = row(k);
                     if (rw[RowF::ON] != 0.0) {
@@ -978,7 +1016,7 @@ struct WarpSolver {
                 if (k == N) r = 0.0;
             }
             if (VB_RG_ALL || k == 0) w.RG[idx] = r;  // only the stage-0 state part is read back (projection)
-            if constexpr (MPC) {
+            if constexpr (ROWS) {
                 if (rw_) bar += rw_[RowF::BARG] * rw_[RowF::GC + i - NU];
             }
             rk[R::HH + i] = hh;
@@ -1066,7 +1104,7 @@ struct WarpSolver {
 #pragma unroll
                     for (int j = 0; j < NX; ++j) {
                         double pv = (j == lane && !fx) ? hh : 0.0;
-                        if constexpr (MPC) {  // barrier Hessian of the terminal row
+                        if constexpr (ROWS) {  // barrier Hessian of the terminal row
                             const double *rw = row(N);
                             if (rw[RowF::ON] != 0.0) pv += rw[RowF::WEFF] * rw[RowF::GC + lane] * rw[RowF::GC + j];
                         }
@@ -1107,7 +1145,7 @@ struct WarpSolver {
                     // (row, column) of the idx-th entry of the row-major lower triangle, from the table
                     const int ab = s.tri[idx], a_ = ab >> 4, b_ = ab & 15;
                     double a = dotv<NX>(r + R::BAT + a_ * NX, &s.PBAT[b_][0], (a_ == b_) ? r[R::HH + a_] : 0.0);
-                    if constexpr (MPC) {  // barrier Hessian of this stage's row (rank one in the states)
+                    if constexpr (ROWS) {  // barrier Hessian of this stage's row (rank one in the states)
                         if (b_ >= NU) {
                             const double *rw = row(k);
                             if (rw[RowF::ON] != 0.0) a += rw[RowF::WEFF] * rw[RowF::GC + a_ - NU] * rw[RowF::GC + b_ - NU];
@@ -1520,7 +1558,7 @@ struct WarpSolver {
         LV(double, a2);
         FOR_LANES
         double al = 1.0, s0 = 0, s1 = 0, s2 = 0;
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             // the rows (lanes over the stages): slack steps from the eliminated slack equations, then the steps of the
             // four (two, if hard) one-sided constraints like those of a bound
             const int nsd = g->soft ? 4 : 2;
@@ -1646,7 +1684,7 @@ struct WarpSolver {
         END_LANES
         S0 = WARP_SUM(a0), S1 = WARP_SUM(a1), S2 = WARP_SUM(a2);
         double alpha = WARP_MIN(amin);
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             if (mode == 0) {  // the rows' pieces of the corrector gradient act on x_k through the row gradient
                 FOR_LANES
                 for (int idx = lane; idx < (N + 1) * NX; idx += 32) {
@@ -1730,7 +1768,7 @@ struct WarpSolver {
                     a = s.nuv[mI];
                 } else {
                     a = s.hhN[mI] * dxn[mI] + s.rN[mI];
-                    if constexpr (MPC) {
+                    if constexpr (ROWS) {
                         const double *rw = row(N);
                         if (rw[RowF::ON] != 0.0) {
                             double gd = 0.0;
@@ -1754,7 +1792,7 @@ struct WarpSolver {
 #pragma unroll
             for (int m = 0; m < NX; ++m) a += col[m] * w.PIQ[m];
             if (active(0, NU + i)) a += w.LAMQ[CI(0, NU + i, 1)] - w.LAMQ[CI(0, NU + i, 0)];
-            if constexpr (MPC) {
+            if constexpr (ROWS) {
                 const double *rw = row(0);
                 if (rw[RowF::ON] != 0.0) a += rw[RowF::GC + i] * (rw[RowF::LQ + 1] - rw[RowF::LQ]);
             }
@@ -1778,7 +1816,7 @@ struct WarpSolver {
     // ---------------------------------------------------------------- merit function
     VB_DEV double total_cost(const double *Zs) {
         const int N = s.N;
-        if (FAM == VBOC_FAMILY_VBOC) {
+        if (VBOCLIKE) {
             double c = s.wtdt;
 #pragma unroll
             for (int i = 0; i < NQ; ++i) c += s.w[i] * Zs[NU + NQ + i];
@@ -1839,12 +1877,12 @@ struct WarpSolver {
         L(acc) = a;
         END_LANES
         double m = WARP_SUM(acc) + total_cost(Zs);
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             // rows at the trial point: violation against the trial slacks (RowF::RD, set by line_search) and the
             // slacks' own cost; the trial slacks are convex combinations of non-negative values
             m += slack_cost(true);
 #pragma unroll 1
-            for (int k = row_first(); k <= N; ++k) {
+            for (int k = row_first(); k <= row_last(); ++k) {
                 const double h = row_value(Zs, k);
                 const double *rw = row(k);
                 const double fl = g->lh - h - rw[RowF::RD], fu = h - rw[RowF::RD + 1] - g->uh;
@@ -1881,7 +1919,7 @@ struct WarpSolver {
             s.w0[lane] = sqp_iter == 0 ? a : fmax(a, 0.5 * (s.w0[lane] + a));
             s.wN[lane] = sqp_iter == 0 ? b : fmax(b, 0.5 * (s.wN[lane] + b));
         }
-        if constexpr (MPC) {
+        if constexpr (ROWS) {
             for (int idx = lane; idx < (N + 1) * 4; idx += 32) {
                 double *rw = row(idx >> 2);
                 const int sd = idx & 3;  // WGM[2] and WSM[2] are adjacent, like LQ[0..3]
@@ -1896,7 +1934,7 @@ struct WarpSolver {
         for (int trial = -1;; ++trial) {
             FOR_LANES
             for (int idx = lane; idx < (N + 1) * NZ; idx += 32) w.ZT[idx] = w.Z[idx] + alpha * w.DZ[idx];
-            if constexpr (MPC) {
+            if constexpr (ROWS) {
                 for (int idx = lane; idx < (N + 1) * 2; idx += 32) {  // trial slacks (the QP's SIG is the new slack VALUE)
                     double *rw = row(idx >> 1);
                     const int sd = idx & 1;
@@ -1960,7 +1998,7 @@ struct WarpSolver {
                 w.PI[idx] = (1.0 - alpha) * w.PI[idx] + alpha * w.PIQ[idx];
             for (int idx = lane; idx < (N + 1) * NC; idx += 32)
                 w.LAM[idx] = (1.0 - alpha) * w.LAM[idx] + alpha * w.LAMQ[idx];
-            if constexpr (MPC) {
+            if constexpr (ROWS) {
                 for (int idx = lane; idx < (N + 1) * 6; idx += 32) {
                     double *rw = row(idx / 6);
                     const int j = idx - (idx / 6) * 6;  // LAMG[2], LAMS[2] <- LQ[4]; SL[2] <- SIG[2]

@@ -72,6 +72,7 @@ struct Batch {
     int rows_soft = 0;               // vboc_set_mpc_rows: the margin row at every stage, softened
     const double *rowZ = nullptr;    // [batch][Nmax + 1][4] penalties (Zl, Zu, zl, zu)
     double *rowm_out = nullptr;      // [batch][Nmax + 1][6] row multipliers and slacks
+    double cart_xc = 0.0, cart_yc = 0.0;  // vboc_set_cartesian (VBOC family, n = 2): circle centre; lh / uh above
     // AL family: guess network evaluated in the kernel (vboc_set_guess_network) and the export of the computed guesses
     const GuessNet *gnn = nullptr;
     double *xg_out = nullptr;
@@ -166,20 +167,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, VB_LB_MINB(MINB)) solve_ke
     }
 }
 
-// solve_mpc_kernel: solve_kernel for the MPC family: the same warp-per-OCP solver with the tracking
-// cost and the learned margin as a terminal constraint; every warp carries the extra SmemMpc block.
-template <int NQ>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) solve_mpc_kernel(const Batch B) {
+// solve_rows_kernel: solve_kernel for the families that carry general rows (RowF records behind the workspace, the extra
+// SmemMpc block per warp): FAM = VBOC_FAMILY_MPC (tracking cost + the learned margin as a hard terminal
+// row or as soft rows at every stage) and FAM = VBOC_FAMILY_CART (the VBOC OCP + the Cartesian path constraint).
+template <int NQ, int FAM>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) solve_rows_kernel(const Batch B) {
     __shared__ Smem<NQ> smem[WARPS_PER_CTA];
     __shared__ SmemMpc<NQ> mpc[WARPS_PER_CTA];
     __shared__ NnNet net;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * WARPS_PER_CTA + warp;
-    if (threadIdx.x == 0) net = B.nn;
-    __syncthreads();
+    if constexpr (FAM == VBOC_FAMILY_MPC) {
+        if (threadIdx.x == 0) net = B.nn;
+        __syncthreads();
+    }
     Work<NQ> w;
     w.carve(B.work + (size_t)slot * B.work_doubles, B.Nmax);
-    WarpSolver<NQ, VBOC_FAMILY_MPC> sol(smem[warp], w, B.opts, &mpc[warp]);
+    WarpSolver<NQ, FAM> sol(smem[warp], w, B.opts, &mpc[warp]);
     const int nu = NQ, nz = 3 * NQ;
     for (;;) {
         unsigned int b = 0;
@@ -195,11 +199,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) solve_mpc_kernel(const 
         pb.lbu = B.lbu + (size_t)b * nu, pb.ubu = B.ubu + (size_t)b * nu;
         pb.x = B.x + (size_t)b * (B.Nmax + 1) * B.nxr, pb.u = B.u + (size_t)b * B.Nmax * nu;
         pb.st = B.st + b;
-        pb.Wz = B.Wz, pb.WzN = B.WzN, pb.yref = B.yref + (size_t)b * nz, pb.yrefN = B.yrefN + (size_t)b * B.nxr;
-        pb.nn = &net, pb.lh = B.lh, pb.uh = B.uh;
-        pb.lamg_out = B.lamg_out ? B.lamg_out + 2 * (size_t)b : nullptr;
-        pb.rows_soft = B.rows_soft;
-        pb.rowZ = B.rowZ ? B.rowZ + (size_t)b * (B.Nmax + 1) * 4 : nullptr;
+        pb.lh = B.lh, pb.uh = B.uh;
+        if constexpr (FAM == VBOC_FAMILY_MPC) {
+            pb.Wz = B.Wz, pb.WzN = B.WzN, pb.yref = B.yref + (size_t)b * nz, pb.yrefN = B.yrefN + (size_t)b * B.nxr;
+            pb.nn = &net;
+            pb.lamg_out = B.lamg_out ? B.lamg_out + 2 * (size_t)b : nullptr;
+            pb.rows_soft = B.rows_soft;
+            pb.rowZ = B.rowZ ? B.rowZ + (size_t)b * (B.Nmax + 1) * 4 : nullptr;
+        } else {
+            pb.p = B.p + (size_t)b * (NQ + 1), pb.wt = pb.p[NQ];
+            pb.dir = B.dir ? B.dir + (size_t)b * NQ : nullptr;
+            pb.cart_xc = B.cart_xc, pb.cart_yc = B.cart_yc;
+        }
         pb.rowm_out = B.rowm_out ? B.rowm_out + (size_t)b * (B.Nmax + 1) * 6 : nullptr;
         if (B.pi_out) {
             pb.pi_out = B.pi_out + (size_t)b * B.Nmax * 2 * NQ;
@@ -402,6 +413,8 @@ struct vboc_solver {
     double *dnn, *dWz, *dWzN, *dyref, *dyrefN, *dlamg;
     double *drowZ, *drowm;  // soft rows (vboc_set_mpc_rows)
     int rows_soft, rows_batch;
+    int cart_on;            // vboc_set_cartesian (VBOC family, n = 2)
+    double cart_xc, cart_yc;
     NnNet nn;
     double mpc_lh, mpc_uh;
     int mpc_set, mpc_ref_batch;
@@ -838,8 +851,17 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
         B.rows_soft = s->rows_soft, B.rowZ = s->rows_soft ? s->drowZ : nullptr, B.rowm_out = s->drowm;
         const int g4 = (s->batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const int grid = g4 < s->grid ? g4 : s->grid;
-        if (s->n == 2) solve_mpc_kernel<2><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
-        else solve_mpc_kernel<3><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+        if (s->n == 2) solve_rows_kernel<2, VBOC_FAMILY_MPC><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+        else solve_rows_kernel<3, VBOC_FAMILY_MPC><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+        e = cudaGetLastError();
+#endif
+    } else if (s->cart_on) {
+#ifndef VB_TUNE_BUILD
+        if (s->free_dt || s->lane_kernel) return fail(VBOC_ERR_UNSUPPORTED, "Cartesian constraint: warp kernel, pinned dt only");
+        B.lh = s->mpc_lh, B.uh = s->mpc_uh, B.cart_xc = s->cart_xc, B.cart_yc = s->cart_yc, B.rowm_out = s->drowm;
+        const int g4 = (s->batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        const int grid = g4 < s->grid ? g4 : s->grid;
+        solve_rows_kernel<2, VBOC_FAMILY_CART><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
         e = cudaGetLastError();
 #endif
     } else if (s->free_dt) {
@@ -969,8 +991,31 @@ int vboc_set_mpc_rows(vboc_solver *s, int batch, const double *Z) {
     return 0;
 }
 
+int vboc_set_cartesian(vboc_solver *s, int on, double xc, double yc, double lh, double uh) {
+    if (!s || s->family != VBOC_FAMILY_VBOC || s->n != 2)
+        return fail(VBOC_ERR_ARG, "vboc_set_cartesian: a VBOC-family handle of the double pendulum is required");
+    if (s->lane_kernel) return fail(VBOC_ERR_UNSUPPORTED, "vboc_set_cartesian: served by the warp kernel only");
+    CUDA_OK(cudaSetDevice(s->device));
+    if (!on) {
+        s->cart_on = 0;
+        return 0;
+    }
+    if (!(lh <= uh)) return fail(VBOC_ERR_ARG, "vboc_set_cartesian: lh > uh");
+    const size_t need = Work<2>::doubles_rows(s->Nmax);
+    if (s->work_doubles < need) {  // the row records live behind every warp slot's workspace
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        cudaFree(s->dwork);
+        s->dwork = nullptr;
+        s->work_doubles = need;
+        CUDA_OK(cudaMalloc((void **)&s->dwork, (size_t)s->slots * s->work_doubles * sizeof(double)));
+    }
+    if (!s->drowm) CUDA_OK(cudaMalloc((void **)&s->drowm, (size_t)s->cap * (s->Nmax + 1) * 6 * sizeof(double)));
+    s->cart_on = 1, s->cart_xc = xc, s->cart_yc = yc, s->mpc_lh = lh, s->mpc_uh = uh;
+    return 0;
+}
+
 int vboc_download_mpc_rows(vboc_solver *s, double *rows) {
-    if (!s || !s->batch || s->family != VBOC_FAMILY_MPC || !rows || !s->drowm)
+    if (!s || !s->batch || (s->family != VBOC_FAMILY_MPC && !s->cart_on) || !rows || !s->drowm)
         return fail(VBOC_ERR_ARG, "vboc_download_mpc_rows: bad argument");
     CUDA_OK(cudaSetDevice(s->device));
     return d2h(s, rows, s->drowm, (size_t)s->batch * (s->Nmax + 1) * 6 * sizeof(double));

@@ -145,6 +145,12 @@ class BatchSolver:
         check(_lib.lib().vboc_download_mpc_rows(self._h, _dp(rows)))
         return rows
 
+    def set_cartesian(self, xc=0.0, yc=-1.2, radius=0.2, uh=1e6, on=True):
+        """VBOC family, n = 2: the end effector stays outside the circle of `radius` around (xc, yc) at stages 0..N-1
+        (VBOC/Cartesian constraints/doublependulum_class_fixedveldir.py:150-158: x_c = 0, y_c = -l1 - l2/2, radius = l2/4).
+        Row multipliers of a solve: mpc_rows()[..., 0:2]."""
+        check(_lib.lib().vboc_set_cartesian(self._h, int(on), float(xc), float(yc), float(radius) ** 2, float(uh)))
+
     def mpc_multipliers(self):
         lamg = np.zeros((self._batch, 2))
         check(_lib.lib().vboc_download_mpc_multipliers(self._h, _dp(lamg)))

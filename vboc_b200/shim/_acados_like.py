@@ -37,6 +37,7 @@ class OcpSolverShim:
         self.opts = engine.default_opts(family)
         self._sol = None
         self._out = None
+        self.cartesian = None   # dict(xc, yc, radius, uh): the Cartesian path constraint (VBOC family, n = 2)
 
     # -- acados API ----------------------------------------------------------------------------
     def reset(self):
@@ -101,6 +102,8 @@ class OcpSolverShim:
     def solve(self):
         if self._sol is None:
             self._sol = engine.BatchSolver(self.n, self.family, 1, N_MAX, device=self.device)
+            if self.cartesian is not None:
+                self._sol.set_cartesian(**self.cartesian)
         self._sol.set_opts(self.opts)
         self._out = self._sol.solve(self._problem(), MODE_RTI if self.mode == "SQP_RTI" else MODE_SQP)
         N = self.N

@@ -177,6 +177,10 @@ int vboc_download_mpc_multipliers(vboc_solver *s, double *lamg);
  * vboc_download_mpc_rows: rows [batch][N_max+1][6] = (lam_l, lam_u, lam_sl, lam_su, sl, su) at the returned iterate.
  */
 int vboc_set_mpc_rows(vboc_solver *s, int batch, const double *Z);
+/* vel_norm = |x[vstart:]| in the margin function (default vstart = n_dof: the velocities).  The triple-pendulum classes
+ * write `norm_2(x[2:])` like the double-pendulum ones (VBOC/Safe MPC/triplependulum_class_vboc.py:217, 282), which for
+ * n_dof = 3 includes theta_3; vstart = 2 reproduces their constraint function exactly.  Call after vboc_set_mpc. */
+int vboc_set_mpc_velnorm_start(vboc_solver *s, int vstart);
 int vboc_download_mpc_rows(vboc_solver *s, double *rows);
 /*
  * Cartesian path constraint (VBOC/Cartesian constraints/doublependulum_class_fixedveldir.py:147-160, driven by

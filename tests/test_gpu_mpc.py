@@ -215,3 +215,54 @@ def test_parallel_safe_mpc_class_like_the_driver():
         ocp.ocp_solver.cost_set(i, "Zl", 1e6 * np.ones((1,)))
     assert ocp.OCP_solve(x_bad, q_ref, np.full((ocp.N + 1, 4), x_bad), ug) == 0
     assert max(ocp.ocp_solver.get(i, "sl")[0] for i in range(ocp.N + 1)) > 1e-2
+
+
+def test_triple_pendulum_safe_mpc_classes_like_the_driver():
+    """VBOC/Safe MPC/soft_traj_constraints/3dof_sym.py:17-70, 102-116 and hard_terminal_constraints/3dof_sym.py: the
+    triple-pendulum classes (time_step 5e-3, tot_time 0.18 -> N = 36), Zl = 0 on the running stages and 1e6 on the
+    terminal one, OCP_solve(x0, guesses) in closed loop with the simulator; the tracking-only and hard-terminal classes
+    on the same state."""
+    import torch
+    from vboc_b200.shim.my_nn import NeuralNetDIR
+    from vboc_b200.shim.SafeMPC.triplependulum_class_vboc import (OCPtriplependulumHardTerm, OCPtriplependulumSoftTraj,
+                                                                   OCPtriplependulumSTD, SYMtriplependulum)
+    torch.manual_seed(0)
+    model = NeuralNetDIR(6, 500, 1)
+    with torch.no_grad():
+        model.linear_relu_stack[4].bias.fill_(8.0)
+    params = list(model.parameters())
+    mean, std, safety = 3.14, 0.45, 5.0
+    time_step, tot_time = 5e-3, 0.18
+    ocp = OCPtriplependulumSoftTraj("SQP_RTI", time_step, tot_time, params, mean, std, safety, True)
+    sim = SYMtriplependulum(time_step, tot_time, True)
+    N = ocp.ocp.dims.N
+    assert N == 36
+    for i in range(N):
+        ocp.ocp_solver.cost_set(i, "Zl", 0 * np.ones((1,)))
+    ocp.ocp_solver.cost_set(N, "Zl", 1e6 * np.ones((1,)))
+    x = np.array([3.0, 3.3, 3.2, 0.5, -0.5, 0.2])
+    xg = np.full((N + 1, 6), x)
+    ug = np.zeros((N, 3))
+    for step in range(4):
+        assert ocp.OCP_solve(x, xg, ug) == 0
+        xN = ocp.ocp_solver.get(N, "x")
+        # the terminal row: inside the set, or the violation is the (penalised) slack
+        h = ocp.nn_decisionfunction_conservative(params, mean, std, safety, xN)
+        assert h + ocp.ocp_solver.get(N, "sl")[0] >= -1e-4
+        u0 = ocp.ocp_solver.get(0, "u")
+        assert np.abs(u0).max() <= ocp.Cmax + 1e-9
+        for i in range(N - 1):
+            xg[i], ug[i] = ocp.ocp_solver.get(i + 1, "x"), ocp.ocp_solver.get(i + 1, "u")
+        xg[N - 1] = xg[N] = ocp.ocp_solver.get(N, "x")
+        sim.acados_integrator.set("u", u0)
+        sim.acados_integrator.set("x", x)
+        sim.acados_integrator.solve()
+        x = sim.acados_integrator.get("x")
+    x0 = np.array([3.0, 3.3, 3.2, 0.5, -0.5, 0.2])
+    std_ocp = OCPtriplependulumSTD("SQP_RTI", time_step, tot_time, True)
+    hard = OCPtriplependulumHardTerm("SQP_RTI", time_step, tot_time, params, mean, std, True)
+    g = np.full((N + 1, 6), x0)
+    assert std_ocp.OCP_solve(x0, g, np.zeros((N, 3))) == 0 and hard.OCP_solve(x0, g, np.zeros((N, 3))) == 0
+    assert hard.nn_decisionfunction(params, mean, std, hard.ocp_solver.get(N, "x")) >= -1e-6
+    # the margin is far from binding here (bias 8 against |x[2:]| ~ 3.3): both classes return the tracking solution
+    assert np.abs(hard.ocp_solver.get(0, "u") - std_ocp.ocp_solver.get(0, "u")).max() < 1e-6

@@ -168,3 +168,37 @@ def test_soft_rows_limits(emu):
     ok = (hard["status"] == 0) & (stiff["status"] == 0)
     assert ok.sum() >= 10
     assert np.abs(stiff["x"] - hard["x"])[ok].max() < 1e-5 and np.abs(stiff["u"] - hard["u"])[ok].max() < 1e-3
+
+
+def test_triple_pendulum_velnorm_over_x2(emu):
+    """The triple-pendulum Safe-MPC classes write vel_norm = norm_2(x[2:]) (VBOC/Safe MPC/triplependulum_class_vboc.py:217,
+    282), i.e. including theta_3: with vstart = 2 the engine's row is that function's linearisation (dense KKT with the
+    complex-step gradient of the numpy restatement), and the shim's numeric twin is the same expression."""
+    n, B, N = 3, 16, 10
+    net = make_net(n, 96, 1, 4.0)
+    net["vstart"] = 2
+    bp = pr.sample_mpc(n, B, seed=4)
+    Z = _row_penalties("soft_traj", B, N)
+    out = emu.solve_mpc(n, 1, bp, net, mpc_opts(emu), multipliers=True, rowZ=Z)
+    ok = np.where(out["status"] == 0)[0]
+    assert len(ok) >= 12
+    for b in ok:
+        r = certify.mpc_rows_kkt(n, bp, net, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["rowm"][b], Z[b],
+                                 1.0, first_qp_at_guess=True)
+        rel, feas = _rel(r, out["rowm"][b])
+        assert rel < 2e-6 and feas < 2e-6, (b, r)
+    wrong = dict(net, vstart=3)          # the certificate distinguishes the two expressions where the row is active
+    b = ok[np.argmax(out["rowm"][ok, :, 0].max(axis=1))]
+    assert out["rowm"][b, :, 0].max() > 1.0
+    r = certify.mpc_rows_kkt(n, bp, wrong, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["rowm"][b], Z[b], 1.0,
+                             first_qp_at_guess=True)
+    assert max(_rel(r, out["rowm"][b])) > 1e-4
+    from vboc_b200.shim.SafeMPC.triplependulum_class_vboc import OCPtriplependulumSoftTraj
+    params = [net[k] if k != "W3" else net[k][None, :] for k in ("W1", "b1", "W2", "b2", "W3")] + [np.array([net["b3"]])]
+    ocp = OCPtriplependulumSoftTraj("SQP_RTI", 5e-3, 0.18, params, net["mean"], net["std"], 5.0, True)
+    assert ocp.N == 36 and ocp.ocp.dims.N == 36 and ocp.SOFT_ROWS and callable(ocp.OCP_solve)
+    rng = np.random.default_rng(0)
+    for _ in range(10):
+        x = np.concatenate([rng.uniform(2.4, 3.9, 3), rng.uniform(-8, 8, 3)])
+        want = certify.nn_margin(dict(net, scale=0.95), x, 3)
+        assert abs(ocp.nn_decisionfunction_conservative(params, net["mean"], net["std"], 5.0, x) - want) < 1e-12

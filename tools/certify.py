@@ -285,7 +285,10 @@ def nn_margin(net, x, n):
     (VBOC/Safe MPC/hard_terminal_constraints/doublependulum_class_fixedveldir.py:232-258) in numpy, complex-step safe:
     h(x) = scale * MLP([(q - mean) / std, v / vn]) - vn,  vn = max(|v|, 1e-3), no ReLU on the output."""
     q, v = x[..., :n], x[..., n:]
-    vn = np.sqrt(np.sum(v * v, axis=-1))
+    # net["vstart"] (default n): vel_norm = norm_2(x[vstart:]).  The reference writes x[2:] for the double AND the triple
+    # pendulum (VBOC/Safe MPC/triplependulum_class_vboc.py:217), which for n = 3 includes theta_3; vstart = 2 mirrors that.
+    vs = x[..., int(net.get("vstart", n)):]
+    vn = np.sqrt(np.sum(vs * vs, axis=-1))
     vn = np.where(vn.real > 1e-3, vn, 1e-3)
     a = np.concatenate([(q - net["mean"]) / net["std"], v / vn[..., None]], axis=-1)
     a = a @ net["W1"].T + net["b1"]

@@ -251,13 +251,13 @@ extern "C" int emu_solve_mpc(int n, int mode, int batch, int Nmax, const int *N,
                              int hidden, const double *W1, const double *b1, const double *W2, const double *b2,
                              const double *W3, double b3, double mean, double stdv, double scale, double lh, double uh,
                              const vboc_opts *o, double *x, double *u, vboc_stats *st, double *lamg, int rows_soft,
-                             const double *rowZ, double *rowm) {
+                             const double *rowZ, double *rowm, int vstart) {
     std::vector<double> w2t((size_t)hidden * hidden);
     for (int j = 0; j < hidden; ++j)
         for (int k = 0; k < hidden; ++k) w2t[(size_t)k * hidden + j] = W2[(size_t)j * hidden + k];
     NnNet net;
     net.n_in = 2 * n, net.hidden = hidden, net.W1 = W1, net.b1 = b1, net.W2 = W2, net.W2T = w2t.data(), net.b2 = b2;
-    net.W3 = W3, net.b3 = b3, net.mean = mean, net.stdv = stdv, net.scale = scale;
+    net.W3 = W3, net.b3 = b3, net.mean = mean, net.stdv = stdv, net.scale = scale, net.vstart = vstart < 0 ? n : vstart;
     if (hidden > NN_HMAX) return -1;
     if (n == 2) run_mpc<2>(mode, batch, Nmax, N, xg, ug, x0, lbx, ubx, lbu, ubu, Wz, WzN, yref, yrefN, Tf, net, lh, uh, o, x, u, st, lamg, rows_soft, rowZ, rowm);
     else if (n == 3) run_mpc<3>(mode, batch, Nmax, N, xg, ug, x0, lbx, ubx, lbu, ubu, Wz, WzN, yref, yrefN, Tf, net, lh, uh, o, x, u, st, lamg, rows_soft, rowZ, rowm);

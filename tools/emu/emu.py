@@ -142,7 +142,7 @@ def solve_mpc(n, mode, bp, net, opts, multipliers=False, rowZ=None):
                            C.c_double(bp["Tf"]), int(w[0].shape[0]), *[_p(a) for a in w], C.c_double(float(net["b3"])),
                            C.c_double(net["mean"]), C.c_double(net["std"]), C.c_double(net["scale"]), C.c_double(bp["lh"]),
                            C.c_double(bp["uh"]), C.byref(opts), _p(x), _p(u), st, _p(lamg), int(rowZ is not None),
-                           _p(rowZ) if rowZ is not None else None, _p(rowm))
+                           _p(rowZ) if rowZ is not None else None, _p(rowm), int(net.get("vstart", -1)))
     assert rc == 0
     if multipliers:
         lib.emu_set_multiplier_out(None, None)

@@ -19,7 +19,7 @@ EXPORTS = (
     "vboc_default_opts", "vboc_create", "vboc_destroy", "vboc_set_opts", "vboc_set_stream",
     "vboc_solve_batch", "vboc_upload", "vboc_solve_resident", "vboc_solve_resident_async", "vboc_sync",
     "vboc_download", "vboc_last_kernel_ms", "vboc_export_multipliers", "vboc_download_multipliers",
-    "vboc_set_mpc", "vboc_set_mpc_reference", "vboc_download_mpc_multipliers", "vboc_set_mpc_rows", "vboc_download_mpc_rows", "vboc_set_cartesian", "vboc_set_guess_network", "vboc_download_guess",
+    "vboc_set_mpc", "vboc_set_mpc_reference", "vboc_download_mpc_multipliers", "vboc_set_mpc_rows", "vboc_download_mpc_rows", "vboc_set_cartesian", "vboc_set_mpc_velnorm_start", "vboc_set_guess_network", "vboc_download_guess",
     "vboc_stream_create", "vboc_stream_destroy", "vboc_stream_set_opts", "vboc_stream_free_slots",
     "vboc_stream_pending", "vboc_stream_submit", "vboc_stream_poll", "vboc_stream_fetch", "vboc_stream_sim_step",
     "vboc_datagen_create", "vboc_datagen_destroy", "vboc_datagen_set_opts", "vboc_datagen_run", "vboc_datagen_last_kernel_ms",
@@ -100,6 +100,7 @@ def lib():
         L.vboc_set_mpc_rows.argtypes = [vp, C.c_int, dp]
         L.vboc_download_mpc_rows.argtypes = [vp, dp]
         L.vboc_set_cartesian.argtypes = [vp, C.c_int] + [C.c_double] * 4
+        L.vboc_set_mpc_velnorm_start.argtypes = [vp, C.c_int]
         L.vboc_set_guess_network.argtypes = [vp, C.c_int, C.c_int] + [fp_] * 6 + [C.c_double, C.c_double]
         L.vboc_download_guess.argtypes = [vp, dp]
         L.vboc_export_multipliers.argtypes = [vp, C.c_int]

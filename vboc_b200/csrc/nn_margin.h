@@ -29,6 +29,9 @@ struct NnNet {
     const double *W3;   // [H]   (one output)
     double b3;
     double mean, stdv, scale;  // scale = (100 - safety_margin) / 100
+    // vel_norm = |x[vstart:]|.  n_dof for the double-pendulum classes; the triple-pendulum classes write `x[2:]` as well
+    // (VBOC/Safe MPC/triplependulum_class_vboc.py:217, 282), which includes theta_3: vstart = 2 mirrors them
+    int vstart;
 };
 
 // Guess network of the AL drivers (AL/triplependulum_class_al.py:171-201, `compute_problem_nnguess`): a 2n-H-H-(N 2n)
@@ -82,7 +85,8 @@ VB_DEV double nn_margin(const NnNet &net, const double *x, double *grad, double 
     const int H = net.hidden;
     double vn2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) vn2 += x[NQ + i] * x[NQ + i];
+    for (int i = 0; i < NX; ++i)
+        if (i >= net.vstart) vn2 += x[i] * x[i];
     const double vraw = sqrt(vn2);
     const bool clip = !(vraw > 1e-3);
     const double vn = clip ? 1e-3 : vraw;
@@ -143,21 +147,16 @@ VB_DEV double nn_margin(const NnNet &net, const double *x, double *grad, double 
         }
         // through the normalisation: in_q = (q - mean) / std ; in_v = v / vn ; h = scale * out - vn
         FOR_LANES
-        if (lane < NQ) {
-            grad[lane] = net.scale * gin[lane] / net.stdv;
-        } else if (lane < NX) {
-            const int i = lane - NQ;
-            double g;
-            if (clip) {
-                g = net.scale * gin[lane] / vn;  // vn is the constant 1e-3
-            } else {
+        if (lane < NX) {
+            double gd = lane < NQ ? net.scale * gin[lane] / net.stdv : net.scale * gin[lane] / vn;
+            if (!clip && lane >= net.vstart) {
+                // through vn = |x[vstart:]|: the velocity inputs v / vn and the -vn term
                 double dot = 0.0;                // sum_m gin_v[m] v_m
 #pragma unroll
                 for (int m = 0; m < NQ; ++m) dot += gin[NQ + m] * x[NQ + m];
-                g = net.scale * (gin[lane] / vn - dot * x[lane] / (vn * vn * vn)) - x[lane] / vn;
-                (void)i;
+                gd -= (net.scale * dot / (vn * vn) + 1.0) * x[lane] / vn;
             }
-            grad[lane] = g;
+            grad[lane] = gd;
         }
         END_LANES
     }

@@ -937,6 +937,7 @@ int vboc_set_mpc(vboc_solver *s, int hidden, const float *W1, const float *b1, c
     s->nn.n_in = nx, s->nn.hidden = H, s->nn.W1 = s->dnn, s->nn.b1 = s->dnn + o_b1, s->nn.W2 = s->dnn + o_W2;
     s->nn.W2T = s->dnn + o_W2T, s->nn.b2 = s->dnn + o_b2, s->nn.W3 = s->dnn + o_W3, s->nn.b3 = b3[0];
     s->nn.mean = mean, s->nn.stdv = stdv, s->nn.scale = (100.0 - safety_margin) / 100.0;
+    s->nn.vstart = s->n;  // vel_norm over the velocities (vboc_set_mpc_velnorm_start changes it)
     s->mpc_lh = lh, s->mpc_uh = uh;
     // weights arrive in acados' y = [x; u] order (cost.W = blkdiag(Q, R)); the engine orders z = [u; x]
     std::vector<double> wz(nz), wzN(nx);
@@ -970,6 +971,13 @@ int vboc_set_mpc_reference(vboc_solver *s, int batch, const double *yref, const 
     if ((rc = h2d(s, s->dyref, yz.data(), yz.size() * sizeof(double)))) return rc;
     if ((rc = h2d(s, s->dyrefN, yref_e, (size_t)batch * nx * sizeof(double)))) return rc;
     s->mpc_ref_batch = batch;
+    return 0;
+}
+
+int vboc_set_mpc_velnorm_start(vboc_solver *s, int vstart) {
+    if (!s || s->family != VBOC_FAMILY_MPC || !s->mpc_set) return fail(VBOC_ERR_ARG, "vboc_set_mpc_velnorm_start: call vboc_set_mpc first");
+    if (vstart < 0 || vstart > s->n) return fail(VBOC_ERR_ARG, "vboc_set_mpc_velnorm_start: 0 <= vstart <= n_dof");
+    s->nn.vstart = vstart;
     return 0;
 }
 

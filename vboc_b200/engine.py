@@ -104,7 +104,7 @@ class BatchSolver:
         return self._result(x, u, st)
 
     # -- MPC family ------------------------------------------------------------
-    def set_mpc(self, net, mean, std, safety_margin, W, W_e, lh=0.0, uh=1e6):
+    def set_mpc(self, net, mean, std, safety_margin, W, W_e, lh=0.0, uh=1e6, vstart=None):
         """The margin network (a torch module with `linear_relu_stack`, or a dict of W1, b1, W2, b2, W3, b3 arrays in
         nn.Linear layout), its normalisation, the constraint's bounds and the diagonals of cost.W ([x; u] order) /
         cost.W_e."""
@@ -120,6 +120,8 @@ class BatchSolver:
         fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
         check(_lib.lib().vboc_set_mpc(self._h, H, *[fp(a) for a in w], float(mean), float(std), float(safety_margin),
                                       float(lh), float(uh), _dp(_c(W)), _dp(_c(W_e))))
+        if vstart is not None:   # vel_norm = |x[vstart:]| (the triple-pendulum classes' x[2:])
+            check(_lib.lib().vboc_set_mpc_velnorm_start(self._h, int(vstart)))
 
     def set_mpc_reference(self, yref, yref_e):
         yref, yref_e = _c(np.atleast_2d(yref)), _c(np.atleast_2d(yref_e))

@@ -90,18 +90,19 @@ class _MpcSolverShim:
             if self._sol is None:
                 self._sol = engine.BatchSolver(o.nu, "mpc", 1, o.N)
             self._sol.set_mpc(dict(zip(("W1", "b1", "W2", "b2", "W3", "b3"), o._params)), o._mean, o._std, o._margin_pct,
-                              o._W, o._W_e, lh=0.0, uh=1e6)
+                              o._W, o._W_e, lh=getattr(o, "_lh", 0.0), uh=1e6, vstart=getattr(o, "_vstart", None))
             self._sol_dirty = False
         self._sol.set_opts(o.opts)
         self._sol.set_mpc_reference(self.yref[0], self.yref_e)
         if o.SOFT_ROWS:
             self._sol.set_mpc_rows(self.Zl[None, :])
         one = lambda a: np.ascontiguousarray(np.asarray(a, dtype=float)[None])
-        lo = np.concatenate([[o.thetamin] * 2, [-o.dthetamax] * 2])
-        hi = np.concatenate([[o.thetamax] * 2, [o.dthetamax] * 2])
-        bp = dict(n=2, family="mpc", N=np.array([o.N], dtype=np.int32), Tf=o.Tf, x_guess=one(self.x), u_guess=one(self.u),
+        nq = o.nu
+        lo = np.concatenate([[o.thetamin] * nq, [-o.dthetamax] * nq])
+        hi = np.concatenate([[o.thetamax] * nq, [o.dthetamax] * nq])
+        bp = dict(n=nq, family="mpc", N=np.array([o.N], dtype=np.int32), Tf=o.Tf, x_guess=one(self.x), u_guess=one(self.u),
                   p=None, C0=None, lbx0=one(self.x0), ubx0=one(self.x0), lbx=one(lo), ubx=one(hi), lbxN=one(lo),
-                  ubxN=one(hi), lbu=one([-o.Cmax] * 2), ubu=one([o.Cmax] * 2))
+                  ubxN=one(hi), lbu=one([-o.Cmax] * nq), ubu=one([o.Cmax] * nq))
         self._out = self._sol.solve(bp, MODE_RTI if o.ocp.solver_options.nlp_solver_type == "SQP_RTI" else MODE_SQP)
         self.x[:] = self._out["x"][0, :o.N + 1]
         self.u[:] = self._out["u"][0, :o.N]

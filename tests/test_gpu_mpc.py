@@ -18,7 +18,10 @@ from test_mpc_family import make_net  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-def _solve(n, bp, net, mode, tol=1e-2, qp_tol=1e-9):
+# QP tolerance 1e-8 (HPIPM's default): with a strongly active row (multiplier ~1e4, slack ~1e-14) the Newton systems are
+# conditioned ~1e17 and 1e-9 on the stationarity residual is at the rounding floor of FP64 -- an IPM asked for it wanders
+# after reaching ~3e-9 (the iteration limit is then hit and, as in acados, tolerated).
+def _solve(n, bp, net, mode, tol=1e-2, qp_tol=1e-8):
     from vboc_b200 import engine
     B = len(bp["N"])
     sol = engine.BatchSolver(n, "mpc", B, int(bp["x_guess"].shape[1] - 1))
@@ -110,7 +113,7 @@ def test_safe_mpc_class_like_the_driver():
 
 # ---------------------------------------------------------------------------------------------------------------
 # soft rows (vboc_set_mpc_rows): the parallel / receiding_hard_constraints / soft_traj_constraints variants
-def _solve_rows(n, bp, net, mode, Z, tol=1e-2, qp_tol=1e-9):
+def _solve_rows(n, bp, net, mode, Z, tol=1e-2, qp_tol=1e-8):
     from vboc_b200 import engine
     B = len(bp["N"])
     sol = engine.BatchSolver(n, "mpc", B, int(bp["x_guess"].shape[1] - 1))

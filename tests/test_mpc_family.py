@@ -32,7 +32,7 @@ def make_net(n, H, seed, b3):
                 W3=f32(rng.normal(size=H) / np.sqrt(H)), b3=b3, mean=np.pi, std=0.45, scale=1.0)
 
 
-def mpc_opts(emu, qp_tol=1e-9, tol=1e-2):
+def mpc_opts(emu, qp_tol=1e-8, tol=1e-2):
     o = emu.Opts()
     o.tol_stat = o.tol_eq = o.tol_ineq = o.tol_comp = tol
     o.max_iter, o.levenberg_marquardt = 1000, 1.0

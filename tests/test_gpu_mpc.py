@@ -56,7 +56,8 @@ def test_rti_step_is_the_qp_solution(n, H):
     for b in ok:
         r = certify.mpc_kkt(n, bp, net, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["lamg"][b], 1.0,
                             first_qp_at_guess=True)
-        assert max(r["res_stat"], r["res_eq"], r["res_ineq"], r["res_comp"]) < 1e-7 and r["lam_min"] >= 0.0, (b, r)
+        sc = max(1.0, float(out["lamg"][b].max()))   # the QP's stationarity test is relative to the row multiplier
+        assert max(r["res_stat"] / sc, r["res_eq"], r["res_ineq"], r["res_comp"]) < 1e-7 and r["lam_min"] >= 0.0, (b, r)
         active += out["lamg"][b, 0] > 1e-3
     assert active >= 10
 

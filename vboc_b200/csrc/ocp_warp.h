@@ -822,12 +822,13 @@ struct WarpSolver {
         LV(double, a_m);
         LV(double, a_mu);
         LV(int, bad);
+        LV(double, a_lm);  // ROWS: largest row multiplier (scale of the stationarity test, see below)
         if constexpr (ROWS) {
             // the rows first (lanes over the stages): their updated multipliers enter the stationarity residual of x_k in
             // the flat loop below, their barrier terms (slacks eliminated) the stage Hessian of the
             // backward sweep.  One-sided constraints of a row: 0 lower, 1 upper, 2 sl >= 0, 3 su >= 0.
             FOR_LANES
-            double vg = 0, vd = 0, vm = 0, mu = 0;
+            double vg = 0, vd = 0, vm = 0, mu = 0, lmx = 0;
             int nb = 0;
             const int nsd = g->soft ? 4 : 2;
             for (int k = N - lane; k >= 0; k -= 32) {  // lane 0 takes the terminal row (summation order of the hard-row kernel)
@@ -872,6 +873,7 @@ struct WarpSolver {
                         nb |= (rd[sd] != rd[sd]) | (m_ != m_);
                         vd = fmax(vd, fabs(rd[sd])), vm = fmax(vm, fabs(m_)), mu += m_;
                         rw[RowF::LQ + sd] = lam[sd], rw[RowF::TQ + sd] = t[sd], rw[RowF::RD + sd] = rd[sd];
+                        lmx = fmax(lmx, lam[sd]);
                     }
                 }
                 double a1 = 1.0, a2 = 1.0, c3 = 0.0, c4 = 0.0, rsl = 0.0, rsu = 0.0;
@@ -888,7 +890,7 @@ struct WarpSolver {
                 rw[RowF::WEFF] = wv[0] * a1 + wv[1] * a2;
                 rw[RowF::BARG] = (a1 * beta[0] - c3 * (rsl + beta[2])) - (a2 * beta[1] - c4 * (rsu + beta[3]));
             }
-            L(a_g) = vg, L(a_d) = vd, L(a_m) = vm, L(a_mu) = mu, L(bad) = nb;
+            L(a_g) = vg, L(a_d) = vd, L(a_m) = vm, L(a_mu) = mu, L(bad) = nb, L(a_lm) = lmx;
             END_LANES
         }
         FOR_LANES
@@ -1064,6 +1066,13 @@ struct WarpSolver {
         }
         END_LANES
         ng = WARP_MAX(a_g), nb_ = WARP_MAX(a_b), nd = WARP_MAX(a_d), nm = WARP_MAX(a_m);
+        if constexpr (ROWS) {
+            // Stationarity is tested RELATIVE to the largest row multiplier: with a strongly active row (multiplier ~1e4,
+            // or Zl sl ~ 1e6 ... 1e12 for a penalised slack) the residual is a difference of numbers of that size, and the
+            // barrier weight lam / t of the row conditions the Newton systems ~1e17 near the solution -- an absolute
+            // 1e-8 is then below the rounding floor of FP64 and an IPM asked for it wanders off again after reaching it.
+            ng /= fmax(1.0, WARP_MAX(a_lm));
+        }
         double mu = WARP_SUM(a_mu);
         nan = WARP_ANY(bad);
         FOR_LANES

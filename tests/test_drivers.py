@@ -142,3 +142,21 @@ def test_stream_event_loop_equals_rounds(oracle, backend):
     c = drivers.testing_batch(n, 4, seed=2, backend=backend(n))
     d = drivers.testing_stream(n, 4, seed=2, ssol=FakeStream(oracle, n, slots=2))
     assert np.array_equal(c, d)
+
+
+def test_generic_vboc_worker_ends_on_a_failed_solve():
+    """`VBOC/vboc.py:162-213`: the generic driver has its restart block commented out -- a failed solve ends the problem --
+    while the per-system drivers restart with a perturbed direction and positions (`VBOC/triplependulum_vboc.py:138-174`)."""
+    from types import SimpleNamespace
+    n = 2
+    failed = SimpleNamespace(status=4, cost=0.0, x=None, u=None)
+    g = drivers.data_generation_worker(n, drivers._rng(1, 0), restarts=False)
+    first = next(g)
+    with pytest.raises(StopIteration) as stop:
+        g.send(failed)
+    assert stop.value.value is None
+    g = drivers.data_generation_worker(n, drivers._rng(1, 0))
+    first2 = next(g)
+    again = g.send(failed)                  # the per-system worker asks for another solve ...
+    assert np.array_equal(first.p, first2.p) and again.N == first2.N
+    assert not np.array_equal(again.p, first2.p) and abs(np.linalg.norm(again.p[:n]) - 1.0) < 1e-12   # ... of a perturbed problem

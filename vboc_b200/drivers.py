@@ -338,10 +338,16 @@ def dg_inputs(n, num_prob, seed, first=0, dt_sym=1e-2, tol=1e-3):
     return out
 
 
-def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
+def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3, restarts=True):
     """One VBOC problem: an extreme trajectory from a position limit of a randomly selected joint, then the
     walk along it that classifies every state (on the boundary of the viability kernel, on a state limit,
-    or inside) with sub-OCPs and the simulated unviable twin.  Returns the list of saved rows [q, v] or None."""
+    or inside) with sub-OCPs and the simulated unviable twin.  Returns the list of saved rows [q, v] or None.
+
+    The worker is written for any n; with restarts=False it is the generic `VBOC/vboc.py:23-402` (`system_sel` = n):
+    there the restart after a failed solve is commented out (`:162-213`: a failed solve ends the problem), everything
+    else is the per-system scripts' logic written as loops over `system_sel`.  Its velocity test of the walk indexes
+    rows instead of columns (`x_sol[system_sel:nx-1]`, `:251`, raises on an array truth value); the per-system scripts'
+    test is used.  The unseeded draws differ only in their order."""
     mdl = pr.Model(n)
     eps = 10 * tol
     q_min, q_max, v_max = mdl.thetamin, mdl.thetamax, mdl.dthetamax
@@ -378,6 +384,8 @@ def data_generation_worker(n, rng, N0=100, dt_sym=1e-2, tol=1e-3):
             cost = ans.cost
             xg, ug = _extended_guess(ans, n)
             N += 1
+        elif not restarts:
+            return None
         else:
             N = N0
             dp, dev = _dg_retry(n, rng)
@@ -548,11 +556,11 @@ def testing_batch(n, num_prob, seed, device=0, backend=None, stats=None):
     return np.array([r for r in res if r is not None]).reshape(-1, 2 * n)
 
 
-def data_generation_batch(n, num_prob, seed, device=0, backend=None, stats=None):
+def data_generation_batch(n, num_prob, seed, device=0, backend=None, stats=None, restarts=True):
     """`Pool.map(data_generation, range(num_prob))` + the flattening of `traj`
-    (VBOC/triplependulum_vboc.py:399-405) -> X_save (rows [q, v])."""
+    (VBOC/triplependulum_vboc.py:399-405) -> X_save (rows [q, v]).  restarts=False: the generic `VBOC/vboc.py` worker."""
     solver, sim = backend or _gpu_backend(n, num_prob, device)
-    res = run_workers(n, [data_generation_worker(n, _rng(seed, i)) for i in range(num_prob)], solver, sim, stats)
+    res = run_workers(n, [data_generation_worker(n, _rng(seed, i), restarts=restarts) for i in range(num_prob)], solver, sim, stats)
     rows = [np.asarray(r) for r in res if r is not None and len(r)]
     if stats is not None:
         stats["problems"] = num_prob
@@ -575,11 +583,11 @@ def testing_stream(n, num_prob, seed, device=0, ssol=None, stats=None):
     return np.array([r for r in res if r is not None]).reshape(-1, 2 * n)
 
 
-def data_generation_stream(n, num_prob, seed, device=0, ssol=None, stats=None):
+def data_generation_stream(n, num_prob, seed, device=0, ssol=None, stats=None, restarts=True):
     """`data_generation_batch` through the streaming engine (no round barrier): same workers, same rows."""
     own = ssol is None
     ssol = ssol or _stream_backend(n, num_prob, device)
-    res = run_workers_stream(n, [data_generation_worker(n, _rng(seed, i)) for i in range(num_prob)], ssol, stats)
+    res = run_workers_stream(n, [data_generation_worker(n, _rng(seed, i), restarts=restarts) for i in range(num_prob)], ssol, stats)
     if own:
         ssol.close()
     rows = [np.asarray(r) for r in res if r is not None and len(r)]

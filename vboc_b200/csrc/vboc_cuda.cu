@@ -49,6 +49,15 @@ int fail(int code, const std::string &msg) {
 constexpr int VBOC_N_MAX = 128;
 static_assert(VBOC_N_MAX + 1 <= (int)Work<3>::SMAX && VBOC_N_MAX + 1 <= (int)LaneLayout<3>::SMAX, "workspace stages");
 constexpr int WARPS_PER_CTA = VB_WARPS_PER_CTA;  // tuning builds may change the CTA shape
+// The batch solve kernel runs the same 20 warps per SM as 2-warp CTAs (10 per SM): a persistent CTA frees its registers
+// and shared memory only when ALL its warps have run out of work, and a warp that holds a problem of several hundred SQP
+// iterations keeps its CTA's idle warps' slots from the next launch for seconds.  Measured on the bench (4 steps on 4
+// streams): 4 / 2 / 1 warps per CTA = 3.51 / 3.59 / 3.42 k OCP/s (steady state 3.61 / 3.61 / 3.40 M IPM iterations/s).
+#ifndef VB_SOLVE_WARPS
+#define VB_SOLVE_WARPS (VB_WARPS_PER_CTA < 2 ? VB_WARPS_PER_CTA : 2)
+#endif
+constexpr int SOLVE_WARPS = VB_SOLVE_WARPS;
+static_assert(WARPS_PER_CTA % SOLVE_WARPS == 0, "CTA shapes");
 #ifdef VB_TUNE_MINB
 #define VB_LB_MINB(m) VB_TUNE_MINB
 #else
@@ -92,10 +101,12 @@ struct Batch {
 };
 
 template <int NQ, int FAM, int MINB, bool STREAM = false>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, VB_LB_MINB(MINB)) solve_kernel(const Batch B) {
-    __shared__ Smem<NQ> smem[WARPS_PER_CTA];
+__global__ void __launch_bounds__((STREAM ? WARPS_PER_CTA : SOLVE_WARPS) * 32,
+                                  VB_LB_MINB(MINB) * (STREAM ? 1 : WARPS_PER_CTA / SOLVE_WARPS)) solve_kernel(const Batch B) {
+    constexpr int W = STREAM ? WARPS_PER_CTA : SOLVE_WARPS;  // warps of this CTA (MINB counts 4-warp CTAs' worth of registers)
+    __shared__ Smem<NQ> smem[W];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int slot = blockIdx.x * WARPS_PER_CTA + warp;
+    int slot = blockIdx.x * W + warp;
     unsigned int *ws_word = nullptr;
     unsigned int ws_bit = 0;
     if constexpr (STREAM) {
@@ -452,12 +463,12 @@ static cudaError_t launch(vboc_solver *s, const Batch &B) {
         return cudaGetLastError();
     }
     if (s->ctas_per_sm >= 6)
-        solve_kernel<NQ, FAM, 6><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+        solve_kernel<NQ, FAM, 6><<<s->grid, SOLVE_WARPS * 32, 0, s->stream>>>(B);
     else if (s->ctas_per_sm == 4)
-        solve_kernel<NQ, FAM, 4><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+        solve_kernel<NQ, FAM, 4><<<s->grid, SOLVE_WARPS * 32, 0, s->stream>>>(B);
     else
 #endif
-        solve_kernel<NQ, FAM, 5><<<s->grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
+        solve_kernel<NQ, FAM, 5><<<s->grid, SOLVE_WARPS * 32, 0, s->stream>>>(B);
     return cudaGetLastError();
 }
 
@@ -586,10 +597,12 @@ static int solver_create_impl(vboc_solver *s, int n_dof, int family, int batch_c
     ctas_per_sm = VB_TUNE_CTAS;
 #endif
     s->ctas_per_sm = ctas_per_sm;
-    int max_grid = prop.multiProcessorCount * ctas_per_sm;
-    int need = (batch_capacity + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    s->grid = need < max_grid ? need : max_grid;
-    s->slots = s->grid * WARPS_PER_CTA;
+    // warp slots resident at once (ctas_per_sm counts 4-warp CTAs), a multiple of WARPS_PER_CTA; the batch solve kernel
+    // runs them as CTAs of SOLVE_WARPS warps, the row-family kernels as CTAs of WARPS_PER_CTA
+    int max_slots = prop.multiProcessorCount * ctas_per_sm * WARPS_PER_CTA;
+    int need = (batch_capacity + WARPS_PER_CTA - 1) / WARPS_PER_CTA * WARPS_PER_CTA;
+    s->slots = need < max_slots ? need : max_slots;
+    s->grid = s->slots / SOLVE_WARPS;
     s->work_doubles = work_doubles_for(n_dof, N_max);
     if (family == VBOC_FAMILY_MPC)  // + the row records of the margin constraint
         s->work_doubles = n_dof == 2 ? Work<2>::doubles_rows(N_max) : Work<3>::doubles_rows(N_max);
@@ -849,8 +862,8 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
         if (s->rows_soft && s->rows_batch < s->batch)
             return fail(VBOC_ERR_ARG, "vboc_solve_resident: call vboc_set_mpc_rows for this batch (soft rows are on)");
         B.rows_soft = s->rows_soft, B.rowZ = s->rows_soft ? s->drowZ : nullptr, B.rowm_out = s->drowm;
-        const int g4 = (s->batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        const int grid = g4 < s->grid ? g4 : s->grid;
+        const int g4 = (s->batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA, gmax = s->slots / WARPS_PER_CTA;
+        const int grid = g4 < gmax ? g4 : gmax;
         if (s->n == 2) solve_rows_kernel<2, VBOC_FAMILY_MPC><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
         else solve_rows_kernel<3, VBOC_FAMILY_MPC><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
         e = cudaGetLastError();
@@ -859,8 +872,8 @@ int vboc_solve_resident_async(vboc_solver *s, int mode) {
 #ifndef VB_TUNE_BUILD
         if (s->free_dt || s->lane_kernel) return fail(VBOC_ERR_UNSUPPORTED, "Cartesian constraint: warp kernel, pinned dt only");
         B.lh = s->mpc_lh, B.uh = s->mpc_uh, B.cart_xc = s->cart_xc, B.cart_yc = s->cart_yc, B.rowm_out = s->drowm;
-        const int g4 = (s->batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        const int grid = g4 < s->grid ? g4 : s->grid;
+        const int g4 = (s->batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA, gmax = s->slots / WARPS_PER_CTA;
+        const int grid = g4 < gmax ? g4 : gmax;
         solve_rows_kernel<2, VBOC_FAMILY_CART><<<grid, WARPS_PER_CTA * 32, 0, s->stream>>>(B);
         e = cudaGetLastError();
 #endif

@@ -468,7 +468,12 @@ static cudaError_t launch(vboc_solver *s, const Batch &B) {
         solve_kernel<NQ, FAM, 4><<<s->grid, SOLVE_WARPS * 32, 0, s->stream>>>(B);
     else
 #endif
+    {
+#ifdef VB_TUNE_CARVEOUT  // tuning builds: shared-memory carve-out preference in percent of the SM's 228 KB
+        cudaFuncSetAttribute(solve_kernel<NQ, FAM, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, VB_TUNE_CARVEOUT);
+#endif
         solve_kernel<NQ, FAM, 5><<<s->grid, SOLVE_WARPS * 32, 0, s->stream>>>(B);
+    }
     return cudaGetLastError();
 }
 

@@ -39,8 +39,9 @@ extern "C" {
 
 #define VBOC_FAMILY_VBOC 0 /* VBOC/ *_class_vboc.py: linear cost, dt state, stage-0 direction constraint */
 #define VBOC_FAMILY_AL 1   /* AL/ *_class_al.py: LINEAR_LS cost on velocities, x0 fixed             */
-#define VBOC_FAMILY_MPC 2  /* VBOC/Safe MPC/ *_class_fixedveldir.py: LINEAR_LS tracking cost, x0 fixed, the learned
-                              viability margin h(x_N) >= 0 as a nonlinear terminal constraint (vboc_set_mpc) */
+#define VBOC_FAMILY_MPC 2  /* VBOC/Safe MPC/ *_class_fixedveldir.py, triplependulum_class_vboc.py: LINEAR_LS tracking cost,
+                              x0 fixed, the learned viability margin h(x) >= 0 as a hard terminal constraint (vboc_set_mpc)
+                              or softened at every stage (vboc_set_mpc_rows) */
 
 #define VBOC_MODE_SQP 0 /* nlp_solver_type "SQP"     */
 #define VBOC_MODE_RTI 1 /* nlp_solver_type "SQP_RTI" */

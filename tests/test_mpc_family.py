@@ -203,3 +203,24 @@ def test_triple_pendulum_velnorm_over_x2(emu):
         x = np.concatenate([rng.uniform(2.4, 3.9, 3), rng.uniform(-8, 8, 3)])
         want = certify.nn_margin(dict(net, scale=0.95), x, 3)
         assert abs(ocp.nn_decisionfunction_conservative(params, net["mean"], net["std"], 5.0, x) - want) < 1e-12
+
+
+def test_soft_rows_with_shorter_horizons_in_a_larger_buffer(emu):
+    """N < N_max: the penalties of problem b, stage k are Z[b, k] with the N_max + 1 row stride of the C-ABI
+    (vboc_set_mpc_rows), rows beyond N are ignored; the certificate runs on the first N + 1 stages."""
+    n, B, Nmax = 2, 12, 10
+    net = make_net(n, 64, n, 4.0)
+    bp = pr.sample_mpc(n, B, seed=5, N=Nmax)
+    bp["N"] = np.array([6, 10, 8] * 4, dtype=np.int32)
+    Z = np.zeros((B, Nmax + 1, 4))
+    Z[:, :, 0] = 1e6
+    for b in range(B):
+        Z[b, bp["N"][b] + 1:, 0] = np.nan          # must never be read
+    out = emu.solve_mpc(n, 1, bp, net, mpc_opts(emu), multipliers=True, rowZ=np.nan_to_num(Z, nan=-7.0))
+    ok = np.where(out["status"] == 0)[0]
+    assert len(ok) >= 10
+    for b in ok:
+        r = certify.mpc_rows_kkt(n, bp, net, b, out["x"][b], out["u"][b], out["pi"][b], out["lam"][b], out["rowm"][b],
+                                 np.nan_to_num(Z[b], nan=0.0), 1.0, first_qp_at_guess=True)
+        rel, feas = _rel(r, out["rowm"][b, :bp["N"][b] + 1])
+        assert rel < 2e-6 and feas < 2e-6, (b, r)

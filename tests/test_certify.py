@@ -98,3 +98,23 @@ def test_al_labels_equal_lp_feasibility(oracle, emu):
     feas = np.array([certify.al_lp_feasible(n, bp["lbx0"][b, :2 * n])[0] for b in range(24)])
     assert lab.any() and (~lab).any()
     assert (lab == feas).all()
+
+
+def test_free_dt_solutions_are_kkt_points_with_recovered_multipliers(oracle, emu):
+    """configs[0] (1-DOF, dt a free state, VBOC/pendulum_vboc.py): the lane kernel exports no multipliers, so the
+    certificate recovers them by bounded least squares from the returned iterate (free sign for the equalities, >= 0 for
+    the bounds that are active) -- the point is a KKT point iff the remaining stationarity residual is below tolerance.
+    Negative control: the same point is NOT a KKT point of the problem with the opposite velocity cost."""
+    bp = pr.pendulum_free_dt_problems(10, seed=3)
+    out = emu.solve_batch(1, 0, 0, bp, _opts(emu, oracle.default_opts(0)), "lane_dts")
+    ok = np.where(out["status"] == 0)[0]
+    assert len(ok) >= 8
+    for b in ok:
+        r = certify.free_dt_kkt(bp, b, out["x"][b], out["u"][b])
+        assert r["res_stat"] < 1e-3 and r["res_eq"] < 1e-6 and r["res_ineq"] < 1e-6 and r["lam_min"] >= 0.0, (b, r)
+        assert r["n_active"] >= 40                      # bang-bang: the force bound is active almost everywhere
+    wrong = dict(bp)
+    wrong["p"] = bp["p"].copy()
+    wrong["p"][:, 0] *= -1.0
+    for b in ok[:4]:
+        assert certify.free_dt_kkt(wrong, b, out["x"][b], out["u"][b])["res_stat"] > 1e-2

@@ -177,3 +177,10 @@ def test_pendulum_free_dt_matches_oracle(oracle):
     assert ok.mean() > 0.8
     assert np.abs(ref["x"] - out["x"])[ok].max() < TOL_X_LOOSE
     assert np.abs(ref["cost"] - out["cost"])[ok].max() < TOL_X_LOOSE
+    # ... and without the oracle: every returned point is a KKT point with multipliers recovered by bounded least squares
+    # (tools/certify.py::free_dt_kkt; the lane kernel exports none)
+    import tools_path  # noqa: F401
+    import certify
+    for b in np.where(out["status"] == 0)[0]:
+        r = certify.free_dt_kkt(bp, b, out["x"][b], out["u"][b])
+        assert r["res_stat"] < 1e-3 and r["res_eq"] < 1e-6 and r["res_ineq"] < 1e-6 and r["lam_min"] >= 0.0, (b, r)

@@ -177,6 +177,84 @@ def passes_exit_test(res, tol_stat=1e-3, tol=1e-6):
             & (res["lam_min"] > -1e-12))
 
 
+# ------------------------------------------------------------------------------------------------ 1-DOF, free dt
+def free_dt_kkt(bp, b, x, u, act_tol=1e-5):
+    """Certificate for the 1-DOF VBOC OCP with a FREE dt state (configs[0], VBOC/pendulum_class_vboc.py:60-124,
+    VBOC/pendulum_vboc.py:63-130) WITHOUT multipliers from the engine (the lane kernel does not export them): they are
+    recovered by bounded least squares from the returned iterate -- free-sign multipliers for the shooting equalities and
+    the components fixed by lb == ub, non-negative ones for the bounds that are active to `act_tol` -- so that
+    complementarity holds by construction and the remaining stationarity residual decides whether the point is a KKT
+    point.  NLP: states (theta, dtheta, dt), control F; x+ = RK4 of dt * [dtheta; a; 0] over a unit step (one step of the
+    unscaled model with h = dt, dt+ = dt); cost p[0] dtheta_0 + p[1] sum_{k<N} dt_k (EXTERNAL, :73-75).
+    Returns dict(res_stat, res_eq, res_ineq, n_active, lam_min)."""
+    from scipy.optimize import lsq_linear
+    N = int(bp["N"][b])
+    X, U, p = x[:N + 1, :3], u[:N, :1], np.asarray(bp["p"][b], dtype=float)
+
+    def step(xk, uk):           # complex-step safe
+        q, v, dt = xk[0:1], xk[1:2], xk[2]
+        nxt = rk4(1, np.concatenate([q, v]), uk, dt)
+        return np.concatenate([nxt, [dt]])
+
+    nz = 4                      # z_k = [u_k; theta_k; dtheta_k; dt_k], no u_N
+    eps = 1e-30
+    Jk, gap = [], np.zeros((N, 3))
+    for k in range(N):
+        z = np.concatenate([U[k], X[k]])
+        J = np.zeros((3, nz))
+        for j in range(nz):
+            zc = z.astype(complex)
+            zc[j] += 1j * eps
+            J[:, j] = step(zc[1:], zc[:1]).imag / eps
+        Jk.append(J)
+        gap[k] = step(X[k], U[k]).real - X[k + 1]
+    res_eq = np.abs(gap).max()
+    lb = np.stack([np.concatenate([bp["lbu"][b], bp["lbx0"][b]])] + [np.concatenate([bp["lbu"][b], bp["lbx"][b]])] * (N - 1)
+                  + [np.concatenate([bp["lbu"][b], bp["lbxN"][b]])])
+    ub = np.stack([np.concatenate([bp["ubu"][b], bp["ubx0"][b]])] + [np.concatenate([bp["ubu"][b], bp["ubx"][b]])] * (N - 1)
+                  + [np.concatenate([bp["ubu"][b], bp["ubxN"][b]])])
+    Z = np.concatenate([np.concatenate([U, np.zeros((1, 1))]), X], axis=1)
+    exists = np.ones((N + 1, nz), dtype=bool)
+    exists[N, 0] = False
+    res_ineq = float(np.where(exists, np.maximum(np.maximum(lb - Z, Z - ub), 0.0), 0.0).max())
+    g = np.zeros((N + 1, nz))
+    g[0, 2] = p[0]
+    g[:N, 3] += p[1]
+    # unknowns: pi (N x 3, free), then one multiplier per (stage, component, side) that is fixed (free sign) or active (>= 0)
+    cols, lo = [], []
+    nvar = 3 * N
+    idx = lambda k, i: k * nz + i
+    rows = (N + 1) * nz
+    A = np.zeros((rows, nvar))
+    for k in range(N):
+        for m in range(3):
+            A[idx(k, 0):idx(k, 0) + nz, 3 * k + m] += Jk[k][m]          # + J_k' pi_k on z_k
+            A[idx(k + 1, 1 + m), 3 * k + m] -= 1.0                       # - pi_k on x_{k+1}
+    extra, extra_lo = [], []
+    for k in range(N + 1):
+        for i in range(nz):
+            if not exists[k, i]:
+                continue
+            if lb[k, i] == ub[k, i]:
+                c = np.zeros(rows); c[idx(k, i)] = 1.0
+                extra.append(c); extra_lo.append(-np.inf)
+            else:
+                if Z[k, i] - lb[k, i] < act_tol:
+                    c = np.zeros(rows); c[idx(k, i)] = -1.0              # lam_l (lb - z)
+                    extra.append(c); extra_lo.append(0.0)
+                if ub[k, i] - Z[k, i] < act_tol:
+                    c = np.zeros(rows); c[idx(k, i)] = 1.0               # lam_u (z - ub)
+                    extra.append(c); extra_lo.append(0.0)
+    Afull = np.concatenate([A, np.stack(extra, axis=1)], axis=1) if extra else A
+    keep = exists.reshape(-1)
+    lo_b = np.concatenate([np.full(nvar, -np.inf), np.array(extra_lo)])
+    sol = lsq_linear(Afull[keep], -g.reshape(-1)[keep], bounds=(lo_b, np.full(lo_b.shape, np.inf)), tol=1e-14, max_iter=2000)
+    r = Afull[keep] @ sol.x + g.reshape(-1)[keep]
+    lam = sol.x[nvar:][np.array(extra_lo) == 0.0] if extra else np.zeros(0)
+    return dict(res_stat=float(np.abs(r).max()), res_eq=float(res_eq), res_ineq=res_ineq, n_active=int((np.array(extra_lo) == 0.0).sum()),
+                lam_min=float(lam.min()) if lam.size else 0.0)
+
+
 # ------------------------------------------------------------------------------------------------ AL labels
 def al_lp_feasible(n, x0, N=100, Tf=1.0, x_guess=None, u_guess=None):
     """Feasibility of the QP the AL classes hand to HPIPM in their single SQP_RTI step

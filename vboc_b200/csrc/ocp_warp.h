@@ -189,6 +189,10 @@ VB_HD double dotv(const double *a, const double *b, double init = 0.0) {
 #ifndef VB_RECOMPUTE_STEP
 #define VB_RECOMPUTE_STEP 1  // slack / multiplier steps recomputed inside the fused update: DT / DLAM never written (+0.9 %)
 #endif
+#ifndef VB_FLAT_UNROLL
+#define VB_FLAT_UNROLL 1  // unroll factor of the three flat passes of the IPM (tuning: 2 needs ~128 registers)
+#endif
+constexpr int FLAT_UNROLL = VB_FLAT_UNROLL;
 #ifndef VB_PF_DIST
 #define VB_PF_DIST 64  // software prefetch distance of the flat passes: two lane-strided iterations ahead
 #endif
@@ -897,6 +901,7 @@ struct WarpSolver {
         double vg = 0, vd = 0, vm = 0, mu = 0;
         int nb = 0;
         if constexpr (ROWS) vg = L(a_g), vd = L(a_d), vm = L(a_m), mu = L(a_mu), nb = L(bad);
+#pragma unroll FLAT_UNROLL
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             {
@@ -1621,6 +1626,7 @@ struct WarpSolver {
                 if (mode == 0) rw[RowF::Q1G] = q1g, rw[RowF::Q2G] = q2g;
             }
         }
+#pragma unroll FLAT_UNROLL
         for (int idx = lane; idx < (N + 1) * NZ; idx += 32) {
             int k = idx / NZ, i = idx - k * NZ;
             double *rk = rec(k);
@@ -1758,6 +1764,7 @@ struct WarpSolver {
             // value functions; z, lam, t are stepped inside the next residual pass (qp_residuals(.., upd, as))
             upd = true, as_prev = as;
             FOR_LANES
+#pragma unroll FLAT_UNROLL
             for (int idx = lane; idx < N * NX; idx += 32) {
                 int k = idx / NX, mI = idx - k * NX;
                 const double *dxn = w.DV + (size_t)(k + 1) * NZ + NU;
